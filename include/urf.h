@@ -1,0 +1,173 @@
+/*
+ * urf.h — C-ABI of liburf_b200.so: the B200-native replacement for the per-scan road/curb classification path of
+ * jkk-research/urban_road_filter.
+ *
+ * Reference interface replaced (all paths relative to the reference repo root):
+ *   - void Detector::filtered(const pcl::PointCloud<pcl::PointXYZI>&)      include/urban_road_filter/data_structures.hpp:118,
+ *     defined src/lidar_segmentation.cpp:95-622 (hot path = :95-367; marker tail = :369-602)      -> urf_process / urf_process_batch
+ *   - void paramsCallback(LidarFiltersConfig&, uint32_t)  src/main.cpp:4-34 (fields cfg/LidarFilters.cfg:10-84) -> urf_set_params
+ *   - Detector::Detector / Detector::beam_init            src/lidar_segmentation.cpp:51-65, src/star_shaped_search.cpp:32-66 -> urf_create
+ *   - the five publishers (road, curb, roi, road_probably, road_marker) src/lidar_segmentation.cpp:55-59,601,618-621
+ *     -> urf_result (labels + emission order + marker vertices) and urf_build_markers (line strips)
+ *
+ * Plain C: pointers and sizes only, no C++/torch types. One urf_ctx owns one CUDA device, one stream and all device and
+ * pinned staging memory (allocated in urf_create, never in urf_process*). A ctx is not thread-safe; use one per thread.
+ * There is NO CPU fallback: every entry point that computes fails with URF_ERR_CUDA / URF_ERR_NO_DEVICE without a GPU.
+ */
+#ifndef URF_H_
+#define URF_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define URF_VERSION 100
+#define URF_MAX_VERTS 361        /* one candidate vertex per 1-degree bin 0..360, lidar_segmentation.cpp:305 */
+#define URF_STAR_SECTORS 360     /* `rep`, star_shaped_search.cpp:8 */
+#define URF_MAX_CHANNELS 256     /* upper bound accepted for urf_params.channels */
+
+/* status / error codes (the reference has none: it is `void` and silently returns, lidar_segmentation.cpp:124-126) */
+enum {
+  URF_OK = 0,
+  URF_TOO_FEW_POINTS = 1,        /* fewer than 30 points in the ROI: the reference publishes nothing for this scan */
+  URF_ERR_INVALID = -1,          /* bad argument (NULL, n > max_points, batch > max_batch, bad param range) */
+  URF_ERR_NO_DEVICE = -2,        /* no CUDA device / device index out of range */
+  URF_ERR_CUDA = -3,             /* a CUDA call failed; urf_last_cuda_error() has the text */
+  URF_ERR_NOMEM = -4,            /* device or pinned allocation failed */
+  URF_ERR_CAPACITY = -5          /* scan larger than the ctx was created for */
+};
+
+/* Label encoding = `short isCurbPoint` of the reference (data_structures.hpp:44) plus -1 for "not in the ROI cloud". */
+enum { URF_LABEL_OUTSIDE = -1, URF_LABEL_NONE = 0, URF_LABEL_ROAD = 1, URF_LABEL_CURB = 2 };
+
+/*
+ * The 27 dynamic_reconfigure parameters, same names, types and defaults as cfg/LidarFilters.cfg:10-84
+ * (double_t -> double, int_t -> int, bool_t -> int 0/1, str_t -> char[]). Like src/main.cpp:12-32 the library narrows
+ * every double to float when it is applied. `channels` is the reference's global `int channels = 64`
+ * (src/lidar_segmentation.cpp:4), exposed because 128/256-ring sensors need it.
+ */
+typedef struct urf_params {
+  char   fixed_frame[128];       /* glue only */
+  char   topic_name[128];        /* glue only */
+  int    x_zero_method;
+  int    z_zero_method;
+  int    star_shaped_method;
+  int    blind_spots;
+  int    xDirection;             /* 0 bothX, 1 positiveX, 2 negativeX */
+  double interval;
+  double curb_height;
+  int    curb_points;
+  double beamZone;
+  double min_x, max_x, min_y, max_y, min_z, max_z;
+  double cylinder_deg_x;
+  double cylinder_deg_z;
+  double curb_slope_deg;
+  double kdev_param;
+  double kdist_param;
+  int    starbeam_filter;
+  int    dmin_param;
+  int    simple_poly_allow;      /* marker tail only */
+  double poly_s_param;           /* marker tail only */
+  double poly_z_manual;          /* marker tail only */
+  int    poly_z_avg_allow;       /* marker tail only */
+  int    channels;               /* 1..URF_MAX_CHANNELS, default 64 */
+} urf_params;
+
+/*
+ * Per-scan result. The caller owns every buffer; pointer members may be NULL when that output is not wanted.
+ *   label[i]  (i < n_in)  : URF_LABEL_* of input point i (input order).
+ *   ring[i]   (i < n_in)  : index of the point's ring in ascending-elevation order (= first index of array3D,
+ *                           lidar_segmentation.cpp:226-238), -1 if outside the ROI or no registered ring matches.
+ *   order[k]  (k < n_order): input index of the k-th point in the reference's emission order (ring-major, ascending
+ *                           azimuth — the order of lidar_segmentation.cpp:354-367). road cloud = points of `order` with
+ *                           label 1, curb cloud = label 2, road_probably = the segment of ring 10.
+ *   ring_start[r] (r <= n_rings): offset of ring r inside `order` (ring_start[n_rings] == n_order); caller provides
+ *                           URF_MAX_CHANNELS+1 ints or NULL.
+ *   vert      : marker candidate vertices (x, y, z, redFlag) exactly as markerPointsArray is filled by
+ *               lidar_segmentation.cpp:305-351, BEFORE the flag smoothing of :381-415.
+ */
+typedef struct urf_result {
+  int32_t  status;               /* URF_OK or URF_TOO_FEW_POINTS (all other outputs then describe "nothing published") */
+  int32_t  n_in;
+  int32_t  n_roi;                /* `piece`, lidar_segmentation.cpp:120 */
+  int32_t  n_rings;              /* `index`, lidar_segmentation.cpp:139 */
+  int32_t  n_order;              /* points that were assigned a ring */
+  int32_t  n_road;               /* label 1 count */
+  int32_t  n_curb;               /* label 2 count */
+  int32_t  n_vert;               /* `cM`, lidar_segmentation.cpp:300 */
+  int32_t  flags;                /* bit0: exact-fallback ring registration ran; bit1: sector-radius ties present;
+                                    bit2: ring-azimuth ties present (tie policy differs from the reference's unstable sorts) */
+  int32_t  reserved;
+  int32_t* label;                /* [n_in] or NULL */
+  int32_t* ring;                 /* [n_in] or NULL */
+  int32_t* order;                /* [n_in] or NULL */
+  int32_t* ring_start;           /* [URF_MAX_CHANNELS + 1] or NULL */
+  float    vert[URF_MAX_VERTS][4];
+} urf_result;
+
+/* One line strip of the road_marker MarkerArray (lidar_segmentation.cpp:417-598). */
+typedef struct urf_strip {
+  int32_t id;                    /* Marker.id */
+  int32_t action;                /* 0 = ADD, 2 = DELETE (ghost removal, :592-597) */
+  int32_t red;                   /* 1 = red (1,0,0,1), 0 = green (0,1,0,1) */
+  int32_t first;                 /* first point index in the points array */
+  int32_t count;                 /* number of points */
+} urf_strip;
+
+typedef struct urf_ctx urf_ctx;
+
+/* Fill *p with the defaults of cfg/LidarFilters.cfg (and channels = 64). */
+void urf_default_params(urf_params* p);
+
+/* Create a context on CUDA device `device` able to process scans of up to max_points input points, up to max_batch
+ * scans per urf_process_batch call. Replaces Detector::Detector + beam_init (lidar_segmentation.cpp:51-65). */
+int urf_create(urf_ctx** out, int device, int max_points, int max_batch);
+void urf_destroy(urf_ctx* ctx);
+
+/* Replaces paramsCallback (src/main.cpp:4-34). Takes effect for the next urf_process* call. */
+int urf_set_params(urf_ctx* ctx, const urf_params* p);
+int urf_get_params(const urf_ctx* ctx, urf_params* p);
+
+/* Replaces one Detector::filtered() call. xyzi = n points of 4 floats (x, y, z, intensity) in HOST memory: the first
+ * 16 bytes of each pcl::PointXYZI record once the PointCloud2 has been deserialised. Synchronous. */
+int urf_process(urf_ctx* ctx, const float* xyzi, int n, urf_result* out);
+
+/* `batch` independent scans (distinct clouds, same params), HOST buffers. xyzi[b] has n[b] points; outs[b] as above. */
+int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int batch, urf_result* outs);
+
+/* Device-resident variant used to time the kernels without PCIe: d_xyzi is a DEVICE pointer to the scans stored back to
+ * back (scan b starts at point offset b*stride_points, has n[b] points), d_label a DEVICE pointer with the same layout
+ * (int32 per point) that receives the labels. Small per-scan metadata (counts, vertices) is still returned in outs[b]
+ * (label/ring/order pointers in outs[] are ignored). Runs on the ctx stream; returns after the stream is idle. */
+int urf_process_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch,
+                             int32_t* d_label, urf_result* outs);
+
+/* Asynchronous pair for the above (enqueue on the ctx stream / wait + read back metadata), so callers can bracket the
+ * enqueue with their own CUDA events on urf_stream(). */
+int urf_enqueue_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch,
+                             int32_t* d_label);
+int urf_finish_batch_device(urf_ctx* ctx, urf_result* outs);
+void* urf_stream(urf_ctx* ctx);            /* cudaStream_t of the ctx */
+/* CUDA-event timing of everything enqueued by the last urf_enqueue/process call: total ms on the ctx stream. */
+float urf_last_device_ms(const urf_ctx* ctx);
+/* Number of kernel launches issued by the last urf_process* / urf_enqueue* call. */
+int urf_last_launch_count(const urf_ctx* ctx);
+
+/* Marker tail (lidar_segmentation.cpp:371-598) as a host routine: flag smoothing, strip splitting, optional
+ * Douglas-Peucker simplification, zavg, ghost DELETE markers. `ghostcount` is the reference's global (:23) kept by the
+ * caller between scans. points_xyz receives 3 doubles per point (geometry_msgs::Point); returns the number of strips
+ * written (<= max_strips), or a negative error. n_points_out receives the number of points written. */
+int urf_build_markers(const urf_params* p, const float (*vert)[4], int n_vert, int* ghostcount,
+                      urf_strip* strips, int max_strips, double* points_xyz, int max_points, int* n_points_out);
+
+const char* urf_strerror(int code);
+const char* urf_last_cuda_error(const urf_ctx* ctx);
+int urf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* URF_H_ */
