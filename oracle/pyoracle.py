@@ -82,6 +82,11 @@ class PortResult:
     pass
 
 
+class OracleDebug(C.Structure):
+    _fields_ = [("alpha_v", C.c_void_p), ("az", C.c_void_p), ("d2", C.c_void_p), ("star_mark", C.c_void_p),
+                ("det_label", C.c_void_p), ("ring_angle", C.c_void_p), ("max_dist", C.c_void_p)]
+
+
 class PortOracle:
     """Our CPU restatement of the path (oracle/urf_oracle.cpp): same outputs as urf_result plus intermediates."""
 
@@ -89,6 +94,9 @@ class PortOracle:
         self.lib = C.CDLL(path)
         self.lib.urf_oracle_run.restype = C.c_int
         self.lib.urf_oracle_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(UrfParams), C.POINTER(UrfResult)]
+        self.lib.urf_oracle_run_debug.restype = C.c_int
+        self.lib.urf_oracle_run_debug.argtypes = [C.c_void_p, C.c_int, C.POINTER(UrfParams), C.POINTER(UrfResult),
+                                                  C.POINTER(OracleDebug)]
         self.lib.urf_oracle_time.restype = C.c_double
         self.lib.urf_oracle_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(UrfParams), C.c_int]
 
@@ -96,10 +104,18 @@ class PortOracle:
     def available(path: str = PORT_SO) -> bool:
         return os.path.exists(path)
 
-    def run(self, pts: np.ndarray, prm: UrfParams) -> PortResult:
+    def run(self, pts: np.ndarray, prm: UrfParams, debug: bool = False) -> PortResult:
         pts = _f32c(pts)
         n = pts.shape[0]
         res = UrfResult()
+        dbg = None
+        if debug:
+            m = max(n, 1)
+            dbg_arrays = dict(alpha_v=np.full(m, np.nan, np.float32), az=np.full(m, np.nan, np.float32),
+                              d2=np.full(m, np.nan, np.float32), star_mark=np.zeros(m, np.int8),
+                              det_label=np.full(m, -1, np.int8), ring_angle=np.full(URF_MAX_CHANNELS, np.nan, np.float32),
+                              max_dist=np.full(URF_MAX_CHANNELS, np.nan, np.float32))
+            dbg = OracleDebug(**{k: v.ctypes.data for k, v in dbg_arrays.items()})
         label = np.full(max(n, 1), -1, np.int32)
         ring = np.full(max(n, 1), -1, np.int32)
         order = np.zeros(max(n, 1), np.int32)
@@ -108,9 +124,15 @@ class PortOracle:
         res.ring = ring.ctypes.data_as(C.POINTER(C.c_int32))
         res.order = order.ctypes.data_as(C.POINTER(C.c_int32))
         res.ring_start = ring_start.ctypes.data_as(C.POINTER(C.c_int32))
-        rc = self.lib.urf_oracle_run(pts.ctypes.data, n, C.byref(prm), C.byref(res))
+        if debug:
+            rc = self.lib.urf_oracle_run_debug(pts.ctypes.data, n, C.byref(prm), C.byref(res), C.byref(dbg))
+        else:
+            rc = self.lib.urf_oracle_run(pts.ctypes.data, n, C.byref(prm), C.byref(res))
         assert rc == 0, rc
         r = PortResult()
+        if debug:
+            for k, v in dbg_arrays.items():
+                setattr(r, k, v[:n] if v.shape[0] == max(n, 1) and k not in ("ring_angle", "max_dist") else v)
         r.status = res.status
         r.n_roi, r.n_rings, r.n_order = res.n_roi, res.n_rings, res.n_order
         r.n_road, r.n_curb, r.n_vert, r.flags = res.n_road, res.n_curb, res.n_vert, res.flags
