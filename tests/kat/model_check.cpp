@@ -1,0 +1,303 @@
+// tests/kat/model_check.cpp — CPU model of the CUDA pipeline (TEST CODE, not a product path and not a fallback).
+//
+// Runs the SAME host+device logic functions the kernels call (urban_road_filter_b200/csrc/urf_logic.cuh, compiled for the
+// host with -ffp-contract=off), stage by stage in the order of the kernel pipeline, with sequential stand-ins for what
+// the GPU does with atomics, stable partitions and sorts. tests/test_model.py diffs its outputs against the oracle, so
+// the reformulated stages (speculative ring registration + verification, blindSpots as window tables, marker search as
+// order-independent aggregates) are checked on the CPU before any GPU run. Entry point has the oracle's signature.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../../urban_road_filter_b200/csrc/urf_logic.cuh"
+#include "../../urban_road_filter_b200/csrc/urf_host.hpp"
+
+using namespace urf;
+
+struct urf_oracle_debug {   // same layout as oracle/urf_oracle.cpp
+  float* alpha_v; float* az; float* d2; int8_t* star_mark; int8_t* det_label; float* ring_angle; float* max_dist;
+};
+
+namespace {
+
+// exact registration, mirrors register_exact_cta (sequential form of the rounds)
+int register_exact(const std::vector<float>& alpha, float interval, int channels, std::vector<float>& reg, std::vector<int>& idx) {
+  std::vector<float> vis;
+  bool frozen = false;
+  int i_last = -1;
+  const int n = (int)alpha.size();
+  while ((int)reg.size() < channels) {
+    int istar = -1;
+    for (int i = i_last + 1; i < n; i++) {
+      const float a = alpha[i];
+      if (a < 0.0f) continue;
+      bool cov = false;
+      for (float v : vis) if (fabsf(URF_FSUB(v, a)) <= interval) { cov = true; break; }
+      if (!cov) { istar = i; break; }
+    }
+    if (istar < 0) break;
+    const float a = alpha[istar];
+    reg.push_back(a); idx.push_back(istar);
+    if (!frozen) { if (a == 0.0f) frozen = true; else vis.push_back(a); }
+    i_last = istar;
+  }
+  return (int)reg.size();
+}
+
+}  // namespace
+
+extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf_result* out, const urf_oracle_debug* dbg,
+                             int force_exact) {
+  if (validate_params(up) != URF_OK) return URF_ERR_INVALID;
+  static float beam_d[kSectKeys], beam_o[kSectKeys], Kfi;
+  static unsigned char beam_yx[kSectKeys];
+  static bool init = false;
+  if (!init) { host_beam_init(beam_d, beam_o, beam_yx, &Kfi); init = true; }
+  DevParams prm;
+  narrow_params(up, &prm, Kfi, force_exact, 1);
+  std::vector<float> newY;
+  host_newY(newY, n);
+
+  out->status = URF_OK; out->n_in = n; out->n_roi = 0; out->n_rings = 0; out->n_order = 0; out->n_road = 0;
+  out->n_curb = 0; out->n_vert = 0; out->flags = 0; out->reserved = 0;
+  if (out->label) for (int i = 0; i < n; i++) out->label[i] = URF_LABEL_OUTSIDE;
+  if (out->ring) for (int i = 0; i < n; i++) out->ring[i] = -1;
+  int flags = 0;
+
+  // ---- k_points
+  std::vector<float> alpha(n, -1.0f);
+  std::vector<unsigned> firstidx(kElevBins + 1, 0xffffffffu);
+  int n_roi = 0;
+  for (int i = 0; i < n; i++) {
+    const float x = xyzi[4 * i], y = xyzi[4 * i + 1], z = xyzi[4 * i + 2];
+    if (!roi_keep(prm, x, y, z)) continue;
+    n_roi++;
+    const float a = elev_alpha(x, y, z);
+    alpha[i] = a;
+    int bin = (int)(a * (kElevBins / 180.0f));
+    bin = bin < 0 ? 0 : (bin > kElevBins ? kElevBins : bin);
+    if (firstidx[bin] > (unsigned)i) firstidx[bin] = (unsigned)i;
+    if (a == 0.0f) flags |= F_ZERO_ALPHA;
+  }
+  out->n_roi = n_roi;
+  if (n_roi < 30) { out->status = URF_TOO_FEW_POINTS; return 0; }
+
+  // ---- k_register
+  std::vector<float> reg; std::vector<int> ridx;
+  bool exact = prm.force_exact || (flags & F_ZERO_ALPHA);
+  if (!exact) {
+    std::vector<unsigned> cand;
+    for (unsigned v : firstidx) if (v != 0xffffffffu) cand.push_back(v);
+    if ((int)cand.size() > kMaxCand) exact = true;
+    else {
+      std::sort(cand.begin(), cand.end());
+      for (unsigned c : cand) {
+        if ((int)reg.size() >= prm.channels) break;
+        const float a = alpha[c];
+        bool cov = false;
+        for (float v : reg) if (fabsf(URF_FSUB(v, a)) <= prm.interval) cov = true;
+        if (!cov) { reg.push_back(a); ridx.push_back((int)c); }
+      }
+    }
+  }
+  if (exact) { reg.clear(); ridx.clear(); register_exact(alpha, prm.interval, prm.channels, reg, ridx); flags |= F_EXACT_REG; }
+
+  ScanTab* tabp = new ScanTab();
+  ScanTab& tab = *tabp;
+  std::vector<short> ringid(n, -1), sect(n, -1);
+  int R = 0;
+  auto publish = [&]() {
+    R = (int)reg.size();
+    std::vector<std::pair<float, int>> pr(R);
+    for (int t = 0; t < R; t++) pr[t] = {reg[t], ridx[t]};
+    std::sort(pr.begin(), pr.end());
+    for (int t = 0; t < kRingKeys; t++) { tab.angle[t] = 0.f; tab.regidx[t] = 0x7fffffff; tab.regorder[t] = 0x7fffffff; }
+    for (int t = 0; t < R; t++) { tab.angle[t] = pr[t].first; tab.regidx[t] = pr[t].second; tab.regorder[t] = ridx[t]; }
+  };
+  publish();
+  // ---- k_assign (+ verify, + repair)
+  auto assign_all = [&](bool verify) {
+    bool viol = false;
+    for (int i = 0; i < n; i++) {
+      const float a = alpha[i];
+      ringid[i] = -1; sect[i] = -1;
+      if (a < 0.0f) continue;
+      int lo;
+      ringid[i] = (short)assign_ring(tab.angle, R, a, prm.interval, &lo);
+      if (verify && registration_violation(tab.angle, tab.regidx, tab.regorder, R, prm.channels, prm.interval, a, i, lo)) viol = true;
+      if (prm.star) sect[i] = (short)star_sector(prm, xyzi[4 * i], xyzi[4 * i + 1], beam_d, beam_o, beam_yx);
+    }
+    return viol;
+  };
+  if (assign_all(!(flags & F_EXACT_REG))) {
+    flags |= F_SPEC_VIOLATION | F_EXACT_REG;
+    reg.clear(); ridx.clear();
+    register_exact(alpha, prm.interval, prm.channels, reg, ridx);
+    publish();
+    assign_all(false);
+  }
+  if (out->label) for (int i = 0; i < n; i++) if (alpha[i] >= 0.0f) out->label[i] = URF_LABEL_NONE;
+
+  // ---- k_scan_offsets + k_scatter (stable partitions)
+  std::vector<int> ring_start(kRingKeys + 1, 0), sect_start(kSectKeys + 1, 0);
+  for (int i = 0; i < n; i++) { if (ringid[i] >= 0) ring_start[ringid[i] + 1]++; if (sect[i] >= 0) sect_start[sect[i] + 1]++; }
+  for (int k = 0; k < kRingKeys; k++) ring_start[k + 1] += ring_start[k];
+  for (int k = 0; k < kSectKeys; k++) sect_start[k + 1] += sect_start[k];
+  const int N = ring_start[kRingKeys];
+  std::vector<float4> bpt(std::max(N, 1)), spt(std::max(sect_start[kSectKeys], 1));
+  {
+    std::vector<int> rr(ring_start.begin(), ring_start.end() - 1), ss(sect_start.begin(), sect_start.end() - 1);
+    for (int i = 0; i < n; i++) {
+      const float x = xyzi[4 * i], y = xyzi[4 * i + 1], z = xyzi[4 * i + 2];
+      if (ringid[i] >= 0) bpt[rr[ringid[i]]++] = make_float4(x, y, z, URF_I2F(i));
+      if (sect[i] >= 0) spt[ss[sect[i]]++] = make_float4(star_radius(x, y), z, URF_I2F(i), 0.f);
+    }
+  }
+
+  // ---- k_star_sort + k_star_scan
+  std::vector<unsigned char> mark(n, 0);
+  if (prm.star) {
+    for (int s = 0; s < kSectKeys; s++) {
+      const int base = sect_start[s], m = sect_start[s + 1] - base;
+      if (m <= 0) continue;
+      std::vector<unsigned long long> keys(m);
+      for (int t = 0; t < m; t++) keys[t] = ((unsigned long long)fbits(spt[base + t].x) << 32) | (unsigned)t;
+      std::sort(keys.begin(), keys.end());
+      std::vector<float4> sorted(m);
+      for (int t = 0; t < m; t++) {
+        sorted[t] = spt[base + (unsigned)keys[t]];
+        if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(keys[t] >> 32)) flags |= F_TIE_SECTOR;
+      }
+      const int hit = star_scan_sector(prm, sorted.data(), m);
+      if (hit >= 0) mark[URF_F2I(sorted[hit].z)] = 2;
+    }
+  }
+
+  // ---- k_ring_detect
+  std::vector<float> az(std::max(N, 1)), d2(std::max(N, 1));
+  std::vector<unsigned char> blabel(std::max(N, 1), 0);
+  const size_t nb = (size_t)prm.channels * kDegBins;
+  std::vector<unsigned> cmin(nb, 0x7f800000u), cmax(nb, 0u);
+  std::vector<unsigned short> ne((size_t)prm.channels * (kDegBins + 1), 0);
+  for (int k = 0; k < kRingKeys; k++) tab.maxdist[k] = 0u;
+  for (int k = 0; k < R; k++) {
+    const int base = ring_start[k], m = ring_start[k + 1] - base;
+    const float4* ring = bpt.data() + base;
+    for (int t = 0; t < m; t++) {
+      float d, a;
+      planar_az(ring[t].x, ring[t].y, &d, &a);
+      az[base + t] = a; d2[base + t] = d;
+      if (fbits(d) > tab.maxdist[k]) tab.maxdist[k] = fbits(d);
+      const int idx = URF_F2I(ring[t].w);
+      int lab = prm.star ? mark[idx] : 0;
+      if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, m, t, newY.data())) lab = 2;
+      if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, m, t)) lab = 2;
+      blabel[base + t] = (unsigned char)lab;
+      if (lab == 2 && a >= 0.0f) {
+        const size_t o = (size_t)k * kDegBins + deg_bin(a);
+        if (fbits(a) < cmin[o]) cmin[o] = fbits(a);
+        if (fbits(a) > cmax[o]) cmax[o] = fbits(a);
+      }
+    }
+  }
+  if (dbg) {
+    for (int i = 0; i < n; i++) {
+      if (alpha[i] < 0.0f) continue;
+      if (dbg->alpha_v) dbg->alpha_v[i] = alpha[i];
+      if (dbg->star_mark) dbg->star_mark[i] = (int8_t)mark[i];
+    }
+    for (int p = 0; p < N; p++) {
+      const int idx = URF_F2I(bpt[p].w);
+      if (dbg->az) dbg->az[idx] = az[p];
+      if (dbg->d2) dbg->d2[idx] = d2[p];
+      if (dbg->det_label) dbg->det_label[idx] = (int8_t)blabel[p];
+    }
+    for (int k = 0; k < R; k++) {
+      if (dbg->ring_angle) dbg->ring_angle[k] = tab.angle[k];
+      if (dbg->max_dist) dbg->max_dist[k] = bitsf(tab.maxdist[k]);
+    }
+  }
+
+  // ---- k_tables
+  CurbView cv{cmin.data(), cmax.data(), ne.data()};
+  for (int k = 0; k < R; k++) {
+    unsigned short run = 0;
+    for (int bin = 0; bin < kDegBins; bin++) { ne[(size_t)k * (kDegBins + 1) + bin] = run; run += cmin[(size_t)k * kDegBins + bin] != 0x7f800000u; }
+    ne[(size_t)k * (kDegBins + 1) + kDegBins] = run;
+  }
+  {
+    const float arc = arc_distance(prm, bitsf(tab.maxdist[0]));
+    for (int k = 0; k < R; k++) tab.A[k] = ring_width(arc, bitsf(tab.maxdist[k]));
+    for (int w = 0; w < 4; w++) tab.q[w] = blind_quarter(prm, cv, R, w);
+    for (int dir = 0; dir < 2; dir++)
+      for (int i = 0; i < kDegBins; i++) {
+        const int reach = window_reach(prm, cv, tab.A, tab.q, R, dir, i);
+        tab.reach[dir][i] = (unsigned short)reach; tab.st[dir][0][i] = (unsigned short)reach;
+      }
+    for (int l = 1; l < kStLevels; l++)
+      for (int dir = 0; dir < 2; dir++)
+        for (int i = 0; i < kDegBins; i++) {
+          const int j = i + (1 << (l - 1));
+          const unsigned short a = tab.st[dir][l - 1][i], c = j < kDegBins ? tab.st[dir][l - 1][j] : (unsigned short)0;
+          tab.st[dir][l][i] = a > c ? a : c;
+        }
+  }
+
+  // ---- k_label, k_cutkey, k_dmax, k_best, k_verts
+  for (int i = 0; i < kDegBins; i++) { tab.cut[i] = 0x7fffffff; tab.cutkey[i] = ~0ull; tab.dmax[i] = 0u; tab.best[i] = ~0ull; }
+  std::vector<int> pring(std::max(N, 1));
+  for (int k = 0; k < R; k++) for (int p = ring_start[k]; p < ring_start[k + 1]; p++) pring[p] = k;
+  for (int p = 0; p < N; p++) {
+    const int k = pring[p];
+    int lab = blabel[p];
+    if (lab != 2 && covered_by_window(prm, tab, k, az[p])) lab = 1;
+    blabel[p] = (unsigned char)lab;
+    const int idx = URF_F2I(bpt[p].w);
+    if (out->label) out->label[idx] = lab;
+    if (out->ring) out->ring[idx] = k;
+    if (lab == 1) out->n_road++; else if (lab == 2) out->n_curb++;
+    if (lab != 1 && az[p] >= 0.0f) { const int bin = deg_bin(az[p]); if (tab.cut[bin] > k) tab.cut[bin] = k; }
+  }
+  for (int p = 0; p < N; p++) {
+    if (!(az[p] >= 0.0f)) continue;
+    const int bin = deg_bin(az[p]);
+    if (blabel[p] != 1 && pring[p] == tab.cut[bin]) tab.cutkey[bin] = std::min(tab.cutkey[bin], cut_key(fbits(az[p]), p));
+  }
+  for (int p = 0; p < N; p++) {
+    if (!(az[p] >= 0.0f)) continue;
+    const int bin = deg_bin(az[p]);
+    if (marker_candidate(tab, pring[p], blabel[p], bin, fbits(az[p]), p)) tab.dmax[bin] = std::max(tab.dmax[bin], fbits(d2[p]));
+  }
+  for (int p = 0; p < N; p++) {
+    if (!(az[p] >= 0.0f)) continue;
+    const int bin = deg_bin(az[p]);
+    if (marker_candidate(tab, pring[p], blabel[p], bin, fbits(az[p]), p) && fbits(d2[p]) != 0u && fbits(d2[p]) == tab.dmax[bin])
+      tab.best[bin] = std::min(tab.best[bin], best_key(pring[p], fbits(az[p]), p));
+  }
+  int cM = 0;
+  for (int i = 0; i < kDegBins; i++) {
+    if (tab.best[i] == ~0ull) continue;
+    const int p = (int)(tab.best[i] & 0xffffffull);
+    out->vert[cM][0] = bpt[p].x; out->vert[cM][1] = bpt[p].y; out->vert[cM][2] = bpt[p].z;
+    out->vert[cM][3] = tab.cut[i] != 0x7fffffff ? 1.0f : 0.0f;
+    cM++;
+  }
+  out->n_vert = cM;
+
+  // ---- k_sort_rings
+  for (int k = 0; k < R; k++) {
+    const int base = ring_start[k], m = ring_start[k + 1] - base;
+    std::vector<unsigned long long> keys(m);
+    for (int t = 0; t < m; t++) keys[t] = ((unsigned long long)fbits(az[base + t]) << 32) | (unsigned)t;
+    std::sort(keys.begin(), keys.end());
+    for (int t = 0; t < m; t++) {
+      if (out->order) out->order[base + t] = URF_F2I(bpt[base + (unsigned)keys[t]].w);
+      if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(keys[t] >> 32)) flags |= F_TIE_AZIMUTH;
+    }
+  }
+  out->n_rings = R; out->n_order = N;
+  if (out->ring_start) for (int k = 0; k <= kRingKeys; k++) out->ring_start[k] = ring_start[k];
+  out->flags = flags;   // the model reports internal bits too (tests look at F_SPEC_VIOLATION / F_EXACT_REG)
+  delete tabp;
+  return 0;
+}

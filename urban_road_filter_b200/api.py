@@ -1,0 +1,207 @@
+"""ctypes binding of liburf_b200.so plus `Detector`, the host-side mirror of the reference node's interface
+(`paramsCallback` -> set_params, `Detector::filtered` -> filtered / filtered_batch; src/main.cpp:4-34,
+src/lidar_segmentation.cpp:95). There is no CPU fallback: loading fails loudly when the CUDA library is missing and
+every compute call raises without a GPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .ctypes_abi import (URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_TOO_FEW_POINTS, UrfParams, UrfResult, UrfStrip,
+                         make_params)
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liburf_b200.so")
+
+EXPORTS = ["urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
+           "urf_set_params", "urf_get_params", "urf_process", "urf_process_batch", "urf_process_batch_device",
+           "urf_enqueue_batch_device", "urf_finish_batch_device", "urf_stream", "urf_last_device_ms",
+           "urf_last_launch_count", "urf_build_markers"]
+
+_lib = None
+
+
+class UrfError(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{where}: urf error {code}" + (f" ({detail})" if detail else ""))
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """Loads the CUDA library. Raises if it has not been built — there is deliberately no fallback."""
+    global _lib
+    if _lib is not None and path == LIB_PATH:
+        return _lib
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(urban_road_filter_b200 has no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, ip = C.c_void_p, C.c_int
+    lib.urf_version.restype = ip
+    lib.urf_strerror.restype = C.c_char_p
+    lib.urf_strerror.argtypes = [ip]
+    lib.urf_last_cuda_error.restype = C.c_char_p
+    lib.urf_last_cuda_error.argtypes = [vp]
+    lib.urf_default_params.argtypes = [C.POINTER(UrfParams)]
+    lib.urf_create.argtypes = [C.POINTER(vp), ip, ip, ip]
+    lib.urf_destroy.argtypes = [vp]
+    lib.urf_set_params.argtypes = [vp, C.POINTER(UrfParams)]
+    lib.urf_get_params.argtypes = [vp, C.POINTER(UrfParams)]
+    lib.urf_set_option.argtypes = [vp, ip, ip]
+    lib.urf_process.argtypes = [vp, vp, ip, C.POINTER(UrfResult)]
+    lib.urf_process_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(ip), ip, C.POINTER(UrfResult)]
+    lib.urf_process_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp, C.POINTER(UrfResult)]
+    lib.urf_enqueue_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp]
+    lib.urf_finish_batch_device.argtypes = [vp, C.POINTER(UrfResult)]
+    lib.urf_stream.restype = vp
+    lib.urf_stream.argtypes = [vp]
+    lib.urf_last_device_ms.restype = C.c_float
+    lib.urf_last_device_ms.argtypes = [vp]
+    lib.urf_last_launch_count.argtypes = [vp]
+    lib.urf_build_markers.argtypes = [C.POINTER(UrfParams), vp, ip, C.POINTER(ip), C.POINTER(UrfStrip), ip, vp, ip,
+                                      C.POINTER(ip)]
+    lib.urf_test_math.argtypes = [ip, ip, vp, vp, vp, ip]
+    lib.urf_debug_fetch.argtypes = [vp, ip, ip, vp, C.c_size_t]
+    lib.urf_debug_sizeof_tab.restype = C.c_size_t
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+class ScanResult:
+    """Per-scan output of the path (urf_result, include/urf.h)."""
+    __slots__ = ("status", "n_in", "n_roi", "n_rings", "n_order", "n_road", "n_curb", "n_vert", "flags", "label",
+                 "ring", "order", "ring_start", "vert")
+
+    @property
+    def published(self) -> bool:
+        return self.status == URF_OK
+
+    def cloud_indices(self, which: str) -> np.ndarray:
+        """Input indices of the `road` / `curb` / `road_probably` / `roi` clouds in the reference's emission order
+        (lidar_segmentation.cpp:354-367,605-608,620)."""
+        if which == "roi":
+            return np.nonzero(self.label >= 0)[0].astype(np.int32)
+        if self.order is None:
+            raise ValueError("emission order was not requested")
+        if which == "road_probably":
+            if self.n_rings <= 10:
+                return np.zeros(0, np.int32)
+            return self.order[self.ring_start[10]: self.ring_start[11]]
+        lab = self.label[self.order]
+        return self.order[lab == (1 if which == "road" else 2)]
+
+
+def build_markers(prm: UrfParams, vert: np.ndarray, ghostcount: int = 0):
+    """Marker tail (lidar_segmentation.cpp:371-598). Returns (strips, ghostcount'): strips = [(id, action, red, xyz[n,3])]."""
+    lib = load_library()
+    vert = np.ascontiguousarray(vert, np.float32).reshape(-1, 4)
+    strips = (UrfStrip * 1024)()
+    pts = np.zeros(3 * 4096, np.float64)
+    gc = C.c_int(ghostcount)
+    npnt = C.c_int(0)
+    ns = lib.urf_build_markers(C.byref(prm), vert.ctypes.data, vert.shape[0], C.byref(gc), strips, 1024,
+                               pts.ctypes.data, 4096, C.byref(npnt))
+    if ns < 0:
+        raise UrfError(ns, "urf_build_markers")
+    out = [(s.id, s.action, s.red, pts[3 * s.first: 3 * (s.first + s.count)].reshape(-1, 3).copy()) for s in strips[:ns]]
+    return out, gc.value
+
+
+class Detector:
+    """Host-side mirror of the reference's `Detector` (include/urban_road_filter/data_structures.hpp:110-141) on one GPU."""
+
+    def __init__(self, max_points: int, max_batch: int = 1, device: int = 0, params: UrfParams | None = None):
+        self.lib = load_library()
+        self._ctx = C.c_void_p()
+        rc = self.lib.urf_create(C.byref(self._ctx), device, max_points, max_batch)
+        if rc != URF_OK:
+            raise UrfError(rc, "urf_create", self.lib.urf_strerror(rc).decode())
+        self.max_points, self.max_batch, self.device = max_points, max_batch, device
+        self.params = params if params is not None else make_params()
+        self.set_params(self.params)
+        self.ghostcount = 0      # lidar_segmentation.cpp:23
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.urf_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, where: str):
+        if rc < 0:
+            raise UrfError(rc, where, self.lib.urf_strerror(rc).decode() + ": " + self.lib.urf_last_cuda_error(self._ctx).decode())
+
+    def set_params(self, prm: UrfParams):
+        """paramsCallback (src/main.cpp:4-34)."""
+        self._check(self.lib.urf_set_params(self._ctx, C.byref(prm)), "urf_set_params")
+        self.params = prm
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.urf_set_option(self._ctx, option, value), "urf_set_option")
+
+    def filtered_batch(self, clouds, want_ring: bool = True, want_order: bool = True) -> list[ScanResult]:
+        """`batch` independent Detector::filtered() calls (lidar_segmentation.cpp:95) on host (N,4) float32 arrays."""
+        B = len(clouds)
+        arrs = [np.ascontiguousarray(c, np.float32).reshape(-1, 4) for c in clouds]
+        ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+        ns = (C.c_int * B)(*[a.shape[0] for a in arrs])
+        res = (UrfResult * B)()
+        keep = []
+        for b, a in enumerate(arrs):
+            m = max(a.shape[0], 1)
+            lab = np.full(m, -1, np.int32)
+            ring = np.full(m, -1, np.int32) if want_ring else None
+            order = np.zeros(m, np.int32) if want_order else None
+            rs = np.zeros(URF_MAX_CHANNELS + 1, np.int32)
+            res[b].label = lab.ctypes.data_as(C.POINTER(C.c_int32))
+            if want_ring:
+                res[b].ring = ring.ctypes.data_as(C.POINTER(C.c_int32))
+            if want_order:
+                res[b].order = order.ctypes.data_as(C.POINTER(C.c_int32))
+            res[b].ring_start = rs.ctypes.data_as(C.POINTER(C.c_int32))
+            keep.append((lab, ring, order, rs))
+        self._check(self.lib.urf_process_batch(self._ctx, ptrs, ns, B, res), "urf_process_batch")
+        out = []
+        for b, a in enumerate(arrs):
+            lab, ring, order, rs = keep[b]
+            r = ScanResult()
+            n = a.shape[0]
+            for f in ("status", "n_in", "n_roi", "n_rings", "n_order", "n_road", "n_curb", "n_vert", "flags"):
+                setattr(r, f, int(getattr(res[b], f)))
+            r.label = lab[:n]
+            r.ring = ring[:n] if want_ring else None
+            r.order = order[: r.n_order].copy() if want_order else None
+            r.ring_start = rs[: r.n_rings + 1].copy()
+            r.vert = np.ctypeslib.as_array(res[b].vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()
+            out.append(r)
+        return out
+
+    def filtered(self, cloud, **kw) -> ScanResult:
+        """One Detector::filtered() call."""
+        return self.filtered_batch([cloud], **kw)[0]
+
+    def markers(self, result: ScanResult):
+        """road_marker MarkerArray of a scan (keeps the reference's `ghostcount` state between scans)."""
+        if not result.published:
+            return []
+        strips, self.ghostcount = build_markers(self.params, result.vert, self.ghostcount)
+        return strips
+
+    # diagnostics -------------------------------------------------------------------------------------------------
+    def last_device_ms(self) -> float:
+        return float(self.lib.urf_last_device_ms(self._ctx))
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.urf_last_launch_count(self._ctx))
+
+    def debug_fetch(self, scan: int, what: int, dtype, count: int) -> np.ndarray:
+        a = np.zeros(max(count, 1), dtype)
+        self._check(self.lib.urf_debug_fetch(self._ctx, scan, what, a.ctypes.data, a.nbytes if count else 0), "urf_debug_fetch")
+        return a[:count]

@@ -1,0 +1,81 @@
+"""Builds liburf_b200.so (nvcc, sm_100a) in-tree. nvcc cross-compiles without a GPU, so this runs on the CPU box too."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "liburf_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC"]
+SOURCES = ["urf_api.cu"]
+HOST_SOURCES = ["urf_markers.cpp"]
+HEADERS = ["urf_kernels.cuh", "urf_logic.cuh", "urf_device.cuh", "urf_math.cuh", "urf_host.hpp"]
+
+
+def _nvcc() -> str:
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> str:
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HOST_SOURCES + HEADERS] + [os.path.join(ROOT, "include", "urf.h")]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    bdir = os.path.join(ROOT, "build")
+    os.makedirs(bdir, exist_ok=True)
+    objs = []
+    for s in SOURCES:
+        o = os.path.join(bdir, s + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.run(cmd, check=True)
+        objs.append(o)
+    for s in HOST_SOURCES:
+        o = os.path.join(bdir, s + ".o")
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-c", os.path.join(CSRC, s), "-o", o], check=True)
+        objs.append(o)
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs], check=True)
+    return LIB
+
+
+def build_oracle() -> None:
+    """Test infrastructure: the CPU restatement always; the unmodified reference only where /root/reference exists."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True, stdout=subprocess.DEVNULL)
+
+
+def build_kat() -> None:
+    """Host-side known-answer binaries used by tests/ (libm sweep, CPU model of the pipeline)."""
+    bdir = os.path.join(ROOT, "build")
+    os.makedirs(bdir, exist_ok=True)
+    kat = os.path.join(ROOT, "tests", "kat")
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    tgt = os.path.join(bdir, "math_sweep")
+    if _stale(tgt, [os.path.join(kat, "math_sweep.cpp")] + hdrs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", tgt, os.path.join(kat, "math_sweep.cpp"),
+                        "-lpthread", "-lm"], check=True)
+    tgt = os.path.join(bdir, "libmodel.so")
+    if _stale(tgt, [os.path.join(kat, "model_check.cpp")] + hdrs):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+                        "-o", tgt, os.path.join(kat, "model_check.cpp")], check=True)
+
+
+if __name__ == "__main__":
+    print(build_lib(force=True, verbose=True))
+    build_oracle()
+    build_kat()

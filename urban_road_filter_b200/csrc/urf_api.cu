@@ -1,0 +1,402 @@
+// urf_api.cu — host side of liburf_b200.so: context, parameter narrowing, pipeline launcher and the C-ABI of include/urf.h.
+// There is no CPU fallback in this library: without a CUDA device every compute entry point returns an error.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "urf_kernels.cuh"
+#include "urf_host.hpp"
+
+using namespace urf;
+
+struct urf_ctx {
+  int device = 0;
+  int max_points = 0;      // per scan, rounded up to kChunk
+  int max_batch = 0;
+  size_t P = 0;            // max_batch * max_points
+  int Tmax = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuffers buf{};
+  float4* own_in = nullptr;
+  int* own_label = nullptr;
+  urf_params params{};
+  DevParams dp{};
+  int* h_n = nullptr;          // pinned
+  ScanOut* h_out = nullptr;    // pinned
+  int last_B = 0, last_S = 0;
+  int launches = 0;
+  float last_ms = 0.f;
+  bool timing_valid = false;
+  std::string err;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+      return e_ == cudaErrorMemoryAllocation ? URF_ERR_NOMEM : URF_ERR_CUDA;                        \
+    }                                                                                              \
+  } while (0)
+
+template <class T> int dalloc(urf_ctx* ctx, T** p, size_t count) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, count * sizeof(T) + 256));
+  ctx->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return URF_OK;
+}
+
+__global__ void k_ring32(DevBuffers buf, int* dst, int S) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < buf.n[b]) dst[(size_t)b * S + i] = buf.ringid[(size_t)b * S + i];
+}
+
+int launch_pipeline(urf_ctx* ctx, int B, int S, bool want_order) {
+  const DevParams dp = ctx->dp;
+  const DevBuffers buf = ctx->buf;
+  cudaStream_t st = ctx->stream;
+  const int T = (S + kChunk - 1) / kChunk;
+  if (T > ctx->Tmax) return URF_ERR_CAPACITY;
+  int L = 0;
+  const dim3 gpts((S + 255) / 256, B), gchunk((T + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
+  CK(cudaEventRecord(ctx->ev0, st));
+  k_reset<<<dim3(8, B), 256, 0, st>>>(buf, dp); L++;
+  k_points<<<gpts, 256, 0, st>>>(buf, dp, S); L++;
+  k_register<<<B, 256, 0, st>>>(buf, dp, S); L++;
+  k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 0); L++;
+  if (!dp.force_exact) {
+    k_register_exact<<<B, 256, 0, st>>>(buf, dp, S); L++;
+    k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 1); L++;
+    k_mark_exact<<<(B + 127) / 128, 128, 0, st>>>(buf, B); L++;
+  }
+  k_scan_offsets<<<B, 1024, 32 * kKeys * sizeof(unsigned), st>>>(buf, T); L++;
+  k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T); L++;
+  if (dp.star) {
+    k_star_sort<<<dim3(kSectKeys, B), 128, 0, st>>>(buf, S); L++;
+    k_star_scan<<<dim3((kSectKeys + 31) / 32, B), 32, 0, st>>>(buf, dp, S); L++;
+  }
+  k_ring_detect<<<gpts, 256, 0, st>>>(buf, dp, S); L++;
+  k_tables<<<B, 384, 0, st>>>(buf, dp); L++;
+  k_label<<<gpts, 256, 0, st>>>(buf, dp, S); L++;
+  k_cutkey<<<gpts, 256, 0, st>>>(buf, S); L++;
+  k_dmax<<<gpts, 256, 0, st>>>(buf, S); L++;
+  k_best<<<gpts, 256, 0, st>>>(buf, S); L++;
+  k_verts<<<B, 384, 0, st>>>(buf, S); L++;
+  if (want_order) { k_sort_rings<<<dim3(dp.channels, B), 256, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S); L++; }
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaGetLastError());
+  ctx->launches = L;
+  ctx->last_B = B; ctx->last_S = S;
+  ctx->timing_valid = true;
+  return URF_OK;
+}
+
+void fill_result(const ScanOut& o, urf_result* r) {
+  r->n_in = o.n_in; r->n_roi = o.n_roi;
+  r->flags = o.flags & F_PUBLIC_MASK; r->reserved = 0;
+  if (o.n_roi < 30) {                       // lidar_segmentation.cpp:124-126
+    r->status = URF_TOO_FEW_POINTS;
+    r->n_rings = 0; r->n_order = 0; r->n_road = 0; r->n_curb = 0; r->n_vert = 0;
+    if (r->ring_start) for (int k = 0; k <= URF_MAX_CHANNELS; k++) r->ring_start[k] = 0;
+    return;
+  }
+  r->status = URF_OK;
+  r->n_rings = o.n_rings; r->n_order = o.n_order; r->n_road = o.n_road; r->n_curb = o.n_curb; r->n_vert = o.n_vert;
+  std::memcpy(r->vert, o.vert, sizeof(float) * 4 * (size_t)o.n_vert);
+  if (r->ring_start) std::memcpy(r->ring_start, o.ring_start, sizeof(int) * (URF_MAX_CHANNELS + 1));
+}
+
+}  // namespace
+
+extern "C" {
+
+int urf_version(void) { return URF_VERSION; }
+
+const char* urf_strerror(int code) {
+  switch (code) {
+    case URF_OK: return "ok";
+    case URF_TOO_FEW_POINTS: return "fewer than 30 points in the ROI: nothing published";
+    case URF_ERR_INVALID: return "invalid argument";
+    case URF_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case URF_ERR_CUDA: return "CUDA error";
+    case URF_ERR_NOMEM: return "out of device or pinned memory";
+    case URF_ERR_CAPACITY: return "scan or batch larger than the context was created for";
+    default: return "unknown error";
+  }
+}
+
+const char* urf_last_cuda_error(const urf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void urf_default_params(urf_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  std::snprintf(p->fixed_frame, sizeof(p->fixed_frame), "left_os1/os1_lidar");
+  std::snprintf(p->topic_name, sizeof(p->topic_name), "/left_os1/os1_cloud_node/points");
+  p->x_zero_method = 1; p->z_zero_method = 1; p->star_shaped_method = 1; p->blind_spots = 1; p->xDirection = 0;
+  p->interval = 0.18; p->curb_height = 0.05; p->curb_points = 5; p->beamZone = 30;
+  p->min_x = 0; p->max_x = 30; p->min_y = -10; p->max_y = 10; p->min_z = -3; p->max_z = -1;
+  p->cylinder_deg_x = 150; p->cylinder_deg_z = 140; p->curb_slope_deg = 50;
+  p->kdev_param = 1.225; p->kdist_param = 2; p->starbeam_filter = 0; p->dmin_param = 10;
+  p->simple_poly_allow = 1; p->poly_s_param = 0.7; p->poly_z_manual = -1.5; p->poly_z_avg_allow = 1;
+  p->channels = 64;
+}
+
+int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
+  if (!out || max_points < 1 || max_batch < 1 || max_points > (1 << 24)) return URF_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return URF_ERR_NO_DEVICE;
+  urf_ctx* ctx = new urf_ctx();
+  auto fail = [&](int rc) { std::string e = ctx->err; urf_destroy(ctx); (void)e; return rc; };
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) return fail(URF_ERR_NO_DEVICE);
+  ctx->max_points = ((max_points + kChunk - 1) / kChunk) * kChunk;
+  ctx->max_batch = max_batch;
+  ctx->P = (size_t)ctx->max_points * max_batch;
+  ctx->Tmax = ctx->max_points / kChunk;
+  int rc;
+#define TRY(x) do { rc = (x); if (rc != URF_OK) return fail(rc); } while (0)
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = cudaGetErrorString(e_); return fail(URF_ERR_CUDA); } } while (0)
+  CKF(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CKF(cudaEventCreate(&ctx->ev0));
+  CKF(cudaEventCreate(&ctx->ev1));
+  const size_t P = ctx->P;
+  DevBuffers& b = ctx->buf;
+  TRY(dalloc(ctx, &ctx->own_in, P));
+  TRY(dalloc(ctx, &b.alpha_v, P));
+  TRY(dalloc(ctx, &b.mark, P));
+  TRY(dalloc(ctx, &b.ringid, P));
+  TRY(dalloc(ctx, &b.sect, P));
+  TRY(dalloc(ctx, &ctx->own_label, P));
+  TRY(dalloc(ctx, &b.bpt, P));
+  TRY(dalloc(ctx, &b.spt, P));
+  TRY(dalloc(ctx, &b.ssorted, P));
+  TRY(dalloc(ctx, &b.az, P));
+  TRY(dalloc(ctx, &b.d2, P));
+  TRY(dalloc(ctx, &b.blabel, P));
+  TRY(dalloc(ctx, &b.order, P));
+  TRY(dalloc(ctx, &b.sortbuf, 2 * P));
+  TRY(dalloc(ctx, &b.hist, (size_t)max_batch * ctx->Tmax * kKeys));
+  TRY(dalloc(ctx, &b.firstidx, (size_t)max_batch * (kElevBins + 1)));
+  TRY(dalloc(ctx, &b.cmin, (size_t)max_batch * URF_MAX_CHANNELS * kDegBins));
+  TRY(dalloc(ctx, &b.cmax, (size_t)max_batch * URF_MAX_CHANNELS * kDegBins));
+  TRY(dalloc(ctx, &b.ne, (size_t)max_batch * URF_MAX_CHANNELS * (kDegBins + 1)));
+  TRY(dalloc(ctx, &b.newY, (size_t)ctx->max_points));
+  TRY(dalloc(ctx, &b.n, (size_t)max_batch));
+  TRY(dalloc(ctx, &b.out, (size_t)max_batch));
+  TRY(dalloc(ctx, &b.tab, (size_t)max_batch));
+  b.in = ctx->own_in;
+  b.label = ctx->own_label;
+  CKF(cudaMallocHost((void**)&ctx->h_n, sizeof(int) * max_batch));
+  CKF(cudaMallocHost((void**)&ctx->h_out, sizeof(ScanOut) * max_batch));
+  {
+    std::vector<float> ny;
+    host_newY(ny, ctx->max_points);
+    CKF(cudaMemcpy(b.newY, ny.data(), sizeof(float) * ny.size(), cudaMemcpyHostToDevice));
+    float bd[kSectKeys], bo[kSectKeys], Kfi;
+    unsigned char byx[kSectKeys];
+    host_beam_init(bd, bo, byx, &Kfi);
+    CKF(cudaMemcpyToSymbol(c_beam_d, bd, sizeof(bd)));
+    CKF(cudaMemcpyToSymbol(c_beam_o, bo, sizeof(bo)));
+    CKF(cudaMemcpyToSymbol(c_beam_yx, byx, sizeof(byx)));
+    ctx->dp.Kfi = Kfi;
+  }
+  CKF(cudaFuncSetAttribute(k_scan_offsets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * kKeys * sizeof(unsigned))));
+  CKF(cudaFuncSetAttribute(k_sort_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingSmemKeys * sizeof(unsigned long long))));
+  urf_default_params(&ctx->params);
+  const char* fe = std::getenv("URF_FORCE_EXACT_REGISTRATION");
+  narrow_params(&ctx->params, &ctx->dp, ctx->dp.Kfi, fe && fe[0] == '1', 0);
+#undef TRY
+#undef CKF
+  *out = ctx;
+  return URF_OK;
+}
+
+void urf_destroy(urf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->h_n) cudaFreeHost(ctx->h_n);
+  if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int urf_set_params(urf_ctx* ctx, const urf_params* p) {
+  if (!ctx || !p) return URF_ERR_INVALID;
+  int rc = validate_params(p);
+  if (rc != URF_OK) return rc;
+  ctx->params = *p;
+  narrow_params(p, &ctx->dp, ctx->dp.Kfi, ctx->dp.force_exact, 0);
+  return URF_OK;
+}
+
+int urf_get_params(const urf_ctx* ctx, urf_params* p) {
+  if (!ctx || !p) return URF_ERR_INVALID;
+  *p = ctx->params;
+  return URF_OK;
+}
+
+// test/diagnostic options: 0 = force exact ring registration (0/1)
+int urf_set_option(urf_ctx* ctx, int option, int value) {
+  if (!ctx) return URF_ERR_INVALID;
+  if (option == 0) { ctx->dp.force_exact = value != 0; return URF_OK; }
+  return URF_ERR_INVALID;
+}
+
+void* urf_stream(urf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+float urf_last_device_ms(const urf_ctx* c) {
+  urf_ctx* ctx = const_cast<urf_ctx*>(c);
+  if (!ctx || !ctx->timing_valid) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+int urf_last_launch_count(const urf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int urf_enqueue_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch, int32_t* d_label) {
+  if (!ctx || !d_xyzi || !n || !d_label || batch < 1 || stride_points < 1) return URF_ERR_INVALID;
+  if (batch > ctx->max_batch || (size_t)stride_points * batch > ctx->P || stride_points > ctx->max_points) return URF_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  for (int b = 0; b < batch; b++) {
+    if (n[b] < 0 || n[b] > stride_points) return URF_ERR_INVALID;
+    ctx->h_n[b] = n[b];
+  }
+  CK(cudaMemcpyAsync(ctx->buf.n, ctx->h_n, sizeof(int) * batch, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->buf.in = reinterpret_cast<float4*>(const_cast<float*>(d_xyzi));
+  ctx->buf.label = d_label;
+  int rc = launch_pipeline(ctx, batch, stride_points, false);
+  ctx->buf.in = ctx->own_in;
+  ctx->buf.label = ctx->own_label;
+  return rc;
+}
+
+int urf_finish_batch_device(urf_ctx* ctx, urf_result* outs) {
+  if (!ctx) return URF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  const int B = ctx->last_B;
+  if (outs) CK(cudaMemcpyAsync(ctx->h_out, ctx->buf.out, sizeof(ScanOut) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (outs) for (int b = 0; b < B; b++) {
+    urf_result tmp = outs[b];
+    tmp.ring_start = nullptr;
+    fill_result(ctx->h_out[b], &tmp);
+    tmp.label = outs[b].label; tmp.ring = outs[b].ring; tmp.order = outs[b].order; tmp.ring_start = outs[b].ring_start;
+    outs[b] = tmp;
+  }
+  return URF_OK;
+}
+
+int urf_process_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch,
+                             int32_t* d_label, urf_result* outs) {
+  int rc = urf_enqueue_batch_device(ctx, d_xyzi, stride_points, n, batch, d_label);
+  if (rc != URF_OK) return rc;
+  return urf_finish_batch_device(ctx, outs);
+}
+
+int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int batch, urf_result* outs) {
+  if (!ctx || !xyzi || !n || !outs || batch < 1) return URF_ERR_INVALID;
+  if (batch > ctx->max_batch) return URF_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  int nmax = 1;
+  bool want_order = false, want_ring = false;
+  for (int b = 0; b < batch; b++) {
+    if (n[b] < 0 || (n[b] > 0 && !xyzi[b])) return URF_ERR_INVALID;
+    if (n[b] > ctx->max_points) return URF_ERR_CAPACITY;
+    nmax = n[b] > nmax ? n[b] : nmax;
+    want_order |= outs[b].order != nullptr;
+    want_ring |= outs[b].ring != nullptr;
+    ctx->h_n[b] = n[b];
+  }
+  const int S = ((nmax + 255) / 256) * 256;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->buf.n, ctx->h_n, sizeof(int) * batch, cudaMemcpyHostToDevice, st));
+  for (int b = 0; b < batch; b++)
+    if (n[b] > 0) CK(cudaMemcpyAsync(ctx->own_in + (size_t)b * S, xyzi[b], sizeof(float) * 4 * (size_t)n[b], cudaMemcpyHostToDevice, st));
+  int rc = launch_pipeline(ctx, batch, S, want_order);
+  if (rc != URF_OK) return rc;
+  int* ring32 = reinterpret_cast<int*>(ctx->buf.sortbuf);
+  if (want_ring) k_ring32<<<dim3((S + 255) / 256, batch), 256, 0, st>>>(ctx->buf, ring32, S);
+  CK(cudaMemcpyAsync(ctx->h_out, ctx->buf.out, sizeof(ScanOut) * batch, cudaMemcpyDeviceToHost, st));
+  for (int b = 0; b < batch; b++) {
+    if (n[b] <= 0) continue;
+    if (outs[b].label) CK(cudaMemcpyAsync(outs[b].label, ctx->own_label + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, st));
+    if (outs[b].ring) CK(cudaMemcpyAsync(outs[b].ring, ring32 + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, st));
+    if (outs[b].order) CK(cudaMemcpyAsync(outs[b].order, ctx->buf.order + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  for (int b = 0; b < batch; b++) {
+    fill_result(ctx->h_out[b], &outs[b]);
+    if (outs[b].status == URF_TOO_FEW_POINTS && outs[b].ring) for (int i = 0; i < n[b]; i++) outs[b].ring[i] = -1;
+  }
+  return URF_OK;
+}
+
+int urf_process(urf_ctx* ctx, const float* xyzi, int n, urf_result* out) {
+  const float* ptrs[1] = {xyzi};
+  return urf_process_batch(ctx, ptrs, &n, 1, out);
+}
+
+// ---- test hooks (not part of the reference-facing surface) ------------------------------------------------------------
+// Evaluate the device build of the emulated libm: which = 0 asinf(a), 1 acosf(a), 2 atan2f(a, b), 3 atanf(a).
+int urf_test_math(int device, int which, const float* a, const float* b, float* out, int n) {
+  if (cudaSetDevice(device) != cudaSuccess) return URF_ERR_NO_DEVICE;
+  float *da = nullptr, *db = nullptr, *dout = nullptr;
+  if (cudaMalloc(&da, sizeof(float) * n) != cudaSuccess || cudaMalloc(&db, sizeof(float) * n) != cudaSuccess ||
+      cudaMalloc(&dout, sizeof(float) * n) != cudaSuccess)
+    return URF_ERR_NOMEM;
+  cudaMemcpy(da, a, sizeof(float) * n, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, b ? b : a, sizeof(float) * n, cudaMemcpyHostToDevice);
+  k_test_math<<<(n + 255) / 256, 256>>>(da, db, dout, n, which);
+  cudaError_t e = cudaMemcpy(out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost);
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return e == cudaSuccess ? URF_OK : URF_ERR_CUDA;
+}
+
+// Copy a device-side intermediate of scan `b` of the last call into host memory (stage-level differential tests).
+//   what: 0 alpha_v[f32,n]  1 mark[u8,n]  2 ringid[i16,n]  3 sect[i16,n]  4 az[f32,n_order]  5 d2[f32,n_order]
+//         6 blabel[u8,n_order]  7 bucket input index[i32,n_order]  8 ScanTab (raw)
+int urf_debug_fetch(urf_ctx* ctx, int b, int what, void* dst, size_t bytes) {
+  if (!ctx || !dst || b < 0 || b >= ctx->last_B) return URF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t off = (size_t)b * ctx->last_S;
+  const void* src = nullptr;
+  switch (what) {
+    case 0: src = ctx->buf.alpha_v + off; break;
+    case 1: src = ctx->buf.mark + off; break;
+    case 2: src = ctx->buf.ringid + off; break;
+    case 3: src = ctx->buf.sect + off; break;
+    case 4: src = ctx->buf.az + off; break;
+    case 5: src = ctx->buf.d2 + off; break;
+    case 6: src = ctx->buf.blabel + off; break;
+    case 7: {
+      std::vector<float4> tmp(bytes / 4);
+      CK(cudaMemcpy(tmp.data(), ctx->buf.bpt + off, tmp.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < tmp.size(); i++) std::memcpy((char*)dst + 4 * i, &tmp[i].w, 4);
+      return URF_OK;
+    }
+    case 8: src = ctx->buf.tab + b; if (bytes > sizeof(ScanTab)) bytes = sizeof(ScanTab); break;
+    default: return URF_ERR_INVALID;
+  }
+  CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return URF_OK;
+}
+
+size_t urf_debug_sizeof_tab(void) { return sizeof(ScanTab); }
+
+}  // extern "C"

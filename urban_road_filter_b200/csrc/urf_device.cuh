@@ -1,0 +1,100 @@
+// urf_device.cuh — device-side data layout of liburf_b200 (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/urf.h"
+
+namespace urf {
+
+constexpr int kChunk = 1024;          // input points per warp chunk in the stable partition kernels
+constexpr int kWarpsPerBlock = 8;     // chunks per CTA in the partition kernels
+constexpr int kRingKeys = URF_MAX_CHANNELS;                 // 256 ring keys
+constexpr int kSectKeys = URF_STAR_SECTORS;                 // 360 sector keys
+constexpr int kKeys = kRingKeys + kSectKeys;                // 616 keys per histogram row
+constexpr int kElevBins = 4096;       // fine elevation bins used to speculate the greedy ring registration
+constexpr int kMaxCand = 1024;        // max speculation candidates handled by the fast registration path
+constexpr int kDegBins = 361;         // integer-degree bins 0..360 (marker search, lidar_segmentation.cpp:305)
+constexpr int kStLevels = 9;          // sparse-table levels over 361 window starts (2^9 = 512 > 361)
+
+// internal per-scan flag bits (low 3 bits are the public urf_result.flags)
+enum : int {
+  F_EXACT_REG = 1,       // exact (sequential-semantics) ring registration was used
+  F_TIE_SECTOR = 2,      // a star sector holds two points with identical planar radius
+  F_TIE_AZIMUTH = 4,     // a ring holds two points with identical azimuth (only detected when `order` is produced)
+  F_ZERO_ALPHA = 8,      // an elevation angle of exactly 0 exists (reference's `angle[j]==0` sentinel quirk) -> exact path
+  F_SPEC_VIOLATION = 16, // speculative registration failed verification -> exact path + re-assignment
+  F_PUBLIC_MASK = 7
+};
+
+// Narrowed parameters (src/main.cpp:5-32 narrows every double to float) plus host-derived loop bounds.
+struct DevParams {
+  int x_zero, z_zero, star, blind, xDirection;
+  float interval, curbHeight;
+  int curbPoints;
+  float beamZone, angleFilter1, angleFilter2, slope_param;
+  float min_X, max_X, min_Y, max_Y, min_Z, max_Z;
+  float kdev, kdist;
+  int starbeam, dmin, channels;
+  float Kfi;
+  // blind_spots.cpp:68 `for (i = 0; i <= 360 - beamZone; i++)` and :177 `for (i = 360; i >= 0 + beamZone; --i)`
+  int fwd_last;      // largest i >= 0 with (float)i <= 360.0f - beamZone, or -1
+  int fwd_special;   // the i with (float)i == 360.0f - beamZone (:136), or -1
+  int bwd_first;     // smallest i <= 360 with (float)i >= beamZone, or 361
+  int bwd_special;   // the i with (float)i == beamZone (:245), or -1
+  int force_exact;   // test hook: always use the exact registration path
+  int want_order;    // produce emission order (per-ring azimuth sort)
+};
+
+// Small per-scan outputs copied back to the host after every call.
+struct ScanOut {
+  int n_in, n_roi, n_rings, n_order, n_road, n_curb, n_vert, flags;
+  int ring_start[kRingKeys + 1];
+  float vert[URF_MAX_VERTS][4];
+};
+
+// Per-scan working tables that stay on the device.
+struct ScanTab {
+  float angle[kRingKeys];          // sorted registered elevation angles (lidar_segmentation.cpp:205)
+  int regidx[kRingKeys];           // input index that registered angle[j]
+  int regorder[kRingKeys];         // registration input indices in registration (= ascending) order
+  unsigned maxdist[kRingKeys];     // float bits of maxDistance[j] (:271-274); non-negative floats order like uints
+  double A[kRingKeys];             // arcDistance / ((maxDistance[k] * M_PI) / 180)  (blind_spots.cpp:142)
+  int sect_start[kSectKeys + 1];
+  float q[4];                      // q1..q4 (blind_spots.cpp:13-57)
+  unsigned short reach[2][kDegBins];                 // rings accepted by window start i, forward / backward
+  unsigned short st[2][kStLevels][kDegBins];         // range-max sparse tables over reach
+  int cut[kDegBins];               // first ring holding a non-road point in degree bin i
+  unsigned long long cutkey[kDegBins];               // (azimuth bits, bucket pos) of the first non-road point in that ring/bin
+  unsigned dmax[kDegBins];         // float bits of the farthest candidate road point
+  unsigned long long best[kDegBins];                 // (ring, azimuth bits, bucket pos) of the first candidate reaching dmax
+};
+
+// All device buffers of a context. P = max_batch * max_points; T = ceil(max_points / kChunk).
+struct DevBuffers {
+  float4* in;            // [P]   x, y, z, intensity (input order)
+  float* alpha_v;        // [P]   elevation angle in degrees, -1 = outside ROI
+  unsigned char* mark;   // [P]   star-shaped mark (2) per input point
+  short* ringid;         // [P]   ring index or -1
+  short* sect;           // [P]   star sector or -1
+  int* label;            // [P]   output labels, input order
+  float4* bpt;           // [P]   ring buckets (ring-major, input order inside a ring): x, y, z, input index bits
+  float4* spt;           // [P]   sector buckets: r, z, input index bits, -
+  float4* ssorted;       // [P]   sector buckets sorted by r
+  float* az;             // [P]   azimuth per bucket position
+  float* d2;             // [P]   planar range per bucket position
+  unsigned char* blabel; // [P]   label per bucket position
+  int* order;            // [P]   emission order (input indices), only when requested
+  unsigned long long* sortbuf;   // [2P] scratch for segments too large for shared memory
+  unsigned* hist;        // [B][T][kKeys] chunk histograms, turned into scatter offsets in place
+  unsigned* firstidx;    // [B][kElevBins + 1] first input index per fine elevation bin
+  unsigned* cmin;        // [B][channels][kDegBins] float bits: min curb azimuth per (ring, degree bin), +inf = empty
+  unsigned* cmax;        // [B][channels][kDegBins] float bits: max curb azimuth per (ring, degree bin)
+  unsigned short* ne;    // [B][channels][kDegBins + 1] prefix count of non-empty curb bins
+  float* newY;           // [max_points] x-zero `newY` ramp (x_zero_method.cpp:24-27), depends on the index only
+  int* n;                // [B] points per scan
+  ScanOut* out;          // [B]
+  ScanTab* tab;          // [B]
+};
+
+}  // namespace urf

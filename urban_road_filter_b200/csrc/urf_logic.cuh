@@ -1,0 +1,324 @@
+// urf_logic.cuh — the per-element logic of the path as host+device functions.
+//
+// Everything that decides a label lives here, written with the URF_F*/URF_D* round-to-nearest macros of urf_math.cuh in
+// exactly the operation order of the reference (file:line cited; paths relative to the reference repo). The CUDA kernels
+// (urf_kernels.cuh) only add indexing, staging and synchronisation around these functions. Because the same functions
+// also compile for the host (g++ -ffp-contract=off), tests/kat/model_check.cpp runs them sequentially on the CPU and
+// diffs every stage against the oracle without needing a GPU.
+#pragma once
+#include <math.h>
+
+#include "urf_device.cuh"
+#include "urf_math.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define URF_D2F(x) __double2float_rn((x))
+#define URF_F2I_RZ(x) __float2int_rz((x))
+#else
+#define URF_D2F(x) ((float)(x))
+#define URF_F2I_RZ(x) ((int)(x))
+#endif
+
+#define URF_TWO_PI_D 6.283185307179586476925286766559
+
+namespace urf {
+
+URF_HD unsigned fbits(float f) { return (unsigned)URF_F2I(f); }
+URF_HD float bitsf(unsigned u) { return URF_I2F((int32_t)u); }
+URF_HD double dsq(float a) { return URF_DMUL((double)a, (double)a); }      // pow(float, 2): exact in double
+
+// tail of every `acos(..) * 180 / M_PI` of the reference: float multiply, then double divide
+URF_HD double deg_d(float rad) { return URF_DDIV((double)URF_FMUL(rad, 180.0f), URF_PI_D); }
+
+URF_HD float clamp_unit(float b) {   // lidar_segmentation.cpp:154-157 (NaN passes through)
+  if (b < -1.0f) return -1.0f;
+  if (b > 1.0f) return 1.0f;
+  return b;
+}
+
+// ROI crop predicate, lidar_segmentation.cpp:106-113 (+ PCL ConditionalRemoval drops non-finite xyz)
+URF_HD bool roi_keep(const DevParams& prm, float x, float y, float z) {
+  return isfinite(x) && isfinite(y) && isfinite(z) && x >= prm.min_X && x <= prm.max_X && y >= prm.min_Y &&
+         y <= prm.max_Y && z >= prm.min_Z && z <= prm.max_Z && URF_FADD(URF_FADD(x, y), z) != 0.0f;
+}
+
+// elevation angle in degrees, lidar_segmentation.cpp:148-166
+URF_HD float elev_alpha(float x, float y, float z) {
+  const float d = URF_D2F(URF_DSQRT(URF_DADD(URF_DADD(dsq(x), dsq(y)), dsq(z))));     // :148
+  const float br = clamp_unit(URF_FDIV(fabsf(z), d));                                  // :151-157
+  if (z < 0.0f) return URF_D2F(deg_d(urfm::acosf_glibc(br)));                          // :162
+  return URF_D2F(URF_DADD(deg_d(urfm::asinf_glibc(br)), 90.0));                        // :165
+}
+
+// planar range and azimuth, lidar_segmentation.cpp:245-269
+URF_HD void planar_az(float x, float y, float* d_out, float* az_out) {
+  const float d = URF_D2F(URF_DSQRT(URF_DADD(dsq(x), dsq(y))));
+  const float br = clamp_unit(URF_FDIV(fabsf(x), d));
+  const double t = deg_d(urfm::asinf_glibc(br));
+  float az;
+  if (x >= 0.f && y <= 0.f) az = URF_D2F(t);
+  else if (x >= 0.f && y > 0.f) az = URF_D2F(URF_DSUB(180.0, t));
+  else if (x < 0.f && y >= 0.f) az = URF_D2F(URF_DADD(180.0, t));
+  else az = URF_D2F(URF_DSUB(360.0, t));
+  *d_out = d;
+  *az_out = az;
+}
+
+// star-shaped sector of a point, star_shaped_search.cpp:164-173 (+ rectangular beam filter :73-107): sector or -1
+URF_HD int star_sector(const DevParams& prm, float x, float y, const float* beam_d, const float* beam_o,
+                       const unsigned char* beam_yx) {
+  float fi = urfm::atan2f_glibc(y, x);                                       // :166
+  if (fi < 0.0f) fi = URF_D2F(URF_DADD((double)fi, URF_TWO_PI_D));           // :168-169
+  int f = URF_F2I_RZ(URF_FMUL(fi, prm.Kfi));                                 // :171
+  if (f >= kSectKeys || f < 0) f = 0;   // reference: null-pointer dereference for f == 360 (UB); we wrap
+  if (prm.starbeam) {                                                        // :73-107
+    const float bd = beam_d[f], bo = beam_o[f];
+    if (beam_yx[f]) { const float c = URF_FMUL(bd, y); if (!(URF_FSUB(c, bo) < x && x < URF_FADD(c, bo))) return -1; }
+    else            { const float c = URF_FMUL(bd, x); if (!(URF_FSUB(c, bo) < y && y < URF_FADD(c, bo))) return -1; }
+  }
+  return f;
+}
+URF_HD float star_radius(float x, float y) { return URF_FSQRT(URF_FADD(URF_FMUL(x, x), URF_FMUL(y, y))); }   // :164
+
+// ring of an elevation angle: first sorted registered angle within `interval` (lidar_segmentation.cpp:226-233).
+// *lo_out = first j with angle[j] - a >= -interval (float subtraction is monotone in angle[j]).
+URF_HD int assign_ring(const float* angle, int R, float a, float interval, int* lo_out) {
+  int lo = 0, hi = R;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (URF_FSUB(angle[mid], a) >= -interval) hi = mid; else lo = mid + 1;
+  }
+  *lo_out = lo;
+  return (lo < R && fabsf(URF_FSUB(angle[lo], a)) <= interval) ? lo : -1;    // :228
+}
+
+// Verification of a speculated registration for input point i (see k_register): true = the sequential algorithm of
+// lidar_segmentation.cpp:170-196 would have behaved differently at this point, i.e. the speculation is wrong.
+URF_HD bool registration_violation(const float* angle, const int* regidx, const int* regorder, int R, int channels,
+                                   float interval, float a, int i, int lo) {
+  int minreg = 0x7fffffff;
+  for (int j = lo; j < R && fabsf(URF_FSUB(angle[j], a)) <= interval; j++) minreg = regidx[j] < minreg ? regidx[j] : minreg;
+  if (minreg <= i) return false;           // covered by an angle registered at or before i (== i: i is the registrant)
+  int l2 = 0, h2 = R;                      // registrants with input index < i
+  while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (regorder[mid] < i) l2 = mid + 1; else h2 = mid; }
+  return l2 < channels;                    // uncovered and room left: it would have registered
+}
+
+// x-zero test with local index m as the middle point p2 = j + cp/2 (x_zero_method.cpp:30-67). ring[q] = (x, y, z, -).
+URF_HD bool xzero_mark(const DevParams& prm, const float4* ring, int n, int m, const float* newY) {
+  const int cp = prm.curbPoints;
+  const int j = m - cp / 2;
+  if (!(j >= cp && j <= (n - 1) - cp)) return false;
+  const int p3 = j + cp;
+  const float4 a = ring[j], c = ring[p3];
+  const float z = ring[m].z;
+  const bool h = (fabsf(URF_FSUB(a.z, z)) >= prm.curbHeight || fabsf(URF_FSUB(c.z, z)) >= prm.curbHeight) &&
+                 (double)fabsf(URF_FSUB(a.z, c.z)) >= 0.05;                                                  // :62-64
+  if (!h) return false;
+  const float dd = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(c.x, a.x)), dsq(URF_FSUB(c.y, a.y)))));            // :35-37
+  if (!((double)dd < 5.0)) return false;                                                                      // :40
+  const float yj = newY[j], y2 = newY[m], y3 = newY[p3];
+  const float x1 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y2, yj)), dsq(URF_FSUB(z, a.z)))));               // :42-44
+  const float x2 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y3, y2)), dsq(URF_FSUB(c.z, z)))));               // :45-47
+  const float x3 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y3, yj)), dsq(URF_FSUB(c.z, a.z)))));             // :48-50
+  const double num = URF_DSUB(URF_DSUB(dsq(x3), dsq(x1)), dsq(x2));
+  const float den = URF_FMUL(URF_FMUL(-2.0f, x1), x2);
+  const float bk = clamp_unit(URF_D2F(URF_DDIV(num, (double)den)));                                           // :52-56
+  const float al = URF_D2F(deg_d(urfm::acosf_glibc(bk)));                                                     // :58
+  return al <= prm.angleFilter1;                                                                              // :61
+}
+
+// z-zero test centred on local index m (z_zero_method.cpp:21-72)
+URF_HD bool zzero_mark(const DevParams& prm, const float4* ring, int n, int m) {
+  const int cp = prm.curbPoints;
+  if (!(m >= cp && m <= (n - 1) - cp)) return false;
+  const float4 me = ring[m];
+  const float az0 = fabsf(me.z);
+  float max1 = az0, max2 = az0;
+  for (int q = m - 1; q >= m - cp; q--) { const float v = fabsf(ring[q].z); if (v > max1) max1 = v; }        // :38-40
+  for (int q = m + 1; q <= m + cp; q++) { const float v = fabsf(ring[q].z); if (v > max2) max2 = v; }        // :47-49
+  const bool h = (URF_FSUB(max1, az0) >= prm.curbHeight || URF_FSUB(max2, az0) >= prm.curbHeight) &&
+                 (double)fabsf(URF_FSUB(max1, max2)) >= 0.05;                                                 // :67-69
+  if (!h) return false;
+  const float4 lo = ring[m - cp], hi = ring[m + cp];
+  const float dd = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(hi.x, lo.x)), dsq(URF_FSUB(hi.y, lo.y)))));        // :23-25
+  if (!((double)dd < 5.0)) return false;                                                                      // :28
+  float va1 = 0.f, va2 = 0.f, vb1 = 0.f, vb2 = 0.f;
+  for (int q = m - 1; q >= m - cp; q--) { const float4 o = ring[q]; va1 = URF_FADD(va1, URF_FSUB(o.x, me.x)); va2 = URF_FADD(va2, URF_FSUB(o.y, me.y)); }   // :35-37
+  for (int q = m + 1; q <= m + cp; q++) { const float4 o = ring[q]; vb1 = URF_FADD(vb1, URF_FSUB(o.x, me.x)); vb2 = URF_FADD(vb2, URF_FSUB(o.y, me.y)); }   // :44-46
+  const float sc = URF_FDIV(1.0f, (float)cp);
+  va1 = URF_FMUL(sc, va1); va2 = URF_FMUL(sc, va2); vb1 = URF_FMUL(sc, vb1); vb2 = URF_FMUL(sc, vb2);        // :52-55
+  const float dot = URF_FADD(URF_FMUL(va1, vb1), URF_FMUL(va2, vb2));
+  const double nrm = URF_DMUL(URF_DSQRT(URF_DADD(dsq(va1), dsq(va2))), URF_DSQRT(URF_DADD(dsq(vb1), dsq(vb2))));
+  const float bk = clamp_unit(URF_D2F(URF_DDIV((double)dot, nrm)));                                           // :57-61
+  const float al = URF_D2F(deg_d(urfm::acosf_glibc(bk)));                                                     // :63
+  return al <= prm.angleFilter2;                                                                              // :66
+}
+
+// Edge search along one radius-sorted sector (star_shaped_search.cpp:112-150). pts[i] = (r, z, -, -).
+// Returns the local index of the point that gets marked, or -1.
+URF_HD int star_scan_sector(const DevParams& prm, const float4* pts, int n) {
+  if (n <= 1) return -1;                                                // :112
+  float avg = 0.f, dev = 0.f, nan = 0.f;                                // :118
+  float4 q = pts[0];
+  float bx = q.x, by = q.y, ax, ay;
+  for (int i = 1; i < n; i++) {                                         // :123
+    q = pts[i];
+    ax = bx; bx = q.x; ay = by; by = q.y;
+    const float dx = URF_FSUB(bx, ax);
+    const float slp = URF_FDIV(URF_FSUB(by, ay), dx);                   // :27-30
+    if (isnan(slp)) nan = URF_FADD(nan, 1.0f);                          // :131-132
+    else {
+      const float im = URF_FSUB((float)i, nan);                         // i - nan
+      const float c1 = URF_FSUB(im, 1.0f);                              // i - nan - 1
+      const float c2 = URF_FDIV(1.0f, im);                              // 1 / (i - nan)
+      avg = URF_FMUL(avg, c1); avg = URF_FADD(avg, slp); avg = URF_FMUL(avg, c2);                 // :135-137
+      dev = URF_FMUL(dev, c1); dev = URF_FADD(dev, fabsf(URF_FSUB(slp, avg))); dev = URF_FMUL(dev, c2);   // :138-140
+    }
+    const float lhs = URF_FMUL(URF_FMUL(URF_FSUB(URF_FMUL(slp, slp), URF_FMUL(avg, avg)), prm.kdev),
+                               URF_FMUL(dx, prm.kdist));                // :143
+    if (slp > prm.slope_param || (i > prm.dmin && lhs > dev)) return i; // :142-146
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// blindSpots as tables (blind_spots.cpp:7-283). The curb set is fixed while blindSpots runs (it only ever writes 1, and
+// never into a window that holds a 2), so a point ends as road iff some non-blind window start i of either direction
+// accepts the point's ring (no curb in rings 0..k inside the window) and the point's azimuth lies in the window.
+// Curb points are summarised per (ring, integer-degree bin): min and max curb azimuth and a prefix count of non-empty bins.
+struct CurbView {
+  const unsigned* cmin; const unsigned* cmax; const unsigned short* ne;   // tables of one scan
+  URF_HDM float mn(int k, int bin) const { return bitsf(cmin[(size_t)k * kDegBins + bin]); }   // +inf when empty
+  URF_HDM float mx(int k, int bin) const { return bitsf(cmax[(size_t)k * kDegBins + bin]); }   // 0 when empty
+  URF_HDM int cnt(int k, int b0, int b1) const {                          // non-empty bins in [b0, b1)
+    if (b1 <= b0) return 0;
+    return (int)ne[(size_t)k * (kDegBins + 1) + b1] - (int)ne[(size_t)k * (kDegBins + 1) + b0];
+  }
+  // any curb point of ring k with (float)i <= azimuth <= hi   (blind_spots.cpp:107-117,146-157)
+  URF_HDM bool fwd(int k, int i, float hi) const {
+    if (!(hi >= (float)i)) return false;
+    const int fb = hi >= 361.0f ? 361 : (int)hi;
+    if (cnt(k, i, fb) > 0) return true;
+    return fb <= 360 && mn(k, fb) <= hi;
+  }
+  // any curb point of ring k with lo <= azimuth <= (float)i   (blind_spots.cpp:216-227,255-266)
+  URF_HDM bool bwd(int k, int i, float lo) const {
+    if (!(lo <= (float)i)) return false;
+    if (mn(k, i) <= (float)i) return true;                               // azimuth == i exactly
+    if (lo <= 0.0f) return cnt(k, 0, i) > 0;
+    const int lb = (int)lo;
+    if (lb >= i) return false;
+    if (mx(k, lb) >= lo) return true;
+    return cnt(k, lb + 1, i) > 0;
+  }
+};
+
+URF_HD float fwd_hi(const DevParams& prm, int k, int i, double A) {
+  if (k == 0) return URF_FADD((float)i, prm.beamZone);                                     // blind_spots.cpp:107
+  if (i == prm.fwd_special) return 360.0f;                                                 // :136-139
+  return URF_D2F(URF_DADD((double)i, A));                                                  // :142
+}
+URF_HD float bwd_lo(const DevParams& prm, int k, int i, double A) {
+  if (k == 0) return URF_FSUB((float)i, prm.beamZone);                                     // :216
+  if (i == prm.bwd_special) return 0.0f;                                                   // :245-248
+  return URF_D2F(URF_DSUB((double)i, A));                                                  // :251
+}
+
+// arcDistance (blind_spots.cpp:65) and the per-ring width arcDistance / ((maxDistance[k] * M_PI) / 180) (:142)
+URF_HD float arc_distance(const DevParams& prm, float maxdist0) {
+  return URF_D2F(URF_DMUL(URF_DDIV(URF_DMUL((double)maxdist0, URF_PI_D), 180.0), (double)prm.beamZone));
+}
+URF_HD double ring_width(float arc, float maxdist_k) {
+  return URF_DDIV((double)arc, URF_DDIV(URF_DMUL((double)maxdist_k, URF_PI_D), 180.0));
+}
+
+URF_HD bool is_blind(const DevParams& prm, const float* q, int i) {                        // blind_spots.cpp:72-99,181-208
+  if (!prm.blind) return false;
+  const float fi = (float)i, q1 = q[0], q2 = q[1], q3 = q[2], q4 = q[3];
+  if (prm.xDirection == 0)
+    return (q1 != 0.f && q4 != 360.f && (fi <= q1 || fi >= q4)) || (q2 != 180.f && q3 != 180.f && fi >= q2 && fi <= q3);
+  if (prm.xDirection == 1)
+    return (q2 != 180.f && fi >= q2 && i <= 270) || (q1 != 0.f && (fi <= q1 || i >= 270));
+  return (q4 != 360.f && (fi >= q4 || i <= 90)) || (q3 != 180.f && fi <= q3 && i >= 90);
+}
+
+// q1..q4 from the curb bins of ring index 1 (blind_spots.cpp:13-57); which = 0..3
+URF_HD float blind_quarter(const DevParams& prm, const CurbView& cv, int R, int which) {
+  float q = which == 0 ? 0.f : which == 3 ? 360.f : 180.f;
+  if (prm.blind && R > 1) {
+    const int b0 = which * 90, b1 = which == 3 ? 361 : b0 + 90;
+    for (int bin = b0; bin < b1; bin++) {
+      if (cv.cmin[(size_t)kDegBins + bin] == 0x7f800000u) continue;
+      if (which == 0 || which == 2) { const float v = cv.mx(1, bin); if (v > q) q = v; }
+      else { const float v = cv.mn(1, bin); if (v < q) q = v; }
+    }
+  }
+  return q;
+}
+
+// number of rings window start i accepts: forward (blind_spots.cpp:68-174) dir = 0, backward (:177-283) dir = 1
+URF_HD int window_reach(const DevParams& prm, const CurbView& cv, const double* A, const float* q, int R, int dir, int i) {
+  const bool in_loop = dir == 0 ? (i <= prm.fwd_last) : (i >= prm.bwd_first);
+  if (!in_loop || is_blind(prm, q, i)) return 0;
+  int k = 0;
+  for (; k < R; k++) {
+    const bool curb = dir == 0 ? cv.fwd(k, i, fwd_hi(prm, k, i, A[k])) : cv.bwd(k, i, bwd_lo(prm, k, i, A[k]));
+    if (curb) break;
+  }
+  return k;
+}
+
+URF_HD int st_max(const ScanTab& tab, int dir, int lo, int hi) {                           // max reach over [lo, hi]
+  if (hi < lo) return 0;
+  int l = 0;
+  while ((2 << l) <= hi - lo + 1) l++;
+  const unsigned short a = tab.st[dir][l][lo], c = tab.st[dir][l][hi - (1 << l) + 1];
+  return a > c ? a : c;
+}
+
+// road iff a forward or backward window start accepts ring k and contains azimuth a
+URF_HD bool covered_by_window(const DevParams& prm, const ScanTab& tab, int k, float a) {
+  if (!(a >= 0.0f)) return false;
+  const double A = tab.A[k];
+  const double w = k == 0 ? (double)prm.beamZone : A;
+  {  // forward: (float)i <= a and a <= hi(i); hi(i) >= a is monotone (false..false,true..true) in i
+    int imax = (int)a; if (imax > prm.fwd_last) imax = prm.fwd_last;
+    if (imax >= 0) {
+      const double e = ceil((double)a - w);
+      int est = !(e >= 0.0) ? 0 : (e > (double)(imax + 1) ? imax + 1 : (int)e);
+      while (est > 0 && fwd_hi(prm, k, est - 1, A) >= a) est--;
+      while (est <= imax && !(fwd_hi(prm, k, est, A) >= a)) est++;
+      if (est <= imax && st_max(tab, 0, est, imax) > k) return true;
+    }
+  }
+  {  // backward: a <= (float)i and lo(i) <= a; lo(i) <= a is monotone (true..true,false..false) in i
+    int imin = (int)a; if ((float)imin < a) imin++;
+    if (imin < prm.bwd_first) imin = prm.bwd_first;
+    if (imin <= 360) {
+      const double e = floor((double)a + w);
+      int est = !(e <= 360.0) ? 360 : (e < (double)(imin - 1) ? imin - 1 : (int)e);
+      while (est < 360 && bwd_lo(prm, k, est + 1, A) <= a) est++;
+      while (est >= imin && !(bwd_lo(prm, k, est, A) <= a)) est--;
+      if (est >= imin && st_max(tab, 1, imin, est) > k) return true;
+    }
+  }
+  return false;
+}
+
+// integer-degree bin of an azimuth (lidar_segmentation.cpp:318: `alpha >= i && alpha < i + 1`), a >= 0
+URF_HD int deg_bin(float a) { int bin = (int)a; return bin > 360 ? 360 : bin; }
+
+// Marker candidate vertices (lidar_segmentation.cpp:305-351): keys that order points inside the reference's scan order
+URF_HD unsigned long long cut_key(unsigned az_bits, int p) { return ((unsigned long long)az_bits << 32) | (unsigned)p; }
+URF_HD unsigned long long best_key(int k, unsigned az_bits, int p) {
+  return ((unsigned long long)k << 56) | ((unsigned long long)az_bits << 24) | (unsigned)p;
+}
+// road point (lab == 1) of ring k scanned before the first non-road point of its bin?
+URF_HD bool marker_candidate(const ScanTab& tab, int k, int lab, int bin, unsigned az_bits, int p) {
+  if (lab != 1) return false;
+  const int c = tab.cut[bin];
+  return k < c || (k == c && cut_key(az_bits, p) < tab.cutkey[bin]);
+}
+
+}  // namespace urf

@@ -16,8 +16,10 @@
 
 #if defined(__CUDACC__)
 #define URF_HD __host__ __device__ __forceinline__
+#define URF_HDM __host__ __device__ __forceinline__   /* member functions */
 #else
 #define URF_HD static inline
+#define URF_HDM inline
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -100,17 +100,19 @@ def make_scan(shape: SensorShape | str, seed: int = 0, order: str = "column", no
     pts[:, 1] = (t * dy).astype(np.float32)
     pts[:, 2] = (t * dz).astype(np.float32)
     pts[:, 3] = rng.uniform(0.0, 255.0, t.size).astype(np.float32)
-    _detie_radius(pts)
+    _detie_radius(pts, seed)
     if drop > 0:
         dead = rng.random(t.size) < drop
         pts[dead, :3] = 0.0
     return pts
 
 
-def _detie_radius(pts: np.ndarray) -> None:
+def _detie_radius(pts: np.ndarray, seed: int = 0) -> None:
     """Make the float32 planar radius sqrtf(x*x+y*y) unique across the scan, so that no star-shaped sector
-    (star_shaped_search.cpp:109, std::sort by r) ever holds an exact tie (SURVEY.md §7.4 H3)."""
-    for _ in range(8):
+    (star_shaped_search.cpp:109, std::sort by r) ever holds an exact tie (SURVEY.md §7.4 H3). Colliding points are
+    pushed outwards by a random sub-millimetre amount (dense wall returns need more than a few ulps)."""
+    rng = np.random.default_rng(1_000_003 + seed)
+    for _ in range(32):
         x, y = pts[:, 0], pts[:, 1]
         r = np.sqrt(x * x + y * y)                       # float32 arithmetic, same ops as the reference
         o = np.argsort(r, kind="stable")
@@ -119,7 +121,7 @@ def _detie_radius(pts: np.ndarray) -> None:
         dup[o[1:]] = rs[1:] == rs[:-1]
         if not dup.any():
             return
-        k = np.float32(1.0) + np.float32(2.0 ** -21) * (1 + np.arange(int(dup.sum())) % 7).astype(np.float32)
+        k = np.float32(1.0) + np.float32(2.0 ** -21) * rng.integers(1, 1024, int(dup.sum())).astype(np.float32)
         pts[dup, 0] *= k
         pts[dup, 1] *= k
     raise RuntimeError("could not de-tie radii")
@@ -143,5 +145,5 @@ def random_cloud(n: int, seed: int = 0, rings: int = 8, extent: float = 40.0) ->
     pts[:, 1] = t * np.cos(e) * np.sin(az)
     pts[:, 2] = t * np.sin(e)
     pts[:, 3] = rng.uniform(0, 255, n)
-    _detie_radius(pts)
+    _detie_radius(pts, seed)
     return pts
