@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — scans/s of the per-scan road/curb classification path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA path (liburf_b200.so through the C-ABI)
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] the reference's own CPU implementation, host cores
+
+A "step" is one pass of the hot path over one batch of `--batch` distinct synthetic OS1-64 scans (BASELINE config 2:
+64 rings x 2048 columns = 131,072 points per scan, all three detectors + blindSpots, full-ROI preset so every point
+takes part). N > 1 is launched by torchrun (one rank per GPU); scans are independent units, so ranks just process their
+own batches (weak scaling, no data-path collective) and NCCL carries only the barrier and the max-over-ranks time.
+
+One JSON line on stdout (rank 0): value = whole-job scans/s with inputs resident in HBM, timed with CUDA events on the
+library's stream; e2e = the same metric through urf_process_batch with pinned HOST buffers (H2D + D2H inside the timed
+region); roofline = the dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM peak;
+cpu_baseline = the reference's CPU path timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from urban_road_filter_b200 import FULL_ROI, UrfResult, make_params  # noqa: E402
+from urban_road_filter_b200.synth import SHAPES, make_scan  # noqa: E402
+
+ALGO_BYTES_PER_POINT = 20          # 16 B float4 read + 4 B int32 label written, per input point
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def bench_params(shape_key: str):
+    sh = SHAPES[shape_key]
+    return make_params(channels=sh.channels, interval=sh.interval, **FULL_ROI)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref = unmodified reference sources; else the oracle port)
+def _cpu_worker(args):
+    shape_key, seed, repeat, use_ref = args
+    sys.path.insert(0, ROOT)
+    from oracle.pyoracle import PortOracle, RefOracle
+    pts = make_scan(shape_key, seed)
+    prm = bench_params(shape_key)
+    orc = RefOracle() if use_ref else PortOracle()
+    orc.time(pts, prm, 1)                      # untimed first call: page-faults the reference's big allocations
+    return orc.time(pts, prm, repeat), repeat
+
+
+def cpu_reference_rate(shape_key: str, workers: int, repeat: int, seed0: int = 10_000):
+    """Aggregate scans/s of `workers` processes, each running the single-threaded reference on its own scan."""
+    import multiprocessing as mp
+    from oracle.pyoracle import RefOracle
+    use_ref = RefOracle.available()
+    ctx = mp.get_context("fork" if "torch" not in sys.modules or not _cuda_initialised() else "spawn")
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_cpu_worker, [(shape_key, seed0 + w, repeat, use_ref) for w in range(workers)])
+    rate = sum(r / s for s, r in res)
+    per_scan_ms = 1e3 * statistics.median(s / r for s, r in res)
+    return rate, per_scan_ms, ("reference" if use_ref else "port")
+
+
+def _cuda_initialised() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_initialized()
+    except Exception:
+        return False
+
+
+def usable_cores() -> int:
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        cores = min(cores, max(1, int(psutil.virtual_memory().available / (1.5 * 2**30))))   # ~0.5 GB per reference process
+    except Exception:
+        pass
+    return max(1, min(cores, 64))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled in the background (recipe of B200_PROFILING.md)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[2])); mx.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if one is recorded."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0            # the reference arm is a host-CPU measurement: rank 0 alone runs and prints it
+    cores = usable_cores()
+    n = SHAPES[args.shape].rings * SHAPES[args.shape].cols
+    for _ in range(args.warmup):
+        cpu_reference_rate(args.shape, cores, 1)
+    t0 = time.perf_counter()
+    rates, kind = [], "reference"
+    for k in range(args.steps):
+        r, _, kind = cpu_reference_rate(args.shape, cores, 1, seed0=20_000 + 1000 * k)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = statistics.median(rates)
+    line = {
+        "impl": "reference", "metric": "scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": f"{SHAPES[args.shape].name} {n}-pt scans, all three detectors + blindSpots, full-ROI preset "
+                               f"(BASELINE config 2); one step = {cores} scans, one per host core",
+                   "points_per_scan": n, "mpoints_per_sec": value * n / 1e6},
+        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores} single-threaded processes x 1 scan per step, median of {args.steps} steps"},
+        "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="urf", choices=["urf", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="scans per step and per GPU")
+    ap.add_argument("--shape", default="C2", choices=sorted(SHAPES))
+    ap.add_argument("--cpu-repeat", type=int, default=3, help="scans per host core in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "urf" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N == 1 only), before CUDA is initialised in this process
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = usable_cores()
+        rate, per_scan_ms, kind = cpu_reference_rate(args.shape, cores, args.cpu_repeat)
+        cpu_baseline = {"value": rate, "unit": "scans/s", "cores": cores, "kind": kind,
+                        "sample": f"{cores} single-threaded processes x {args.cpu_repeat} scans each (after one untimed scan), "
+                                  f"median {per_scan_ms:.0f} ms per scan per core"}
+
+    import torch
+    import torch.distributed as dist
+    from urban_road_filter_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl urf needs a CUDA device: urban_road_filter_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    sh = SHAPES[args.shape]
+    B, n = args.batch, sh.rings * sh.cols
+    prm = bench_params(args.shape)
+    clouds = [make_scan(args.shape, 1000 * rank + b) for b in range(B)]
+    det = api.Detector(max_points=n, max_batch=B, device=local, params=prm)
+    lib, ctx = det.lib, det._ctx
+    S = n
+    x = torch.empty((B, S, 4), dtype=torch.float32, device="cuda")
+    for b, c in enumerate(clouds):
+        x[b].copy_(torch.from_numpy(c))
+    labels = torch.empty((B, S), dtype=torch.int32, device="cuda")
+    ns = (C.c_int * B)(*([n] * B))
+    outs = (UrfResult * B)()
+    stream = torch.cuda.ExternalStream(lib.urf_stream(ctx), device=torch.device("cuda", local))
+    det.set_option(1, 1)            # per-kernel CUDA events on the library's stream
+
+    def step_device():
+        rc = lib.urf_enqueue_batch_device(ctx, x.data_ptr(), S, ns, B, labels.data_ptr())
+        assert rc == 0, lib.urf_last_cuda_error(ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        step_device()
+        assert lib.urf_finish_batch_device(ctx, outs) == 0
+    # ---- timed region 1: inputs resident in HBM --------------------------------------------------------------------
+    ktimes: dict[str, float] = {}
+    launches = 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        assert lib.urf_finish_batch_device(ctx, outs) == 0      # syncs the stream; lets us read this step's kernel events
+        launches += det.last_launch_count()
+        for name, ms in det.kernel_times():
+            ktimes[name] = ktimes.get(name, 0.0) + ms
+    e1.record(stream)
+    barrier()
+    t_w1 = time.time()
+    dev_ms = e0.elapsed_time(e1)
+    n_road = sum(o.n_road for o in outs)
+    # ---- timed region 2: end to end through the host-buffer C-ABI call ---------------------------------------------
+    det.set_option(1, 0)
+    h_in = [torch.from_numpy(c).pin_memory() for c in clouds]
+    h_lab = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(B)]
+    ptrs = (C.c_void_p * B)(*[t.data_ptr() for t in h_in])
+    res = (UrfResult * B)()
+    for b in range(B):
+        res[b].label = C.cast(h_lab[b].data_ptr(), C.POINTER(C.c_int32))
+
+    def step_e2e():
+        rc = lib.urf_process_batch(ctx, ptrs, ns, B, res)
+        assert rc == 0, lib.urf_last_cuda_error(ctx)
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t_w2 = time.time()
+    clocks = sampler.stop(t_w0, t_w2)
+    assert sum(r.n_road for r in res) == n_road, "device-resident and host-buffer paths disagree"
+
+    # max over ranks
+    tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        K = args.steps
+        scans = world * B * K
+        value = scans / (dev_ms / 1e3)
+        e2e = scans / (e2e_ms / 1e3)
+        peak, peak_src = hbm_peak()
+        dom = max(ktimes, key=ktimes.get)
+        dom_ms = ktimes[dom] / K
+        algo_bytes = ALGO_BYTES_PER_POINT * n * B              # per launch: every kernel launch covers the whole batch
+        achieved = algo_bytes / (dom_ms / 1e3) / 1e9
+        ksum = sum(ktimes.values())
+        line = {
+            "metric": "scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
+            "data": "synthetic",
+            "config": {"workload": f"{sh.name} {n}-pt scans, all three detectors + blindSpots, full-ROI preset (BASELINE config 2); "
+                                   f"one step = a batch of {B} distinct scans per GPU",
+                       "batch_per_gpu": B, "points_per_scan": n, "mpoints_per_sec": value * n / 1e6,
+                       "l2": f"inputs of one step are {B * n * 16 / 2**20:.0f} MiB per GPU (> 126 MB L2), no reuse between steps",
+                       "parallelism": f"scan-batch sharding x{world}, no data-path collective"},
+            "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": B * n * 16,
+                    "d2h_bytes_per_step": B * n * 4 + B * C.sizeof(UrfResult), "mpoints_per_sec": e2e * n / 1e6},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": dom_ms,
+                         "kernel_share_of_step": ktimes[dom] / ksum,
+                         "pipeline_frac": (algo_bytes / (dev_ms / K / 1e3) / 1e9) / peak,
+                         "kernel_ms_per_step": {k: v / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])}},
+            "clocks": clocks,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    det.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,189 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (urban_road_filter_b200.api.Detector -> liburf_b200.so),
+against the CPU oracle on the same seeded inputs and against the golden fixtures generated from the unmodified reference.
+Bar: per-point labels, ring ids, emission order bit-exact; marker vertices within 1e-4 m (they are in fact bit-exact)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.pyoracle import PortOracle
+from urban_road_filter_b200 import FULL_ROI, make_params
+from urban_road_filter_b200 import api
+from urban_road_filter_b200.synth import SHAPES, make_scan, random_cloud
+
+from util import Golden, assert_matches_golden, golden_names, stage_diffs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def det():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    d = api.Detector(max_points=300_000, max_batch=8)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def port():
+    return PortOracle()
+
+
+class GpuDebug:
+    """Stage intermediates of scan 0 of the last call, re-indexed by input index like the oracle's debug run."""
+
+    def __init__(self, det, res, n):
+        N = res.n_order
+        self.__dict__.update(res.__dict__ if hasattr(res, "__dict__") else {s: getattr(res, s) for s in res.__slots__})
+        a = det.debug_fetch(0, 0, np.float32, n)
+        self.alpha_v = np.where(a < 0, np.nan, a).astype(np.float32)
+        self.star_mark = det.debug_fetch(0, 1, np.uint8, n).astype(np.int8)
+        idx = det.debug_fetch(0, 7, np.int32, N)
+        self.az = np.full(n, np.nan, np.float32)
+        self.d2 = np.full(n, np.nan, np.float32)
+        self.az[idx] = det.debug_fetch(0, 4, np.float32, N)
+        self.d2[idx] = det.debug_fetch(0, 5, np.float32, N)
+        self.det_label = None      # blabel is overwritten with final labels by k_label
+        self.ring_angle = None
+
+
+def check(det, port, pts, prm, exact=False):
+    det.set_params(prm)
+    det.set_option(0, 1 if exact else 0)
+    r = det.filtered(pts)
+    det.set_option(0, 0)
+    o = port.run(pts, prm, debug=True)
+    if o.status == 0 and r.status == 0:
+        g = GpuDebug(det, r, pts.shape[0])
+        bad = stage_diffs(o, g, pts.shape[0])
+    else:
+        bad = [] if o.status == r.status else ["status"]
+    assert bad == [], f"stages differing from the oracle: {bad}"
+    return r
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_gpu_matches_reference_golden(det, name):
+    g = Golden(name)
+    det.set_params(g.params())
+    assert_matches_golden(g, det.filtered(g.cloud), api.build_markers)
+
+
+@pytest.mark.parametrize("cfg,seed,roi,order", [("C1", 0, "def", "column"), ("C1", 1, "full", "ring"), ("C2", 2, "full", "column"),
+                                                 ("C2", 3, "def", "ring"), ("C3", 4, "full", "column"), ("C4", 5, "full", "ring")])
+def test_gpu_shapes(det, port, cfg, seed, roi, order):
+    sh = SHAPES[cfg]
+    check(det, port, make_scan(cfg, seed, order=order), make_params(channels=sh.channels, interval=sh.interval, **(FULL_ROI if roi == "full" else {})))
+
+
+@pytest.mark.parametrize("mask", range(16))
+def test_gpu_detector_toggles(det, port, mask):
+    check(det, port, make_scan("C1", 3), make_params(x_zero_method=mask & 1, z_zero_method=(mask >> 1) & 1,
+                                                      star_shaped_method=(mask >> 2) & 1, blind_spots=(mask >> 3) & 1, **FULL_ROI))
+
+
+@pytest.mark.parametrize("kw", [dict(xDirection=1), dict(xDirection=2, starbeam_filter=1), dict(curb_points=1), dict(curb_points=30),
+                                dict(beamZone=10), dict(beamZone=45.5), dict(beamZone=100), dict(beamZone=360),
+                                dict(curb_height=0.2), dict(curb_slope_deg=5), dict(kdev_param=0.5, kdist_param=10, dmin_param=3),
+                                dict(interval=0.05), dict(interval=3.0), dict(channels=11), dict(channels=3), dict(channels=1)])
+def test_gpu_param_sweep(det, port, kw):
+    check(det, port, make_scan("C1", 3), make_params(**kw, **FULL_ROI))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_gpu_random_clouds_and_exact_registration(det, port, seed):
+    pts = random_cloud(5000, seed)
+    a = check(det, port, pts, make_params(**FULL_ROI))
+    b = check(det, port, pts, make_params(**FULL_ROI), exact=True)
+    assert b.flags & 1
+    assert np.array_equal(a.label, b.label)
+    check(det, port, random_cloud(20000, seed, rings=40), make_params())
+
+
+def test_gpu_speculation_failure_is_repaired(det, port):
+    r = check(det, port, random_cloud(5000, 5), make_params(**FULL_ROI))
+    assert r.flags & 1        # exact registration ran after the failed verification
+
+
+def test_gpu_zero_elevation_quirk(det, port):
+    pts = make_scan("C1", 2)[:6000].copy()
+    pts[5] = (1e-5, 2e-5, -1.5, 1.0)
+    pts[900] = (3e-5, -1e-5, -1.7, 1.0)
+    r = check(det, port, pts, make_params(**FULL_ROI))
+    assert r.flags & 1
+
+
+def test_gpu_edge_cases(det, port):
+    prm = make_params(**FULL_ROI)
+    det.set_params(prm)
+    r = det.filtered(np.zeros((0, 4), np.float32))
+    assert r.status == 1 and r.n_roi == 0
+    r = det.filtered(make_scan("C1", 0)[:29])
+    assert r.status == 1 and np.all(r.label == -1)
+    nan = make_scan("C1", 0)[:2000].copy()
+    nan[::7, 0] = np.nan
+    nan[3::11, 2] = np.inf
+    check(det, port, nan, prm)
+    check(det, port, make_scan("C1", 0), make_params(min_x=100, max_x=101))      # empty ROI
+    with pytest.raises(api.UrfError):
+        det.filtered(np.zeros((400_000, 4), np.float32))                         # larger than the ctx capacity
+
+
+def test_gpu_batch_equals_single(det, port):
+    """Ragged batch: every scan of a batch gets the result it gets alone (scans are independent units)."""
+    clouds = [make_scan("C1", 1), make_scan("C2", 2, order="ring"), random_cloud(5000, 5), make_scan("C1", 4)[:29],
+              make_scan("C3", 3), np.zeros((0, 4), np.float32), make_scan("C1", 7)[:12345]]
+    prm = make_params(**FULL_ROI)
+    det.set_params(prm)
+    rs = det.filtered_batch(clouds)
+    for c, r in zip(clouds, rs):
+        o = port.run(c, prm)
+        assert o.status == r.status
+        if o.status == 0:
+            assert stage_diffs(o, r, c.shape[0]) == []
+
+
+def test_gpu_device_resident_entry_point(det, port):
+    """urf_process_batch_device: inputs and labels stay in device memory (what bench.py times as `value`)."""
+    prm = make_params(**FULL_ROI)
+    det.set_params(prm)
+    clouds = [make_scan("C2", s) for s in range(3)]
+    S = 131072
+    x = torch.zeros((3, S, 4), dtype=torch.float32, device="cuda")
+    for b, c in enumerate(clouds):
+        x[b, : c.shape[0]] = torch.from_numpy(c).cuda()
+    lab = torch.full((3, S), -7, dtype=torch.int32, device="cuda")
+    n = (C.c_int * 3)(*[c.shape[0] for c in clouds])
+    from urban_road_filter_b200 import UrfResult
+    outs = (UrfResult * 3)()
+    torch.cuda.synchronize()
+    rc = det.lib.urf_process_batch_device(det._ctx, x.data_ptr(), S, n, 3, lab.data_ptr(), outs)
+    assert rc == 0
+    assert det.last_launch_count() >= 15 and det.last_device_ms() > 0
+    host = lab.cpu().numpy()
+    for b, c in enumerate(clouds):
+        o = port.run(c, prm)
+        assert np.array_equal(host[b, : c.shape[0]], o.label)
+        assert (outs[b].n_road, outs[b].n_curb, outs[b].n_vert) == (o.n_road, o.n_curb, o.n_vert)
+
+
+def test_gpu_full_size_c5_and_properties(port):
+    """BASELINE config 5 (256 rings x 4096 columns = 1,048,576 points), every detector ablation, vs the oracle; plus
+    size-independent properties: idempotence (same cloud twice -> same labels) and batch-order independence."""
+    sh = SHAPES["C5"]
+    pts = make_scan("C5", 0)
+    d = api.Detector(max_points=pts.shape[0], max_batch=2)
+    try:
+        for kw in (dict(), dict(x_zero_method=0, z_zero_method=0), dict(star_shaped_method=0, z_zero_method=0), dict(star_shaped_method=0, x_zero_method=0)):
+            prm = make_params(channels=sh.channels, interval=sh.interval, **kw, **FULL_ROI)
+            d.set_params(prm)
+            r = d.filtered(pts)
+            o = port.run(pts, prm)
+            assert stage_diffs(o, r, pts.shape[0]) == []
+        a, b = d.filtered_batch([pts, pts[::-1].copy()])
+        again = d.filtered(pts)
+        assert np.array_equal(a.label, again.label) and np.array_equal(a.vert, again.vert)
+        assert a.n_roi == b.n_roi
+    finally:
+        d.close()

@@ -64,6 +64,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.urf_test_math.argtypes = [ip, ip, vp, vp, vp, ip]
     lib.urf_debug_fetch.argtypes = [vp, ip, ip, vp, C.c_size_t]
     lib.urf_debug_sizeof_tab.restype = C.c_size_t
+    lib.urf_profile_count.argtypes = [vp]
+    lib.urf_profile_get.argtypes = [vp, ip, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -200,6 +202,15 @@ class Detector:
 
     def last_launch_count(self) -> int:
         return int(self.lib.urf_last_launch_count(self._ctx))
+
+    def kernel_times(self) -> list[tuple[str, float]]:
+        """(kernel name, device ms) of the last call; needs set_option(1, 1) before the call."""
+        out = []
+        for i in range(self.lib.urf_profile_count(self._ctx)):
+            name, ms = C.c_char_p(), C.c_float()
+            self._check(self.lib.urf_profile_get(self._ctx, i, C.byref(name), C.byref(ms)), "urf_profile_get")
+            out.append((name.value.decode(), float(ms.value)))
+        return out
 
     def debug_fetch(self, scan: int, what: int, dtype, count: int) -> np.ndarray:
         a = np.zeros(max(count, 1), dtype)

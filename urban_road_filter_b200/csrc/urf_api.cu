@@ -33,6 +33,11 @@ struct urf_ctx {
   bool timing_valid = false;
   std::string err;
   std::vector<void*> allocs;
+  // optional per-kernel CUDA-event timing (urf_set_option(ctx, 1, 1)); events live on the ctx stream
+  bool profile = false;
+  std::vector<cudaEvent_t> kev;
+  std::vector<const char*> knames;
+  int kcount = 0;
 };
 
 namespace {
@@ -66,31 +71,45 @@ int launch_pipeline(urf_ctx* ctx, int B, int S, bool want_order) {
   const int T = (S + kChunk - 1) / kChunk;
   if (T > ctx->Tmax) return URF_ERR_CAPACITY;
   int L = 0;
+  ctx->kcount = 0;
   const dim3 gpts((S + 255) / 256, B), gchunk((T + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
+  // K(name, launch): one kernel launch; with profiling on, an event is recorded in front of it
+#define K(name, ...)                                                                         \
+  do {                                                                                       \
+    if (ctx->profile) {                                                                      \
+      if ((int)ctx->kev.size() <= ctx->kcount) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->kev.push_back(e); ctx->knames.push_back(name); } \
+      ctx->knames[ctx->kcount] = name;                                                       \
+      CK(cudaEventRecord(ctx->kev[ctx->kcount], st));                                        \
+      ctx->kcount++;                                                                         \
+    }                                                                                        \
+    __VA_ARGS__;                                                                             \
+    L++;                                                                                     \
+  } while (0)
   CK(cudaEventRecord(ctx->ev0, st));
-  k_reset<<<dim3(8, B), 256, 0, st>>>(buf, dp); L++;
-  k_points<<<gpts, 256, 0, st>>>(buf, dp, S); L++;
-  k_register<<<B, 256, 0, st>>>(buf, dp, S); L++;
-  k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 0); L++;
+  K("k_reset", k_reset<<<dim3(8, B), 256, 0, st>>>(buf, dp));
+  K("k_points", k_points<<<gpts, 256, 0, st>>>(buf, dp, S));
+  K("k_register", k_register<<<B, 256, 0, st>>>(buf, dp, S));
+  K("k_assign", k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 0));
   if (!dp.force_exact) {
-    k_register_exact<<<B, 256, 0, st>>>(buf, dp, S); L++;
-    k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 1); L++;
-    k_mark_exact<<<(B + 127) / 128, 128, 0, st>>>(buf, B); L++;
+    K("k_register_exact", k_register_exact<<<B, 256, 0, st>>>(buf, dp, S));
+    K("k_assign_redo", k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 1));
+    K("k_mark_exact", k_mark_exact<<<(B + 127) / 128, 128, 0, st>>>(buf, B));
   }
-  k_scan_offsets<<<B, 1024, 32 * kKeys * sizeof(unsigned), st>>>(buf, T); L++;
-  k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T); L++;
+  K("k_scan_offsets", k_scan_offsets<<<B, 1024, 32 * kKeys * sizeof(unsigned), st>>>(buf, T));
+  K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
   if (dp.star) {
-    k_star_sort<<<dim3(kSectKeys, B), 128, 0, st>>>(buf, S); L++;
-    k_star_scan<<<dim3((kSectKeys + 31) / 32, B), 32, 0, st>>>(buf, dp, S); L++;
+    K("k_star_sort", k_star_sort<<<dim3(kSectKeys, B), 128, 0, st>>>(buf, S));
+    K("k_star_scan", k_star_scan<<<dim3((kSectKeys + 31) / 32, B), 32, 0, st>>>(buf, dp, S));
   }
-  k_ring_detect<<<gpts, 256, 0, st>>>(buf, dp, S); L++;
-  k_tables<<<B, 384, 0, st>>>(buf, dp); L++;
-  k_label<<<gpts, 256, 0, st>>>(buf, dp, S); L++;
-  k_cutkey<<<gpts, 256, 0, st>>>(buf, S); L++;
-  k_dmax<<<gpts, 256, 0, st>>>(buf, S); L++;
-  k_best<<<gpts, 256, 0, st>>>(buf, S); L++;
-  k_verts<<<B, 384, 0, st>>>(buf, S); L++;
-  if (want_order) { k_sort_rings<<<dim3(dp.channels, B), 256, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S); L++; }
+  K("k_ring_detect", k_ring_detect<<<gpts, 256, 0, st>>>(buf, dp, S));
+  K("k_tables", k_tables<<<B, 384, 0, st>>>(buf, dp));
+  K("k_label", k_label<<<gpts, 256, 0, st>>>(buf, dp, S));
+  K("k_cutkey", k_cutkey<<<gpts, 256, 0, st>>>(buf, S));
+  K("k_dmax", k_dmax<<<gpts, 256, 0, st>>>(buf, S));
+  K("k_best", k_best<<<gpts, 256, 0, st>>>(buf, S));
+  K("k_verts", k_verts<<<B, 384, 0, st>>>(buf, S));
+  if (want_order) K("k_sort_rings", k_sort_rings<<<dim3(dp.channels, B), 256, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S));
+#undef K
   CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaGetLastError());
   ctx->launches = L;
@@ -227,6 +246,7 @@ void urf_destroy(urf_ctx* ctx) {
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->h_n) cudaFreeHost(ctx->h_n);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -248,10 +268,11 @@ int urf_get_params(const urf_ctx* ctx, urf_params* p) {
   return URF_OK;
 }
 
-// test/diagnostic options: 0 = force exact ring registration (0/1)
+// test/diagnostic options: 0 = force exact ring registration (0/1); 1 = per-kernel CUDA-event timing (0/1)
 int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (!ctx) return URF_ERR_INVALID;
   if (option == 0) { ctx->dp.force_exact = value != 0; return URF_OK; }
+  if (option == 1) { ctx->profile = value != 0; return URF_OK; }
   return URF_ERR_INVALID;
 }
 
@@ -267,6 +288,18 @@ float urf_last_device_ms(const urf_ctx* c) {
 }
 
 int urf_last_launch_count(const urf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// With option 1 on: number of kernels of the last call, and name / device milliseconds of kernel `idx` (event before it to
+// the event before the next kernel, or to the end-of-pipeline event for the last one). Waits for the stream.
+int urf_profile_count(const urf_ctx* ctx) { return ctx && ctx->profile ? ctx->kcount : 0; }
+int urf_profile_get(urf_ctx* ctx, int idx, const char** name, float* ms) {
+  if (!ctx || !ctx->profile || idx < 0 || idx >= ctx->kcount) return URF_ERR_INVALID;
+  CK(cudaEventSynchronize(ctx->ev1));
+  cudaEvent_t next = idx + 1 < ctx->kcount ? ctx->kev[idx + 1] : ctx->ev1;
+  CK(cudaEventElapsedTime(ms, ctx->kev[idx], next));
+  if (name) *name = ctx->knames[idx];
+  return URF_OK;
+}
 
 int urf_enqueue_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch, int32_t* d_label) {
   if (!ctx || !d_xyzi || !n || !d_label || batch < 1 || stride_points < 1) return URF_ERR_INVALID;
