@@ -74,8 +74,7 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     n_roi++;
     const float a = elev_alpha(x, y, z);
     alpha[i] = a;
-    int bin = (int)(a * (kElevBins / 180.0f));
-    bin = bin < 0 ? 0 : (bin > kElevBins ? kElevBins : bin);
+    const int bin = elev_bin(a);
     if (firstidx[bin] > (unsigned)i) firstidx[bin] = (unsigned)i;
     if (a == 0.0f) flags |= F_ZERO_ALPHA;
   }
@@ -116,14 +115,17 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
   };
   publish();
   // ---- k_assign (+ verify, + repair)
+  std::vector<unsigned short> lut(kElevBins + 1);
   auto assign_all = [&](bool verify) {
     bool viol = false;
+    for (int e = 0; e <= kElevBins; e++) lut[e] = (unsigned short)ring_lut_entry(tab.angle, R, prm.interval, e);
     for (int i = 0; i < n; i++) {
       const float a = alpha[i];
       ringid[i] = -1; sect[i] = -1;
       if (a < 0.0f) continue;
-      int lo;
-      ringid[i] = (short)assign_ring(tab.angle, R, a, prm.interval, &lo);
+      int lo, lo_ref;
+      ringid[i] = (short)assign_ring_from(tab.angle, R, a, prm.interval, lut[elev_bin(a)], &lo);
+      if (ringid[i] != assign_ring(tab.angle, R, a, prm.interval, &lo_ref) || lo != lo_ref) return true;   // LUT search != binary search: report as violation (tests fail)
       if (verify && registration_violation(tab.angle, tab.regidx, tab.regorder, R, prm.channels, prm.interval, a, i, lo)) viol = true;
       if (prm.star) sect[i] = (short)star_sector(prm, xyzi[4 * i], xyzi[4 * i + 1], beam_d, beam_o, beam_yx);
     }
@@ -160,13 +162,14 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     for (int s = 0; s < kSectKeys; s++) {
       const int base = sect_start[s], m = sect_start[s + 1] - base;
       if (m <= 0) continue;
-      std::vector<unsigned long long> keys(m);
-      for (int t = 0; t < m; t++) keys[t] = ((unsigned long long)fbits(spt[base + t].x) << 32) | (unsigned)t;
+      // the GPU's sector partition is unordered; the sort key breaks radius ties by input index (= push_back order)
+      std::vector<std::pair<unsigned long long, int>> keys(m);
+      for (int t = 0; t < m; t++) keys[t] = {((unsigned long long)fbits(spt[base + t].x) << 32) | (unsigned)URF_F2I(spt[base + t].z), t};
       std::sort(keys.begin(), keys.end());
       std::vector<float4> sorted(m);
       for (int t = 0; t < m; t++) {
-        sorted[t] = spt[base + (unsigned)keys[t]];
-        if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(keys[t] >> 32)) flags |= F_TIE_SECTOR;
+        sorted[t] = spt[base + keys[t].second];
+        if (t > 0 && (unsigned)(keys[t - 1].first >> 32) == (unsigned)(keys[t].first >> 32)) flags |= F_TIE_SECTOR;
       }
       const int hit = star_scan_sector(prm, sorted.data(), m);
       if (hit >= 0) mark[URF_F2I(sorted[hit].z)] = 2;
@@ -225,53 +228,65 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     for (int bin = 0; bin < kDegBins; bin++) { ne[(size_t)k * (kDegBins + 1) + bin] = run; run += cmin[(size_t)k * kDegBins + bin] != 0x7f800000u; }
     ne[(size_t)k * (kDegBins + 1) + kDegBins] = run;
   }
+  std::vector<float> Tf((size_t)kDegBins * prm.channels, 0.f), Tb((size_t)kDegBins * prm.channels, 0.f);
+  SparseMax* spm = new SparseMax();
   {
     const float arc = arc_distance(prm, bitsf(tab.maxdist[0]));
     for (int k = 0; k < R; k++) tab.A[k] = ring_width(arc, bitsf(tab.maxdist[k]));
     for (int w = 0; w < 4; w++) tab.q[w] = blind_quarter(prm, cv, R, w);
+    // k_reach: cells (dir, i, k) in parallel on the GPU, minimum kept with atomicMin
+    for (int dir = 0; dir < 2; dir++)
+      for (int i = 0; i < kDegBins; i++) {
+        tab.reach[dir][i] = R;
+        if (dir == 0 ? i > prm.fwd_last : i < prm.bwd_first) continue;
+        for (int k = R - 1; k >= 0; k--) if (window_blocked(prm, cv, tab.A[k], dir, i, k)) tab.reach[dir][i] = k;
+      }
+    // k_tab2
+    for (int k = 0; k < R; k++) build_T_column(prm, tab.reach[0], tab.reach[1], tab.q, k, tab.A[k], Tf.data() + k, Tb.data() + k, prm.channels);
+    // cross-check tables: the sequential reach (window_reach) and the window-search formulation of the per-point test
     for (int dir = 0; dir < 2; dir++)
       for (int i = 0; i < kDegBins; i++) {
         const int reach = window_reach(prm, cv, tab.A, tab.q, R, dir, i);
-        tab.reach[dir][i] = (unsigned short)reach; tab.st[dir][0][i] = (unsigned short)reach;
+        spm->st[dir][0][i] = (unsigned short)reach;
       }
     for (int l = 1; l < kStLevels; l++)
       for (int dir = 0; dir < 2; dir++)
         for (int i = 0; i < kDegBins; i++) {
           const int j = i + (1 << (l - 1));
-          const unsigned short a = tab.st[dir][l - 1][i], c = j < kDegBins ? tab.st[dir][l - 1][j] : (unsigned short)0;
-          tab.st[dir][l][i] = a > c ? a : c;
+          const unsigned short a = spm->st[dir][l - 1][i], c = j < kDegBins ? spm->st[dir][l - 1][j] : (unsigned short)0;
+          spm->st[dir][l][i] = a > c ? a : c;
         }
   }
 
-  // ---- k_label, k_cutkey, k_dmax, k_best, k_verts
-  for (int i = 0; i < kDegBins; i++) { tab.cut[i] = 0x7fffffff; tab.cutkey[i] = ~0ull; tab.dmax[i] = 0u; tab.best[i] = ~0ull; }
+  // ---- k_label, k_dmax, k_best, k_verts
+  for (int i = 0; i < kDegBins; i++) { tab.cutbest[i] = ~0ull; tab.dmax[i] = 0u; tab.best[i] = ~0ull; }
   std::vector<int> pring(std::max(N, 1));
   for (int k = 0; k < R; k++) for (int p = ring_start[k]; p < ring_start[k + 1]; p++) pring[p] = k;
+  int formulation_mismatch = 0;
+  std::vector<int> road;
   for (int p = 0; p < N; p++) {
     const int k = pring[p];
     int lab = blabel[p];
-    if (lab != 2 && covered_by_window(prm, tab, k, az[p])) lab = 1;
+    const bool cov = covered_T(Tf.data(), Tb.data(), prm.channels, k, az[p]);
+    if (cov != covered_by_window(prm, *spm, tab.A[k], k, az[p])) formulation_mismatch++;
+    if (lab != 2 && cov) lab = 1;
     blabel[p] = (unsigned char)lab;
     const int idx = URF_F2I(bpt[p].w);
     if (out->label) out->label[idx] = lab;
     if (out->ring) out->ring[idx] = k;
-    if (lab == 1) out->n_road++; else if (lab == 2) out->n_curb++;
-    if (lab != 1 && az[p] >= 0.0f) { const int bin = deg_bin(az[p]); if (tab.cut[bin] > k) tab.cut[bin] = k; }
+    if (lab == 1) { out->n_road++; road.push_back(p); } else if (lab == 2) out->n_curb++;
+    if (lab != 1 && az[p] >= 0.0f) { const int bin = deg_bin(az[p]); tab.cutbest[bin] = std::min(tab.cutbest[bin], best_key(k, fbits(az[p]), p)); }
   }
-  for (int p = 0; p < N; p++) {
+  if (formulation_mismatch) return -100;      // threshold tables disagree with the window search: a logic bug
+  for (int p : road) {
     if (!(az[p] >= 0.0f)) continue;
     const int bin = deg_bin(az[p]);
-    if (blabel[p] != 1 && pring[p] == tab.cut[bin]) tab.cutkey[bin] = std::min(tab.cutkey[bin], cut_key(fbits(az[p]), p));
+    if (marker_candidate(tab.cutbest[bin], pring[p], fbits(az[p]), p)) tab.dmax[bin] = std::max(tab.dmax[bin], fbits(d2[p]));
   }
-  for (int p = 0; p < N; p++) {
+  for (int p : road) {
     if (!(az[p] >= 0.0f)) continue;
     const int bin = deg_bin(az[p]);
-    if (marker_candidate(tab, pring[p], blabel[p], bin, fbits(az[p]), p)) tab.dmax[bin] = std::max(tab.dmax[bin], fbits(d2[p]));
-  }
-  for (int p = 0; p < N; p++) {
-    if (!(az[p] >= 0.0f)) continue;
-    const int bin = deg_bin(az[p]);
-    if (marker_candidate(tab, pring[p], blabel[p], bin, fbits(az[p]), p) && fbits(d2[p]) != 0u && fbits(d2[p]) == tab.dmax[bin])
+    if (fbits(d2[p]) != 0u && fbits(d2[p]) == tab.dmax[bin] && marker_candidate(tab.cutbest[bin], pring[p], fbits(az[p]), p))
       tab.best[bin] = std::min(tab.best[bin], best_key(pring[p], fbits(az[p]), p));
   }
   int cM = 0;
@@ -279,10 +294,11 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     if (tab.best[i] == ~0ull) continue;
     const int p = (int)(tab.best[i] & 0xffffffull);
     out->vert[cM][0] = bpt[p].x; out->vert[cM][1] = bpt[p].y; out->vert[cM][2] = bpt[p].z;
-    out->vert[cM][3] = tab.cut[i] != 0x7fffffff ? 1.0f : 0.0f;
+    out->vert[cM][3] = tab.cutbest[i] != ~0ull ? 1.0f : 0.0f;
     cM++;
   }
   out->n_vert = cM;
+  delete spm;
 
   // ---- k_sort_rings
   for (int k = 0; k < R; k++) {

@@ -95,16 +95,19 @@ int launch_pipeline(urf_ctx* ctx, int B, int S, bool want_order) {
     K("k_assign_redo", k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 1));
     K("k_mark_exact", k_mark_exact<<<(B + 127) / 128, 128, 0, st>>>(buf, B));
   }
-  K("k_scan_offsets", k_scan_offsets<<<B, 1024, 32 * kKeys * sizeof(unsigned), st>>>(buf, T));
+  K("k_scan_offsets", k_scan_offsets<<<B, 1024, 0, st>>>(buf, T));
   K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
   if (dp.star) {
+    K("k_star_bsort_warp", k_star_bsort_warp<<<dim3((kSectKeys + kStarWarps - 1) / kStarWarps, B), kStarWarps * 32, 0, st>>>(buf, S));
+    K("k_star_bsort_cta", k_star_bsort_cta<<<dim3(kSectKeys, B), 256, kStarCtaSmem, st>>>(buf, S));
     K("k_star_sort", k_star_sort<<<dim3(kSectKeys, B), 128, 0, st>>>(buf, S));
-    K("k_star_scan", k_star_scan<<<dim3((kSectKeys + 31) / 32, B), 32, 0, st>>>(buf, dp, S));
+    K("k_star_scan", k_star_scan<<<dim3((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B), kScanWarps * 32, 0, st>>>(buf, dp, S));
   }
   K("k_ring_detect", k_ring_detect<<<gpts, 256, 0, st>>>(buf, dp, S));
-  K("k_tables", k_tables<<<B, 384, 0, st>>>(buf, dp));
+  K("k_tab1", k_tab1<<<B, 256, 0, st>>>(buf, dp));
+  K("k_reach", k_reach<<<dim3((2 * kDegBins * dp.channels + 255) / 256, B), 256, 0, st>>>(buf, dp));
+  K("k_tab2", k_tab2<<<dim3((dp.channels + 255) / 256, B), 256, 0, st>>>(buf, dp));
   K("k_label", k_label<<<gpts, 256, 0, st>>>(buf, dp, S));
-  K("k_cutkey", k_cutkey<<<gpts, 256, 0, st>>>(buf, S));
   K("k_dmax", k_dmax<<<gpts, 256, 0, st>>>(buf, S));
   K("k_best", k_best<<<gpts, 256, 0, st>>>(buf, S));
   K("k_verts", k_verts<<<B, 384, 0, st>>>(buf, S));
@@ -201,9 +204,15 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   TRY(dalloc(ctx, &b.az, P));
   TRY(dalloc(ctx, &b.d2, P));
   TRY(dalloc(ctx, &b.blabel, P));
+  TRY(dalloc(ctx, &b.bring, P));
+  TRY(dalloc(ctx, &b.bidx, P));
+  TRY(dalloc(ctx, &b.roadlist, P));
+  TRY(dalloc(ctx, &b.Tf, (size_t)max_batch * kDegBins * URF_MAX_CHANNELS));
+  TRY(dalloc(ctx, &b.Tb, (size_t)max_batch * kDegBins * URF_MAX_CHANNELS));
+  TRY(dalloc(ctx, &b.lut, (size_t)max_batch * (kElevBins + 1)));
   TRY(dalloc(ctx, &b.order, P));
   TRY(dalloc(ctx, &b.sortbuf, 2 * P));
-  TRY(dalloc(ctx, &b.hist, (size_t)max_batch * ctx->Tmax * kKeys));
+  TRY(dalloc(ctx, &b.hist, (size_t)max_batch * ctx->Tmax * kRingKeys));
   TRY(dalloc(ctx, &b.firstidx, (size_t)max_batch * (kElevBins + 1)));
   TRY(dalloc(ctx, &b.cmin, (size_t)max_batch * URF_MAX_CHANNELS * kDegBins));
   TRY(dalloc(ctx, &b.cmax, (size_t)max_batch * URF_MAX_CHANNELS * kDegBins));
@@ -228,7 +237,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
     CKF(cudaMemcpyToSymbol(c_beam_yx, byx, sizeof(byx)));
     ctx->dp.Kfi = Kfi;
   }
-  CKF(cudaFuncSetAttribute(k_scan_offsets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * kKeys * sizeof(unsigned))));
+  CKF(cudaFuncSetAttribute(k_star_bsort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
   CKF(cudaFuncSetAttribute(k_sort_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingSmemKeys * sizeof(unsigned long long))));
   urf_default_params(&ctx->params);
   const char* fe = std::getenv("URF_FORCE_EXACT_REGISTRATION");
@@ -417,12 +426,7 @@ int urf_debug_fetch(urf_ctx* ctx, int b, int what, void* dst, size_t bytes) {
     case 4: src = ctx->buf.az + off; break;
     case 5: src = ctx->buf.d2 + off; break;
     case 6: src = ctx->buf.blabel + off; break;
-    case 7: {
-      std::vector<float4> tmp(bytes / 4);
-      CK(cudaMemcpy(tmp.data(), ctx->buf.bpt + off, tmp.size() * sizeof(float4), cudaMemcpyDeviceToHost));
-      for (size_t i = 0; i < tmp.size(); i++) std::memcpy((char*)dst + 4 * i, &tmp[i].w, 4);
-      return URF_OK;
-    }
+    case 7: src = ctx->buf.bidx + off; break;
     case 8: src = ctx->buf.tab + b; if (bytes > sizeof(ScanTab)) bytes = sizeof(ScanTab); break;
     default: return URF_ERR_INVALID;
   }

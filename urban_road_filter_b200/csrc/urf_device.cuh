@@ -7,15 +7,14 @@
 
 namespace urf {
 
-constexpr int kChunk = 1024;          // input points per warp chunk in the stable partition kernels
+constexpr int kChunk = 512;           // input points per warp chunk in the stable partition kernels
 constexpr int kWarpsPerBlock = 8;     // chunks per CTA in the partition kernels
 constexpr int kRingKeys = URF_MAX_CHANNELS;                 // 256 ring keys
 constexpr int kSectKeys = URF_STAR_SECTORS;                 // 360 sector keys
-constexpr int kKeys = kRingKeys + kSectKeys;                // 616 keys per histogram row
 constexpr int kElevBins = 4096;       // fine elevation bins used to speculate the greedy ring registration
 constexpr int kMaxCand = 1024;        // max speculation candidates handled by the fast registration path
 constexpr int kDegBins = 361;         // integer-degree bins 0..360 (marker search, lidar_segmentation.cpp:305)
-constexpr int kStLevels = 9;          // sparse-table levels over 361 window starts (2^9 = 512 > 361)
+constexpr int kStLevels = 9;          // sparse-table levels over 361 window starts (CPU model cross-check only)
 
 // internal per-scan flag bits (low 3 bits are the public urf_result.flags)
 enum : int {
@@ -61,11 +60,12 @@ struct ScanTab {
   unsigned maxdist[kRingKeys];     // float bits of maxDistance[j] (:271-274); non-negative floats order like uints
   double A[kRingKeys];             // arcDistance / ((maxDistance[k] * M_PI) / 180)  (blind_spots.cpp:142)
   int sect_start[kSectKeys + 1];
+  int sect_cnt[kSectKeys];         // points per star sector (unstable partition: counted with atomics)
+  int sect_cur[kSectKeys];         // scatter cursors
+  unsigned char sflag[kSectKeys];  // sector needs the slow sort path (degenerate radius distribution)
   float q[4];                      // q1..q4 (blind_spots.cpp:13-57)
-  unsigned short reach[2][kDegBins];                 // rings accepted by window start i, forward / backward
-  unsigned short st[2][kStLevels][kDegBins];         // range-max sparse tables over reach
-  int cut[kDegBins];               // first ring holding a non-road point in degree bin i
-  unsigned long long cutkey[kDegBins];               // (azimuth bits, bucket pos) of the first non-road point in that ring/bin
+  int reach[2][kDegBins];          // rings accepted by window start i, forward / backward (atomicMin over cells)
+  unsigned long long cutbest[kDegBins];              // min (ring, azimuth bits, bucket pos) over the bin's non-road points
   unsigned dmax[kDegBins];         // float bits of the farthest candidate road point
   unsigned long long best[kDegBins];                 // (ring, azimuth bits, bucket pos) of the first candidate reaching dmax
 };
@@ -79,14 +79,20 @@ struct DevBuffers {
   short* sect;           // [P]   star sector or -1
   int* label;            // [P]   output labels, input order
   float4* bpt;           // [P]   ring buckets (ring-major, input order inside a ring): x, y, z, input index bits
-  float4* spt;           // [P]   sector buckets: r, z, input index bits, -
+  float4* spt;           // [P]   sector buckets (unordered inside a sector): r, z, input index bits, -
   float4* ssorted;       // [P]   sector buckets sorted by r
   float* az;             // [P]   azimuth per bucket position
   float* d2;             // [P]   planar range per bucket position
   unsigned char* blabel; // [P]   label per bucket position
+  unsigned char* bring;  // [P]   ring index per bucket position
+  int* bidx;             // [P]   input index per bucket position
+  uint4* roadlist;       // [P]   compact list of road points: (bin | ring << 16, azimuth bits, range bits, bucket pos)
+  float* Tf;             // [B][kDegBins][channels] forward threshold table (urf_logic.cuh build_T_column)
+  float* Tb;             // [B][kDegBins][channels] backward threshold table
+  unsigned short* lut;   // [B][kElevBins + 1] ring-search start per fine elevation bin
   int* order;            // [P]   emission order (input indices), only when requested
   unsigned long long* sortbuf;   // [2P] scratch for segments too large for shared memory
-  unsigned* hist;        // [B][T][kKeys] chunk histograms, turned into scatter offsets in place
+  unsigned* hist;        // [B][T][kRingKeys] per-chunk ring histograms, turned into scatter offsets in place
   unsigned* firstidx;    // [B][kElevBins + 1] first input index per fine elevation bin
   unsigned* cmin;        // [B][channels][kDegBins] float bits: min curb azimuth per (ring, degree bin), +inf = empty
   unsigned* cmax;        // [B][channels][kDegBins] float bits: max curb azimuth per (ring, degree bin)

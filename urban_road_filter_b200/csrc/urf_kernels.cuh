@@ -1,13 +1,14 @@
-// urf_kernels.cuh — sm_100a kernels of the per-scan road/curb classification path.
+// urf_kernels.cuh — sm_100a kernels of the per-scan road/curb classification path (pipeline v2).
 //
 // Every kernel takes the batch index from blockIdx.y (or blockIdx.x for one-CTA-per-scan kernels): a launch covers a
-// whole batch of scans laid out back to back with `S` points of stride. All arithmetic that decides a label uses
-// round-to-nearest intrinsics in exactly the operation order of the reference (file:line cited per block; paths are
-// relative to the reference repo), so results are bit-identical to the x86-64 -O2 build of the reference.
+// whole batch of scans laid out back to back with `S` points of stride. Everything that decides a label is computed by
+// the host+device functions of urf_logic.cuh (bit-identical to the x86-64 -O2 build of the reference, file:line cited
+// there); the kernels add indexing, staging, atomics and synchronisation.
 //
 // Pipeline (DESIGN.md has the picture):
-//   k_reset -> k_points -> k_register -> k_assign -> [k_register_exact -> k_assign(redo)] -> k_scan_offsets -> k_scatter
-//   -> k_star_sort -> k_star_scan -> k_ring_detect -> k_tables -> k_label -> k_cutkey -> k_dmax -> k_best -> k_verts
+//   k_reset -> k_points -> k_register -> k_assign -> [k_register_exact -> k_assign(redo) -> k_mark_exact]
+//   -> k_scan_offsets -> k_scatter -> k_star_bsort_warp / k_star_bsort_cta / k_star_sort(fallback) -> k_star_scan
+//   -> k_ring_detect -> k_tab1 -> k_reach -> k_tab2 -> k_label -> k_dmax -> k_best -> k_verts
 //   [-> k_sort_rings when the emission order is requested]
 #pragma once
 #include "urf_device.cuh"
@@ -40,16 +41,6 @@ __device__ void cta_bitonic(T* a, int npad) {
 
 __device__ __forceinline__ int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
-// largest k in [0, n_rings) with ring_start[k] <= p (ring_start ascending, ring_start[0] == 0)
-__device__ __forceinline__ int ring_of(const int* ring_start, int n_rings, int p) {
-  int lo = 0, hi = n_rings;      // invariant: ring_start[lo] <= p < ring_start[hi]
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (ring_start[mid] <= p) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // k_reset: per-call initialisation of the per-scan tables.
 __global__ void k_reset(DevBuffers buf, DevParams prm) {
@@ -63,9 +54,8 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
   }
   for (int i = tid; i <= kRingKeys; i += nth) o.ring_start[i] = 0;
   for (int i = tid; i < kRingKeys; i += nth) { t.maxdist[i] = 0u; t.angle[i] = 0.f; t.regidx[i] = 0x7fffffff; t.regorder[i] = 0x7fffffff; }
-  for (int i = tid; i < kDegBins; i += nth) {
-    t.cut[i] = 0x7fffffff; t.cutkey[i] = ~0ull; t.dmax[i] = 0u; t.best[i] = ~0ull;
-  }
+  for (int i = tid; i < kDegBins; i += nth) { t.cutbest[i] = ~0ull; t.dmax[i] = 0u; t.best[i] = ~0ull; }
+  for (int i = tid; i < kSectKeys; i += nth) { t.sect_cnt[i] = 0; t.sflag[i] = 0; }
   unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1);
   for (int i = tid; i <= kElevBins; i += nth) fi[i] = 0xffffffffu;
   const size_t nb = (size_t)prm.channels * kDegBins;
@@ -75,11 +65,9 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_points: ROI crop predicate + range + elevation angle per input point.
-//   ROI: lidar_segmentation.cpp:106-113 (+ PCL ConditionalRemoval drops non-finite xyz)
-//   d, alpha: lidar_segmentation.cpp:148-166
+// k_points: ROI crop predicate + range + elevation angle per input point (lidar_segmentation.cpp:106-113,148-166).
 // Also records, per fine elevation bin, the first input index that falls into it (speculation input for k_register).
-__global__ void k_points(DevBuffers buf, DevParams prm, int S) {
+__global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   const int n = buf.n[b];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,22 +79,15 @@ __global__ void k_points(DevBuffers buf, DevParams prm, int S) {
     float a = -1.0f;
     if (keep) {
       a = elev_alpha(p.x, p.y, p.z);
-      int bin = (int)(a * (kElevBins / 180.0f));
-      bin = bin < 0 ? 0 : (bin > kElevBins ? kElevBins : bin);
-      unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1) + bin;
-      if (*(volatile unsigned*)fi > (unsigned)i) atomicMin(fi, (unsigned)i);
+      unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1) + elev_bin(a);
+      if (*fi > (unsigned)i) atomicMin(fi, (unsigned)i);      // plain (possibly stale) read: a stale value is only larger
       if (a == 0.0f) atomicOr(&buf.out[b].flags, F_ZERO_ALPHA);
     }
     buf.alpha_v[g] = a;
     buf.mark[g] = 0;
   }
   const unsigned bal = __ballot_sync(0xffffffffu, keep);
-  __shared__ int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
-  if (lane_id() == 0 && bal) atomicAdd(&s_cnt, __popc(bal));
-  __syncthreads();
-  if (threadIdx.x == 0 && s_cnt) atomicAdd(&buf.out[b].n_roi, s_cnt);
+  if (lane_id() == 0 && bal) atomicAdd(&buf.out[b].n_roi, __popc(bal));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -132,7 +113,6 @@ __device__ void register_exact_cta(const float* __restrict__ alpha, int n, float
       }
       if (!cov) { local = i; break; }
     }
-    // CTA min
     for (int o = 16; o > 0; o >>= 1) local = min(local, __shfl_xor_sync(0xffffffffu, local, o));
     if (lane_id() == 0) s_red[threadIdx.x >> 5] = local;
     __syncthreads();
@@ -155,21 +135,26 @@ __device__ void register_exact_cta(const float* __restrict__ alpha, int n, float
   *out_m = m;
 }
 
-// Sort the m registered (angle, regidx) pairs by angle (:205) and publish them. Angles are >= 0 so bits order them.
-__device__ void publish_rings_cta(ScanTab& tab, ScanOut& out, const float* s_reg, const int* s_idx, int m,
-                                  unsigned long long* s_keys) {
+// Sort the m registered (angle, regidx) pairs by angle (:205), publish them and build the elevation-bin lookup table
+// k_assign starts its ring search from. Angles are >= 0 so their bits order them.
+__device__ void publish_rings_cta(ScanTab& tab, ScanOut& out, unsigned short* lut, float interval, const float* s_reg,
+                                  const int* s_idx, int m, unsigned long long* s_keys, float* s_sorted) {
   for (int t = threadIdx.x; t < kRingKeys; t += blockDim.x)
     s_keys[t] = t < m ? (((unsigned long long)fbits(s_reg[t]) << 32) | (unsigned)s_idx[t]) : ~0ull;
   __syncthreads();
   cta_bitonic(s_keys, kRingKeys);
   for (int t = threadIdx.x; t < kRingKeys; t += blockDim.x) {
     if (t < m) {
-      tab.angle[t] = bitsf((unsigned)(s_keys[t] >> 32));
+      const float a = bitsf((unsigned)(s_keys[t] >> 32));
+      s_sorted[t] = a;
+      tab.angle[t] = a;
       tab.regidx[t] = (int)(unsigned)s_keys[t];
       tab.regorder[t] = s_idx[t];
-    } else { tab.angle[t] = 0.f; tab.regidx[t] = 0x7fffffff; tab.regorder[t] = 0x7fffffff; }
+    } else { s_sorted[t] = 0.f; tab.angle[t] = 0.f; tab.regidx[t] = 0x7fffffff; tab.regorder[t] = 0x7fffffff; }
   }
   if (threadIdx.x == 0) out.n_rings = m;
+  __syncthreads();
+  for (int e = threadIdx.x; e <= kElevBins; e += blockDim.x) lut[e] = (unsigned short)ring_lut_entry(s_sorted, m, interval, e);
 }
 
 // k_register: one CTA (256 threads) per scan. Fast path: the greedy registration is run over "candidates" only — the
@@ -185,6 +170,7 @@ __global__ void __launch_bounds__(256) k_register(DevBuffers buf, DevParams prm,
   __shared__ float s_calpha[kMaxCand];
   __shared__ float s_vis[kRingKeys];
   __shared__ float s_reg[kRingKeys];
+  __shared__ float s_sorted[kRingKeys];
   __shared__ int s_idx[kRingKeys];
   __shared__ unsigned long long s_keys[kRingKeys];
   __shared__ int s_red[8];
@@ -237,7 +223,7 @@ __global__ void __launch_bounds__(256) k_register(DevBuffers buf, DevParams prm,
     if (threadIdx.x == 0) { s_m = m; atomicOr(&out.flags, F_EXACT_REG); }
     __syncthreads();
   }
-  publish_rings_cta(tab, out, s_reg, s_idx, s_m, s_keys);
+  publish_rings_cta(tab, out, buf.lut + (size_t)b * (kElevBins + 1), prm.interval, s_reg, s_idx, s_m, s_keys, s_sorted);
 }
 
 // k_register_exact: repairs scans whose speculation failed verification in k_assign (F_SPEC_VIOLATION).
@@ -247,22 +233,25 @@ __global__ void __launch_bounds__(256) k_register_exact(DevBuffers buf, DevParam
   if (!(out.flags & F_SPEC_VIOLATION) || (out.flags & F_EXACT_REG)) return;
   __shared__ float s_vis[kRingKeys];
   __shared__ float s_reg[kRingKeys];
+  __shared__ float s_sorted[kRingKeys];
   __shared__ int s_idx[kRingKeys];
   __shared__ unsigned long long s_keys[kRingKeys];
   __shared__ int s_red[8];
   __shared__ int s_m;
+  for (int t = threadIdx.x; t < kSectKeys; t += blockDim.x) buf.tab[b].sect_cnt[t] = 0;   // the redo pass counts again
   int m;
   register_exact_cta(buf.alpha_v + (size_t)b * S, buf.n[b], prm.interval, prm.channels, s_vis, s_reg, s_idx, s_red, &m);
   if (threadIdx.x == 0) s_m = m;
   __syncthreads();
-  publish_rings_cta(buf.tab[b], out, s_reg, s_idx, s_m, s_keys);
-  // F_EXACT_REG is set by the redo pass of k_assign (it must still see "violation and not yet exact" in every CTA)
+  publish_rings_cta(buf.tab[b], out, buf.lut + (size_t)b * (kElevBins + 1), prm.interval, s_reg, s_idx, s_m, s_keys, s_sorted);
+  // F_EXACT_REG is set by k_mark_exact after the redo pass of k_assign (every redo CTA must still see the old flags)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_assign: per input point — ring index (lidar_segmentation.cpp:226-233: first sorted angle within `interval`),
-// star-shaped sector (star_shaped_search.cpp:164-173 + rectangular beam filter :73-107), default label, and the
-// per-warp-chunk key histograms of the two stable partitions. redo=1 re-runs only for scans that were repaired.
+// star-shaped sector (star_shaped_search.cpp:164-173 + rectangular beam filter :73-107), default label, the per-warp-
+// chunk ring histogram of the stable ring partition and the per-sector counts of the (unordered) sector partition.
+// redo=1 re-runs only for scans whose registration was repaired.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, DevParams prm, int S, int T, int redo) {
   const int b = blockIdx.y;
   ScanOut& out = buf.out[b];
@@ -273,15 +262,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, 
   const int chunk = blockIdx.x * kWarpsPerBlock + warp;
   __shared__ float s_angle[kRingKeys];
   __shared__ int s_regidx[kRingKeys];
-  __shared__ unsigned s_cnt[kWarpsPerBlock][kKeys];
-  const ScanTab& tab = buf.tab[b];
+  __shared__ unsigned s_cnt[kWarpsPerBlock][kRingKeys];
+  ScanTab& tab = buf.tab[b];
   const int R = out.n_rings;
   for (int t = threadIdx.x; t < kRingKeys; t += blockDim.x) { s_angle[t] = tab.angle[t]; s_regidx[t] = tab.regidx[t]; }
-  for (int t = lane; t < kKeys; t += 32) s_cnt[warp][t] = 0;
+  for (int t = lane; t < kRingKeys; t += 32) s_cnt[warp][t] = 0;
   __syncthreads();
   if (chunk * kChunk >= n) return;             // whole warp; no block-level sync follows
   const bool live = out.n_roi >= 30;
   const bool verify = !redo && !(flags & F_EXACT_REG);
+  const unsigned short* lut = buf.lut + (size_t)b * (kElevBins + 1);
   unsigned* cnt = s_cnt[warp];
   bool violation = false;
   for (int it = 0; it < kChunk / 32; it++) {
@@ -293,7 +283,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, 
       const bool kept = live && a >= 0.0f;
       if (kept) {
         int lo;
-        ring = assign_ring(s_angle, R, a, prm.interval, &lo);
+        ring = assign_ring_from(s_angle, R, a, prm.interval, lut[elev_bin(a)], &lo);
         if (verify && registration_violation(s_angle, s_regidx, tab.regorder, R, prm.channels, prm.interval, a, i, lo))
           violation = true;
         if (prm.star) {
@@ -308,12 +298,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, 
     unsigned peers = __match_any_sync(0xffffffffu, ring);
     if (ring >= 0 && lane == __ffs(peers) - 1) cnt[ring] += __popc(peers);
     peers = __match_any_sync(0xffffffffu, sec);
-    if (sec >= 0 && lane == __ffs(peers) - 1) cnt[kRingKeys + sec] += __popc(peers);
+    if (sec >= 0 && lane == __ffs(peers) - 1) atomicAdd(&tab.sect_cnt[sec], __popc(peers));
     __syncwarp();
   }
   if (__any_sync(0xffffffffu, violation) && lane == 0) atomicOr(&out.flags, F_SPEC_VIOLATION);
-  unsigned* row = buf.hist + ((size_t)b * T + chunk) * kKeys;
-  for (int t = lane; t < kKeys; t += 32) row[t] = cnt[t];
+  unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
+  for (int t = lane; t < kRingKeys; t += 32) row[t] = cnt[t];
 }
 
 // After the redo pass: mark repaired scans as exact (separate tiny kernel so every k_assign(redo) CTA saw the old flags).
@@ -323,46 +313,47 @@ __global__ void k_mark_exact(DevBuffers buf, int B) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_scan_offsets: one CTA (1024 threads) per scan turns hist[chunk][key] into exclusive scatter offsets
-// (key-major bases + prefix over chunks) and publishes ring_start / sect_start.
+// k_scan_offsets: one CTA (1024 threads) per scan turns hist[chunk][ring] into exclusive scatter offsets (ring-major
+// bases + prefix over chunks), publishes ring_start, and turns the sector counts into sect_start + scatter cursors.
 __global__ void __launch_bounds__(1024) k_scan_offsets(DevBuffers buf, int T) {
-  extern __shared__ unsigned s_part[];          // [32][kKeys] per-warp partial sums, then per-warp exclusive prefixes
-  __shared__ unsigned s_base[kKeys];
+  __shared__ unsigned s_part[32][kRingKeys];     // per-warp partial sums, then per-warp exclusive prefixes
+  __shared__ unsigned s_base[kRingKeys];
   const int b = blockIdx.x;
   const int n = buf.n[b];
   const int rows = (n + kChunk - 1) / kChunk;
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int rpw = (rows + 31) / 32;
   const int r0 = min(rows, warp * rpw), r1 = min(rows, (warp + 1) * rpw);
-  unsigned* hist = buf.hist + (size_t)b * T * kKeys;
-  for (int key = lane; key < kKeys; key += 32) {
+  unsigned* hist = buf.hist + (size_t)b * T * kRingKeys;
+  for (int key = lane; key < kRingKeys; key += 32) {
     unsigned s = 0;
-    for (int r = r0; r < r1; r++) s += hist[(size_t)r * kKeys + key];
-    s_part[warp * kKeys + key] = s;
+    for (int r = r0; r < r1; r++) s += hist[(size_t)r * kRingKeys + key];
+    s_part[warp][key] = s;
   }
   __syncthreads();
-  if (threadIdx.x < kKeys) {
+  if (threadIdx.x < kRingKeys) {
     unsigned run = 0;
-    for (int w = 0; w < 32; w++) { unsigned v = s_part[w * kKeys + threadIdx.x]; s_part[w * kKeys + threadIdx.x] = run; run += v; }
-    s_base[threadIdx.x] = run;                  // total of this key
+    for (int w = 0; w < 32; w++) { unsigned v = s_part[w][threadIdx.x]; s_part[w][threadIdx.x] = run; run += v; }
+    s_base[threadIdx.x] = run;                  // total of this ring
   }
   __syncthreads();
-  if (threadIdx.x == 0) {                        // key bases: rings and sectors are separate address spaces
+  if (threadIdx.x == 0) {
     unsigned run = 0;
     ScanOut& o = buf.out[b];
     for (int k = 0; k < kRingKeys; k++) { unsigned v = s_base[k]; s_base[k] = run; o.ring_start[k] = (int)run; run += v; }
     o.ring_start[kRingKeys] = (int)run;
     o.n_order = (int)run;
+  } else if (threadIdx.x == 32) {
     ScanTab& t = buf.tab[b];
-    run = 0;
-    for (int k = 0; k < kSectKeys; k++) { unsigned v = s_base[kRingKeys + k]; s_base[kRingKeys + k] = run; t.sect_start[k] = (int)run; run += v; }
-    t.sect_start[kSectKeys] = (int)run;
+    int run = 0;
+    for (int k = 0; k < kSectKeys; k++) { const int v = t.sect_cnt[k]; t.sect_start[k] = run; t.sect_cur[k] = run; run += v; }
+    t.sect_start[kSectKeys] = run;
   }
   __syncthreads();
-  for (int key = lane; key < kKeys; key += 32) {
-    unsigned run = s_base[key] + s_part[warp * kKeys + key];
+  for (int key = lane; key < kRingKeys; key += 32) {
+    unsigned run = s_base[key] + s_part[warp][key];
     for (int r = r0; r < r1; r++) {
-      unsigned* p = &hist[(size_t)r * kKeys + key];
+      unsigned* p = &hist[(size_t)r * kRingKeys + key];
       unsigned v = *p; *p = run; run += v;
     }
   }
@@ -370,114 +361,318 @@ __global__ void __launch_bounds__(1024) k_scan_offsets(DevBuffers buf, int T) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_scatter: stable scatter of every point into its ring bucket (input order inside a ring, lidar_segmentation.cpp:221-
-// 277) and into its star sector (push_back order, star_shaped_search.cpp:173).
+// 277) and unordered scatter into its star sector (the radius sort that follows breaks ties by input index, which is the
+// push_back order of star_shaped_search.cpp:173).
+// Ring buckets are written coalesced: the warp first ranks its 512-point chunk by ring in shared memory, then walks the
+// chunk in ring order so that consecutive lanes write consecutive bucket slots.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf, DevParams prm, int S, int T) {
   const int b = blockIdx.y;
   const int n = buf.n[b];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int chunk = blockIdx.x * kWarpsPerBlock + warp;
-  __shared__ unsigned s_run[kWarpsPerBlock][kKeys];
+  __shared__ unsigned s_goff[kWarpsPerBlock][kRingKeys];          // global bucket offset of this chunk, per ring
+  __shared__ unsigned short s_lcnt[kWarpsPerBlock][kRingKeys];    // per-ring count, then exclusive local start
+  __shared__ unsigned short s_perm[kWarpsPerBlock][kChunk];       // chunk-local point index in ring order
+  __shared__ unsigned char s_pring[kWarpsPerBlock][kChunk];       // ring of that slot
   if (chunk * kChunk >= n) return;
-  unsigned* run = s_run[warp];
-  const unsigned* row = buf.hist + ((size_t)b * T + chunk) * kKeys;
-  for (int t = lane; t < kKeys; t += 32) run[t] = row[t];
+  unsigned* goff = s_goff[warp];
+  unsigned short* lcnt = s_lcnt[warp];
+  unsigned short* perm = s_perm[warp];
+  unsigned char* pring = s_pring[warp];
+  ScanTab& tab = buf.tab[b];
+  const unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
+  for (int t = lane; t < kRingKeys; t += 32) { goff[t] = row[t]; lcnt[t] = 0; }
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
+  unsigned packed[kChunk / 32];                 // (ring + 1) << 16 | rank inside the chunk's ring group
+  const size_t g0 = (size_t)b * S + (size_t)chunk * kChunk;
+#pragma unroll
   for (int it = 0; it < kChunk / 32; it++) {
-    const int i = chunk * kChunk + it * 32 + lane;
+    const int li = it * 32 + lane;
+    const int i = chunk * kChunk + li;
     int ring = -1, sec = -1;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < n) {
-      const size_t g = (size_t)b * S + i;
-      ring = buf.ringid[g];
-      sec = buf.sect[g];
-      if (ring >= 0 || sec >= 0) p = __ldg(&buf.in[g]);
-    }
+    if (i < n) { ring = buf.ringid[g0 + li]; sec = buf.sect[g0 + li]; }
     unsigned peers = __match_any_sync(0xffffffffu, ring);
-    unsigned dst = 0;
-    if (ring >= 0) dst = run[ring] + __popc(peers & lt);
+    unsigned pk = 0;
+    if (ring >= 0) pk = ((unsigned)(ring + 1) << 16) | (lcnt[ring] + __popc(peers & lt));
     __syncwarp();
-    if (ring >= 0 && lane == __ffs(peers) - 1) run[ring] += __popc(peers);
-    if (ring >= 0) buf.bpt[(size_t)b * S + dst] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    if (ring >= 0 && lane == __ffs(peers) - 1) lcnt[ring] += (unsigned short)__popc(peers);
+    packed[it] = pk;
+    // sector: one atomic per group of equal sectors, slots handed out in lane order
     peers = __match_any_sync(0xffffffffu, sec);
-    if (sec >= 0) dst = run[kRingKeys + sec] + __popc(peers & lt);
-    __syncwarp();
-    if (sec >= 0 && lane == __ffs(peers) - 1) run[kRingKeys + sec] += __popc(peers);
     if (sec >= 0) {
-      const float r = star_radius(p.x, p.y);
-      buf.spt[(size_t)b * S + dst] = make_float4(r, p.z, __int_as_float(i), 0.f);
+      const int leader = __ffs(peers) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&tab.sect_cur[sec], __popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      const float4 p = __ldg(&buf.in[g0 + li]);
+      buf.spt[(size_t)b * S + base + __popc(peers & lt)] = make_float4(star_radius(p.x, p.y), p.z, __int_as_float(i), 0.f);
     }
     __syncwarp();
+  }
+  // exclusive scan of the chunk's ring counts -> local starts
+  {
+    unsigned v[kRingKeys / 32], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kRingKeys / 32; j++) { v[j] = lcnt[lane * (kRingKeys / 32) + j]; sum += v[j]; }
+    unsigned inc = sum;
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    unsigned run = inc - sum;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kRingKeys / 32; j++) { lcnt[lane * (kRingKeys / 32) + j] = (unsigned short)run; run += v[j]; }
+  }
+  __syncwarp();
+  int total = 0;
+#pragma unroll
+  for (int it = 0; it < kChunk / 32; it++) {
+    const unsigned pk = packed[it];
+    if (pk) {
+      const int ring = (int)(pk >> 16) - 1;
+      const int slot = lcnt[ring] + (pk & 0xffffu);
+      perm[slot] = (unsigned short)(it * 32 + lane);
+      pring[slot] = (unsigned char)ring;
+    }
+    total += __popc(__ballot_sync(0xffffffffu, pk != 0));
+  }
+  __syncwarp();
+  for (int t = lane; t < total; t += 32) {
+    const int li = perm[t], ring = pring[t];
+    const float4 p = __ldg(&buf.in[g0 + li]);
+    const size_t dst = (size_t)b * S + goff[ring] + (t - lcnt[ring]);
+    buf.bpt[dst] = make_float4(p.x, p.y, p.z, __int_as_float(chunk * kChunk + li));
+    buf.bring[dst] = (unsigned char)ring;
+    buf.bidx[dst] = chunk * kChunk + li;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_star_sort: one CTA per (sector, scan): sort the sector's points by planar radius (star_shaped_search.cpp:109).
-// Tie policy: (r, push_back order) — the reference's introsort order for equal r is unspecified; ties raise F_TIE_SECTOR.
+// Star-shaped search, sort by planar radius (star_shaped_search.cpp:109). Order: (r, input index) — the reference's
+// introsort order for equal r is unspecified; ties raise F_TIE_SECTOR.
+//
+// Fast path: one-pass bucket sort. Radius bits are mapped onto ~n buckets with an adaptive shift, counted and scattered
+// in shared memory, and every element ranks itself inside its (tiny) bucket. A sector whose radii pile up in one bucket
+// (more than kBucketMax) is flagged for the bitonic fallback below. GROUP = 32: one warp per sector (n <= kWarpCap);
+// GROUP = 256: one CTA per sector (n <= kCtaCap).
+constexpr int kWarpCap = 512, kCtaCap = 8192, kBucketMax = 48, kStarWarps = 6;
+
+template <int GROUP>
+__device__ __forceinline__ void group_sync() { if (GROUP == 32) __syncwarp(); else __syncthreads(); }
+
+template <int GROUP, int CAP>
+__device__ void bucket_sort_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid,
+                                   unsigned* s_cnt /*CAP + 2*/, unsigned long long* s_key /*CAP*/, unsigned short* s_el /*CAP*/,
+                                   unsigned* s_w /*GROUP / 32*/, int* tie_out, unsigned char* slow_flag) {
+  // (1) range of the radius bits
+  unsigned mn = 0xffffffffu, mx = 0u;
+  for (int e = tid; e < n; e += GROUP) { const unsigned v = fbits(src[e].x); mn = min(mn, v); mx = max(mx, v); }
+  if (tid == 0) { s_cnt[CAP] = 0xffffffffu; s_cnt[CAP + 1] = 0u; }
+  group_sync<GROUP>();
+  for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if ((tid & 31) == 0) { atomicMin(&s_cnt[CAP], mn); atomicMax(&s_cnt[CAP + 1], mx); }
+  group_sync<GROUP>();
+  mn = s_cnt[CAP]; mx = s_cnt[CAP + 1];
+  int nb = next_pow2(n); if (nb > CAP) nb = CAP;
+  int shift = 0;
+  while (((mx - mn) >> shift) >= (unsigned)nb) shift++;
+  // (2) count
+  for (int t = tid; t < nb; t += GROUP) s_cnt[t] = 0;
+  group_sync<GROUP>();
+  for (int e = tid; e < n; e += GROUP) atomicAdd(&s_cnt[(fbits(src[e].x) - mn) >> shift], 1u);
+  group_sync<GROUP>();
+  // (3) exclusive scan over nb buckets (each thread owns a contiguous run of nb / GROUP buckets)
+  {
+    const int per = (nb + GROUP - 1) / GROUP;
+    const int t0 = min(nb, tid * per), t1 = min(nb, t0 + per);
+    unsigned sum = 0;
+    for (int t = t0; t < t1; t++) sum += s_cnt[t];
+    unsigned inc = sum;
+    for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += v; }
+    unsigned woff = 0;
+    if (GROUP > 32) {
+      if ((tid & 31) == 31) s_w[tid >> 5] = inc;
+      __syncthreads();
+      for (int w = 0; w < (tid >> 5); w++) woff += s_w[w];
+    }
+    unsigned run = woff + inc - sum;
+    for (int t = t0; t < t1; t++) { unsigned v = s_cnt[t]; s_cnt[t] = run; run += v; }
+  }
+  group_sync<GROUP>();
+  // (4) scatter into bucket order (the cursor of bucket b ends at the start of bucket b + 1)
+  for (int e = tid; e < n; e += GROUP) {
+    const float4 p = src[e];
+    const unsigned v = fbits(p.x);
+    const unsigned slot = atomicAdd(&s_cnt[(v - mn) >> shift], 1u);
+    s_key[slot] = ((unsigned long long)v << 32) | (unsigned)__float_as_int(p.z);
+    s_el[slot] = (unsigned short)e;
+  }
+  group_sync<GROUP>();
+  // (5) rank inside the bucket and write out
+  bool tie = false, slow = false;
+  for (int q = tid; q < n; q += GROUP) {
+    const unsigned long long key = s_key[q];
+    const unsigned bkt = ((unsigned)(key >> 32) - mn) >> shift;
+    const int s = bkt ? (int)s_cnt[bkt - 1] : 0, e = (int)s_cnt[bkt];
+    if (e - s > kBucketMax) { slow = true; continue; }
+    int rank = 0;
+    for (int j = s; j < e; j++) {
+      const unsigned long long o = s_key[j];
+      rank += o < key;
+      tie |= (j != q) && ((unsigned)(o >> 32) == (unsigned)(key >> 32));
+    }
+    dst[s + rank] = src[s_el[q]];
+  }
+  if (slow) *slow_flag = 1;
+  if (tie) *tie_out = 1;
+}
+
+__global__ void __launch_bounds__(kStarWarps * 32) k_star_bsort_warp(DevBuffers buf, int S) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5;
+  const int s = blockIdx.x * kStarWarps + warp;
+  __shared__ unsigned s_cnt[kStarWarps][kWarpCap + 2];
+  __shared__ unsigned long long s_key[kStarWarps][kWarpCap];
+  __shared__ unsigned short s_el[kStarWarps][kWarpCap];
+  if (s >= kSectKeys) return;
+  ScanTab& tab = buf.tab[b];
+  const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+  if (n <= 0 || n > kWarpCap) return;
+  const float4* src = buf.spt + (size_t)b * S + base;
+  float4* dst = buf.ssorted + (size_t)b * S + base;
+  if (n == 1) { if (lane_id() == 0) dst[0] = src[0]; return; }
+  int tie = 0;
+  bucket_sort_sector<32, kWarpCap>(src, dst, n, lane_id(), s_cnt[warp], s_key[warp], s_el[warp], nullptr, &tie, &tab.sflag[s]);
+  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+}
+
+constexpr size_t kStarCtaSmem = sizeof(unsigned long long) * kCtaCap + sizeof(unsigned) * (kCtaCap + 2) + sizeof(unsigned short) * kCtaCap + 64;
+__global__ void __launch_bounds__(256) k_star_bsort_cta(DevBuffers buf, int S) {
+  extern __shared__ unsigned long long s_raw64[];
+  const int b = blockIdx.y, s = blockIdx.x;
+  ScanTab& tab = buf.tab[b];
+  const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+  if (n <= kWarpCap || n > kCtaCap) return;
+  unsigned long long* s_key = s_raw64;
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_key + kCtaCap);
+  unsigned short* s_el = reinterpret_cast<unsigned short*>(s_cnt + kCtaCap + 2);
+  unsigned* s_w = reinterpret_cast<unsigned*>(s_el + kCtaCap);
+  int tie = 0;
+  bucket_sort_sector<256, kCtaCap>(buf.spt + (size_t)b * S + base, buf.ssorted + (size_t)b * S + base, n, threadIdx.x, s_cnt,
+                                   s_key, s_el, s_w, &tie, &tab.sflag[s]);
+  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+}
+
+// Fallback: CTA-wide bitonic sort (shared memory up to 4096 keys, global scratch beyond) for sectors that are too large
+// for the bucket kernels or whose radii collapse into one bucket.
 constexpr int kStarSmemKeys = 4096;
 __global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S) {
   const int b = blockIdx.y, s = blockIdx.x;
   const ScanTab& tab = buf.tab[b];
   const int base = tab.sect_start[s];
   const int n = tab.sect_start[s + 1] - base;
-  if (n <= 0) return;
+  if (n <= 1 || !(n > kCtaCap || tab.sflag[s])) return;
   const float4* src = buf.spt + (size_t)b * S + base;
   float4* dst = buf.ssorted + (size_t)b * S + base;
-  if (n == 1) { if (threadIdx.x == 0) dst[0] = src[0]; return; }
   __shared__ unsigned long long s_keys[kStarSmemKeys];
   const int npad = next_pow2(n);
   unsigned long long* keys = npad <= kStarSmemKeys ? s_keys : buf.sortbuf + 2 * ((size_t)b * S + base);
   for (int t = threadIdx.x; t < npad; t += blockDim.x)
-    keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)t) : ~0ull;
+    keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
   __syncthreads();
   cta_bitonic(keys, npad);
+  // keys hold (radius bits, input index) ascending: rebuild the records (z comes from the input record of that index)
   bool tie = false;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const unsigned long long k = keys[t];
-    dst[t] = src[(unsigned)k];
     if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
+    const int idx = (int)(unsigned)k;
+    dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
   }
   if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
 }
 
 // k_star_scan: one lane per sector walks its radius-sorted points with the reference's running mean / average absolute
-// deviation recurrence (star_shaped_search.cpp:112-150) and marks the first edge point.
-__global__ void __launch_bounds__(32) k_star_scan(DevBuffers buf, DevParams prm, int S) {
-  const int b = blockIdx.y;
-  const int s = blockIdx.x * 32 + threadIdx.x;
-  if (s >= kSectKeys) return;
+// deviation recurrence (star_shaped_search.cpp:112-150) and marks the first edge point. The warp stages 32-point tiles
+// of its 32 sectors in shared memory with coalesced loads; the serial walk then reads shared memory only.
+constexpr int kScanWarps = 4;
+__global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, DevParams prm, int S) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = lane_id();
+  const int s = (blockIdx.x * kScanWarps + warp) * 32 + lane;
+  __shared__ float s_r[kScanWarps][32][33];
+  __shared__ float s_z[kScanWarps][32][33];
   const ScanTab& tab = buf.tab[b];
-  const int base = tab.sect_start[s];
-  const int n = tab.sect_start[s + 1] - base;
-  const float4* pts = buf.ssorted + (size_t)b * S + base;
-  const int hit = star_scan_sector(prm, pts, n);
-  if (hit >= 0) buf.mark[(size_t)b * S + __float_as_int(pts[hit].z)] = 2;   // star_shaped_search.cpp:146
+  int base = 0, n = 0;
+  if (s < kSectKeys) { base = tab.sect_start[s]; n = tab.sect_start[s + 1] - base; }
+  const float4* all = buf.ssorted + (size_t)b * S;
+  StarState st;
+  star_init(st, 0.f, 0.f);
+  bool done = n <= 1;                                                   // star_shaped_search.cpp:112
+  int hit = -1;
+  int nmax = n;
+  for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+  for (int t0 = 0; t0 < nmax; t0 += 32) {
+    // stage tile [t0, t0 + 32) of every sector of this warp whose lane is still walking
+    for (int q = 0; q < 32; q++) {
+      const int qn = __shfl_sync(0xffffffffu, n, q), qbase = __shfl_sync(0xffffffffu, base, q);
+      const int qdone = __shfl_sync(0xffffffffu, (int)done, q);
+      if (qdone || t0 >= qn) continue;
+      const int e = t0 + lane;
+      if (e < qn) { const float4 p = all[qbase + e]; s_r[warp][q][lane] = p.x; s_z[warp][q][lane] = p.y; }
+    }
+    __syncwarp();
+    if (!done) {
+      const int e1 = min(32, n - t0);
+      for (int e = 0; e < e1; e++) {
+        const int i = t0 + e;
+        const float r = s_r[warp][lane][e], z = s_z[warp][lane][e];
+        if (i == 0) { star_init(st, r, z); continue; }
+        if (star_step(prm, st, i, r, z)) { hit = i; done = true; break; }
+      }
+      if (t0 + 32 >= n) done = true;
+    }
+    __syncwarp();
+    if (__all_sync(0xffffffffu, done)) break;
+  }
+  if (hit >= 0) buf.mark[(size_t)b * S + __float_as_int(all[base + hit].z)] = 2;   // star_shaped_search.cpp:146
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_ring_detect: one thread per ring-bucket position. Planar range + azimuth (lidar_segmentation.cpp:245-274), the
 // x-zero test for which this point is the middle point p2 (x_zero_method.cpp:30-67), the z-zero test centred on it
-// (z_zero_method.cpp:21-72), and the curb aggregates blindSpots needs.
+// (z_zero_method.cpp:21-72), the curb aggregates blindSpots needs and maxDistance per ring. The CTA stages its 256
+// bucket positions plus a halo of curb_points on each side in shared memory (plain global reads when curb_points
+// exceeds kHalo).
+constexpr int kHalo = 32;
 __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
-  const int R = out.n_rings, N = out.n_order;
+  const int N = out.n_order;
+  __shared__ float4 s_tile[256 + 2 * kHalo];
   __shared__ int s_rs[kRingKeys + 1];
+  const int p0 = blockIdx.x * blockDim.x;
+  if (p0 >= N) return;
   for (int t = threadIdx.x; t <= kRingKeys; t += blockDim.x) s_rs[t] = out.ring_start[t];
+  const float4* bucket = buf.bpt + (size_t)b * S;
+  const bool tiled = prm.curbPoints <= kHalo;
+  if (tiled) {
+    for (int t = threadIdx.x; t < 256 + 2 * kHalo; t += blockDim.x) {
+      const int p = p0 - kHalo + t;
+      if (p >= 0 && p < N) s_tile[t] = bucket[p];
+    }
+  }
   __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = p0 + threadIdx.x;
   const bool act = p < N;
   int k = -1;
   unsigned dbits = 0;
   if (act) {
-    k = ring_of(s_rs, R, p);
+    k = buf.bring[(size_t)b * S + p];
     const int base = s_rs[k], n = s_rs[k + 1] - base, m = p - base;
-    const float4* ring = buf.bpt + (size_t)b * S + base;
+    // ring[q] must address bucket position base + q: through the tile, or straight from global memory
+    const float4* ring = tiled ? (s_tile + (base - (p0 - kHalo))) : (bucket + base);
     const float4 me = ring[m];
-    const float x = me.x, y = me.y;
     const int idx = __float_as_int(me.w);
     float d, az;
-    planar_az(x, y, &d, &az);                                           // lidar_segmentation.cpp:245-269
+    planar_az(me.x, me.y, &d, &az);                                     // lidar_segmentation.cpp:245-269
     buf.az[(size_t)b * S + p] = az;
     buf.d2[(size_t)b * S + p] = d;
     dbits = fbits(d);
@@ -496,159 +691,140 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
   if (__all_sync(0xffffffffu, k == k0)) {
     if (k0 >= 0) {
       const unsigned mx = __reduce_max_sync(0xffffffffu, dbits);
-      if (lane_id() == 0) atomicMax(&buf.tab[b].maxdist[k0], mx);
+      if (lane_id() == 0 && buf.tab[b].maxdist[k0] < mx) atomicMax(&buf.tab[b].maxdist[k0], mx);
     }
   } else if (act) atomicMax(&buf.tab[b].maxdist[k], dbits);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// blindSpots as tables: see urf_logic.cuh (CurbView, window_reach, covered_by_window).
-__global__ void __launch_bounds__(384) k_tables(DevBuffers buf, DevParams prm) {
+// blindSpots as tables (urf_logic.cuh: CurbView, window_blocked, build_T_column, covered_T).
+// k_tab1: per scan — prefix counts of non-empty curb bins per ring, arc widths, q1..q4, reach := n_rings.
+__global__ void __launch_bounds__(256) k_tab1(DevBuffers buf, DevParams prm) {
   const int b = blockIdx.x;
   const ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
   const int R = out.n_rings;
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  for (int t = threadIdx.x; t < 2 * kDegBins; t += blockDim.x) tab.reach[t / kDegBins][t % kDegBins] = R;
   if (R <= 0) return;
   const size_t nb = (size_t)prm.channels * kDegBins;
-  CurbView cv{buf.cmin + (size_t)b * nb, buf.cmax + (size_t)b * nb, buf.ne + (size_t)b * prm.channels * (kDegBins + 1)};
+  const unsigned* cmin = buf.cmin + (size_t)b * nb;
   unsigned short* ne = buf.ne + (size_t)b * prm.channels * (kDegBins + 1);
-  __shared__ float s_q[4];
-  // (1) prefix count of non-empty curb bins per ring
-  for (int k = threadIdx.x; k < R; k += blockDim.x) {
-    unsigned short run = 0;
-    for (int bin = 0; bin < kDegBins; bin++) {
-      ne[(size_t)k * (kDegBins + 1) + bin] = run;
-      run += cv.cmin[(size_t)k * kDegBins + bin] != 0x7f800000u;
+  for (int k = warp; k < R; k += blockDim.x >> 5) {        // one warp per ring: 12 x 32 bins with a running carry
+    unsigned carry = 0;
+    for (int c = 0; c < (kDegBins + 31) / 32; c++) {
+      const int bin = c * 32 + lane;
+      const unsigned f = bin < kDegBins && cmin[(size_t)k * kDegBins + bin] != 0x7f800000u;
+      const unsigned bal = __ballot_sync(0xffffffffu, f);
+      if (bin < kDegBins) ne[(size_t)k * (kDegBins + 1) + bin] = (unsigned short)(carry + __popc(bal & ((1u << lane) - 1u)));
+      carry += __popc(bal);
     }
-    ne[(size_t)k * (kDegBins + 1) + kDegBins] = run;
+    if (lane == 0) ne[(size_t)k * (kDegBins + 1) + kDegBins] = (unsigned short)carry;
   }
-  // (2) per-ring arc widths, blind_spots.cpp:65,142
-  {
-    const float arc = arc_distance(prm, bitsf(tab.maxdist[0]));
-    for (int k = threadIdx.x; k < R; k += blockDim.x) tab.A[k] = ring_width(arc, bitsf(tab.maxdist[k]));
-  }
-  // (3) q1..q4 from the curb points of ring index 1, blind_spots.cpp:13-57
+  const float arc = arc_distance(prm, bitsf(tab.maxdist[0]));            // blind_spots.cpp:65
+  for (int k = threadIdx.x; k < R; k += blockDim.x) tab.A[k] = ring_width(arc, bitsf(tab.maxdist[k]));   // :142
   if (threadIdx.x < 4) {
-    const float q = blind_quarter(prm, cv, R, threadIdx.x);
-    s_q[threadIdx.x] = q;
-    tab.q[threadIdx.x] = q;
-  }
-  __syncthreads();
-  // (4) how many rings each window start accepts: forward (blind_spots.cpp:68-174) and backward (:177-283)
-  for (int t = threadIdx.x; t < 2 * kDegBins; t += blockDim.x) {
-    const int dir = t / kDegBins, i = t % kDegBins;
-    const int reach = window_reach(prm, cv, tab.A, s_q, R, dir, i);
-    tab.reach[dir][i] = (unsigned short)reach;
-    tab.st[dir][0][i] = (unsigned short)reach;
-  }
-  __syncthreads();
-  // (5) range-max sparse tables over the window starts
-  for (int l = 1; l < kStLevels; l++) {
-    for (int t = threadIdx.x; t < 2 * kDegBins; t += blockDim.x) {
-      const int dir = t / kDegBins, i = t % kDegBins;
-      const int j = i + (1 << (l - 1));
-      const unsigned short a = tab.st[dir][l - 1][i];
-      const unsigned short c = j < kDegBins ? tab.st[dir][l - 1][j] : (unsigned short)0;
-      tab.st[dir][l][i] = a > c ? a : c;
-    }
-    __syncthreads();
+    CurbView cv{cmin, buf.cmax + (size_t)b * nb, ne};
+    tab.q[threadIdx.x] = blind_quarter(prm, cv, R, threadIdx.x);         // :13-57
   }
 }
 
-// k_label: final label per ring-bucket position, scattered back to input order; counts; first non-road ring per bin.
+// k_reach: one thread per (direction, window start i, ring k) cell: does ring k hold a curb point inside window i?
+// reach[dir][i] = the first such ring (blind_spots.cpp:107-171 / :216-280 stop at it).
+__global__ void __launch_bounds__(256) k_reach(DevBuffers buf, DevParams prm) {
+  const int b = blockIdx.y;
+  const ScanOut& out = buf.out[b];
+  ScanTab& tab = buf.tab[b];
+  const int R = out.n_rings;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * kDegBins * R) return;
+  const int k = c % R, di = c / R, dir = di / kDegBins, i = di % kDegBins;
+  if (dir == 0 ? i > prm.fwd_last : i < prm.bwd_first) return;
+  if (tab.reach[dir][i] <= k) return;
+  const size_t nb = (size_t)prm.channels * kDegBins;
+  CurbView cv{buf.cmin + (size_t)b * nb, buf.cmax + (size_t)b * nb, buf.ne + (size_t)b * prm.channels * (kDegBins + 1)};
+  if (window_blocked(prm, cv, tab.A[k], dir, i, k)) atomicMin(&tab.reach[dir][i], k);
+}
+
+// k_tab2: one thread per ring builds its column of the two threshold tables.
+__global__ void __launch_bounds__(256) k_tab2(DevBuffers buf, DevParams prm) {
+  const int b = blockIdx.y;
+  const ScanOut& out = buf.out[b];
+  const ScanTab& tab = buf.tab[b];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= out.n_rings) return;
+  const size_t o = (size_t)b * kDegBins * prm.channels + k;
+  build_T_column(prm, tab.reach[0], tab.reach[1], tab.q, k, tab.A[k], buf.Tf + o, buf.Tb + o, prm.channels);
+}
+
+// k_label: final label per ring-bucket position, scattered back to input order; counts; per degree bin the first
+// non-road point in the reference's scan order; road points are appended to a compact list for the marker search.
 __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
-  const int R = out.n_rings, N = out.n_order;
-  __shared__ int s_rs[kRingKeys + 1];
-  __shared__ int s_road, s_curb;
-  for (int t = threadIdx.x; t <= kRingKeys; t += blockDim.x) s_rs[t] = out.ring_start[t];
-  if (threadIdx.x == 0) { s_road = 0; s_curb = 0; }
-  __syncthreads();
+  const int N = out.n_order;
+  if ((int)(blockIdx.x * blockDim.x) >= N) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  int lab = -1;
+  int lab = -1, k = 0, bin = 0;
+  float a = 0.f;
+  const size_t g = (size_t)b * S + p;
   if (p < N) {
-    const size_t g = (size_t)b * S + p;
-    const int k = ring_of(s_rs, R, p);
-    const float a = buf.az[g];
+    k = buf.bring[g];
+    a = buf.az[g];
     lab = buf.blabel[g];
-    if (lab != 2 && covered_by_window(prm, tab, k, a)) lab = 1;
+    const size_t o = (size_t)b * kDegBins * prm.channels;
+    if (lab != 2 && covered_T(buf.Tf + o, buf.Tb + o, prm.channels, k, a)) lab = 1;
     buf.blabel[g] = (unsigned char)lab;
-    const int idx = __float_as_int(buf.bpt[g].w);
-    buf.label[(size_t)b * S + idx] = lab;
-    if (lab != 1 && a >= 0.0f) {                   // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
-      const int bin = deg_bin(a);
-      if (tab.cut[bin] > k) atomicMin(&tab.cut[bin], k);
+    buf.label[(size_t)b * S + buf.bidx[g]] = lab;
+    if (a >= 0.0f) {
+      bin = deg_bin(a);
+      if (lab != 1) {                               // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
+        const unsigned long long key = best_key(k, fbits(a), p);
+        if (tab.cutbest[bin] > key) atomicMin(&tab.cutbest[bin], key);
+      }
     }
   }
   const unsigned br = __ballot_sync(0xffffffffu, lab == 1), bc = __ballot_sync(0xffffffffu, lab == 2);
-  if (lane_id() == 0) { if (br) atomicAdd(&s_road, __popc(br)); if (bc) atomicAdd(&s_curb, __popc(bc)); }
-  __syncthreads();
-  if (threadIdx.x == 0) { if (s_road) atomicAdd(&out.n_road, s_road); if (s_curb) atomicAdd(&out.n_curb, s_curb); }
+  int base = 0;
+  if (lane_id() == 0) {
+    if (br) base = atomicAdd(&out.n_road, __popc(br));
+    if (bc) atomicAdd(&out.n_curb, __popc(bc));
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (lab == 1) {
+    // one list slot per road point, handed out per warp from the running road count; a road point whose azimuth is NaN
+    // belongs to no degree bin and is listed as a placeholder
+    const int slot = base + __popc(br & ((1u << lane_id()) - 1u));
+    buf.roadlist[(size_t)b * S + slot] = a >= 0.0f ? make_uint4((unsigned)bin | ((unsigned)k << 16), fbits(a), fbits(buf.d2[g]), (unsigned)p)
+                                                   : make_uint4(0xffffffffu, 0u, 0u, 0u);
+  }
 }
 
-// Marker candidate vertices, lidar_segmentation.cpp:305-351, as three order-independent passes over the ring buckets:
-//   k_cutkey: first non-road point (azimuth, bucket position) of the cut ring of every bin
-//   k_dmax  : farthest candidate road point per bin (candidates: road points scanned before the first non-road point)
-//   k_best  : first candidate (ring, azimuth, position order) that reaches that distance (`d > maxDistanceRoad` is strict)
-__device__ __forceinline__ bool marker_point(const DevBuffers& buf, const ScanOut& out, const int* s_rs, int b, int S,
-                                             int p, int& k, int& lab, int& bin, unsigned& abits) {
-  if (p >= out.n_order) return false;
-  const size_t g = (size_t)b * S + p;
-  const float a = buf.az[g];
-  if (!(a >= 0.0f)) return false;
-  abits = fbits(a);
-  bin = deg_bin(a);
-  k = ring_of(s_rs, out.n_rings, p);
-  lab = buf.blabel[g];
-  return true;
-}
-
-__global__ void __launch_bounds__(256) k_cutkey(DevBuffers buf, int S) {
-  const int b = blockIdx.y;
-  const ScanOut& out = buf.out[b];
-  ScanTab& tab = buf.tab[b];
-  __shared__ int s_rs[kRingKeys + 1];
-  for (int t = threadIdx.x; t <= kRingKeys; t += blockDim.x) s_rs[t] = out.ring_start[t];
-  __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  int k, lab, bin; unsigned ab;
-  if (!marker_point(buf, out, s_rs, b, S, p, k, lab, bin, ab)) return;
-  if (lab != 1 && k == tab.cut[bin]) atomicMin(&tab.cutkey[bin], cut_key(ab, p));
-}
-
+// Marker candidate vertices, lidar_segmentation.cpp:305-351, over the compact road list:
+//   k_dmax: farthest candidate road point per bin (candidates: road points scanned before the bin's first non-road point)
+//   k_best: first candidate in scan order that reaches that distance (`d > maxDistanceRoad` is strict, :329)
 __global__ void __launch_bounds__(256) k_dmax(DevBuffers buf, int S) {
   const int b = blockIdx.y;
-  const ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
-  __shared__ int s_rs[kRingKeys + 1];
-  for (int t = threadIdx.x; t <= kRingKeys; t += blockDim.x) s_rs[t] = out.ring_start[t];
-  __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  int k, lab, bin; unsigned ab;
-  if (!marker_point(buf, out, s_rs, b, S, p, k, lab, bin, ab)) return;
-  if (marker_candidate(tab, k, lab, bin, ab, p)) {
-    const unsigned d = fbits(buf.d2[(size_t)b * S + p]);                 // :327 (same value as the ring's planar range)
-    if (tab.dmax[bin] < d) atomicMax(&tab.dmax[bin], d);
-  }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= buf.out[b].n_road) return;
+  const uint4 e = buf.roadlist[(size_t)b * S + t];
+  if (e.x == 0xffffffffu) return;
+  const int bin = e.x & 0xffff, k = e.x >> 16;
+  if (marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w) && tab.dmax[bin] < e.z) atomicMax(&tab.dmax[bin], e.z);
 }
 
 __global__ void __launch_bounds__(256) k_best(DevBuffers buf, int S) {
   const int b = blockIdx.y;
-  const ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
-  __shared__ int s_rs[kRingKeys + 1];
-  for (int t = threadIdx.x; t <= kRingKeys; t += blockDim.x) s_rs[t] = out.ring_start[t];
-  __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  int k, lab, bin; unsigned ab;
-  if (!marker_point(buf, out, s_rs, b, S, p, k, lab, bin, ab)) return;
-  if (marker_candidate(tab, k, lab, bin, ab, p)) {
-    const unsigned d = fbits(buf.d2[(size_t)b * S + p]);
-    if (d != 0u && d == tab.dmax[bin])                                   // :329 `d > maxDistanceRoad`, initial 0
-      atomicMin(&tab.best[bin], best_key(k, ab, p));
-  }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= buf.out[b].n_road) return;
+  const uint4 e = buf.roadlist[(size_t)b * S + t];
+  if (e.x == 0xffffffffu) return;
+  const int bin = e.x & 0xffff, k = e.x >> 16;
+  if (e.z != 0u && e.z == tab.dmax[bin] && marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w))
+    atomicMin(&tab.best[bin], best_key(k, e.y, (int)e.w));
 }
 
 // k_verts: compact the per-bin winners in bin order into markerPointsArray (lidar_segmentation.cpp:343-350).
@@ -670,7 +846,7 @@ __global__ void __launch_bounds__(384) k_verts(DevBuffers buf, int S) {
     const int p = (int)(tab.best[i] & 0xffffffull);
     const float4 q = buf.bpt[(size_t)b * S + p];
     out.vert[slot][0] = q.x; out.vert[slot][1] = q.y; out.vert[slot][2] = q.z;
-    out.vert[slot][3] = tab.cut[i] != 0x7fffffff ? 1.0f : 0.0f;         // redPoints, :320,348
+    out.vert[slot][3] = tab.cutbest[i] != ~0ull ? 1.0f : 0.0f;          // redPoints, :320,348
   }
   if (i == 0) out.n_vert = total;
 }
@@ -696,7 +872,7 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
   bool tie = false;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const unsigned long long key = keys[t];
-    buf.order[g0 + t] = __float_as_int(buf.bpt[g0 + (unsigned)key].w);
+    buf.order[g0 + t] = buf.bidx[g0 + (unsigned)key];
     if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(key >> 32)) tie = true;
   }
   if (tie) atomicOr(&out.flags, F_TIE_AZIMUTH);

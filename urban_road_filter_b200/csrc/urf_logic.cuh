@@ -92,6 +92,26 @@ URF_HD int assign_ring(const float* angle, int R, float a, float interval, int* 
   return (lo < R && fabsf(URF_FSUB(angle[lo], a)) <= interval) ? lo : -1;    // :228
 }
 
+// Fine elevation bin of an angle (speculation bins of k_points and the ring-search lookup table); monotone in a.
+URF_HD int elev_bin(float a) {
+  int bin = (int)(a * (kElevBins / 180.0f));
+  return bin < 0 ? 0 : (bin > kElevBins ? kElevBins : bin);
+}
+// Lookup table entry for elevation bin e: the ring search start for an angle one whole bin below e, which is <= the
+// search start of every angle that falls into bin e (assign_ring's `lo` is non-decreasing in the angle).
+URF_HD int ring_lut_entry(const float* angle, int R, float interval, int e) {
+  int lo;
+  assign_ring(angle, R, (float)(e - 1) * (180.0f / kElevBins), interval, &lo);
+  return lo;
+}
+// assign_ring with the binary search replaced by a short linear walk from a lookup-table start (start <= lo)
+URF_HD int assign_ring_from(const float* angle, int R, float a, float interval, int start, int* lo_out) {
+  int lo = start;
+  while (lo < R && !(URF_FSUB(angle[lo], a) >= -interval)) lo++;
+  *lo_out = lo;
+  return (lo < R && fabsf(URF_FSUB(angle[lo], a)) <= interval) ? lo : -1;    // :228
+}
+
 // Verification of a speculated registration for input point i (see k_register): true = the sequential algorithm of
 // lidar_segmentation.cpp:170-196 would have behaved differently at this point, i.e. the speculation is wrong.
 URF_HD bool registration_violation(const float* angle, const int* regidx, const int* regorder, int R, int channels,
@@ -155,30 +175,34 @@ URF_HD bool zzero_mark(const DevParams& prm, const float4* ring, int n, int m) {
   return al <= prm.angleFilter2;                                                                              // :66
 }
 
-// Edge search along one radius-sorted sector (star_shaped_search.cpp:112-150). pts[i] = (r, z, -, -).
-// Returns the local index of the point that gets marked, or -1.
+// Edge search along one radius-sorted sector (star_shaped_search.cpp:112-150) as a step function: state after point
+// i-1, fed point i (planar radius r, height z); returns true when point i gets marked (the scan then stops).
+struct StarState { float avg, dev, nan, bx, by; };
+URF_HD void star_init(StarState& s, float r0, float z0) { s.avg = 0.f; s.dev = 0.f; s.nan = 0.f; s.bx = r0; s.by = z0; }   // :118-121
+URF_HD bool star_step(const DevParams& prm, StarState& s, int i, float r, float z) {
+  const float ax = s.bx, ay = s.by;                                     // :125-128
+  s.bx = r; s.by = z;
+  const float dx = URF_FSUB(r, ax);
+  const float slp = URF_FDIV(URF_FSUB(z, ay), dx);                      // :27-30
+  if (isnan(slp)) s.nan = URF_FADD(s.nan, 1.0f);                        // :131-132
+  else {
+    const float im = URF_FSUB((float)i, s.nan);                         // i - nan
+    const float c1 = URF_FSUB(im, 1.0f);                                // i - nan - 1
+    const float c2 = URF_FDIV(1.0f, im);                                // 1 / (i - nan)
+    s.avg = URF_FMUL(s.avg, c1); s.avg = URF_FADD(s.avg, slp); s.avg = URF_FMUL(s.avg, c2);                    // :135-137
+    s.dev = URF_FMUL(s.dev, c1); s.dev = URF_FADD(s.dev, fabsf(URF_FSUB(slp, s.avg))); s.dev = URF_FMUL(s.dev, c2);   // :138-140
+  }
+  const float lhs = URF_FMUL(URF_FMUL(URF_FSUB(URF_FMUL(slp, slp), URF_FMUL(s.avg, s.avg)), prm.kdev),
+                             URF_FMUL(dx, prm.kdist));                  // :143
+  return slp > prm.slope_param || (i > prm.dmin && lhs > s.dev);        // :142-143
+}
+// whole sector at once: pts[i] = (r, z, -, -); returns the local index of the marked point or -1
 URF_HD int star_scan_sector(const DevParams& prm, const float4* pts, int n) {
   if (n <= 1) return -1;                                                // :112
-  float avg = 0.f, dev = 0.f, nan = 0.f;                                // :118
-  float4 q = pts[0];
-  float bx = q.x, by = q.y, ax, ay;
-  for (int i = 1; i < n; i++) {                                         // :123
-    q = pts[i];
-    ax = bx; bx = q.x; ay = by; by = q.y;
-    const float dx = URF_FSUB(bx, ax);
-    const float slp = URF_FDIV(URF_FSUB(by, ay), dx);                   // :27-30
-    if (isnan(slp)) nan = URF_FADD(nan, 1.0f);                          // :131-132
-    else {
-      const float im = URF_FSUB((float)i, nan);                         // i - nan
-      const float c1 = URF_FSUB(im, 1.0f);                              // i - nan - 1
-      const float c2 = URF_FDIV(1.0f, im);                              // 1 / (i - nan)
-      avg = URF_FMUL(avg, c1); avg = URF_FADD(avg, slp); avg = URF_FMUL(avg, c2);                 // :135-137
-      dev = URF_FMUL(dev, c1); dev = URF_FADD(dev, fabsf(URF_FSUB(slp, avg))); dev = URF_FMUL(dev, c2);   // :138-140
-    }
-    const float lhs = URF_FMUL(URF_FMUL(URF_FSUB(URF_FMUL(slp, slp), URF_FMUL(avg, avg)), prm.kdev),
-                               URF_FMUL(dx, prm.kdist));                // :143
-    if (slp > prm.slope_param || (i > prm.dmin && lhs > dev)) return i; // :142-146
-  }
+  StarState st;
+  star_init(st, pts[0].x, pts[0].y);
+  for (int i = 1; i < n; i++)                                           // :123
+    if (star_step(prm, st, i, pts[i].x, pts[i].y)) return i;            // :146
   return -1;
 }
 
@@ -269,7 +293,10 @@ URF_HD int window_reach(const DevParams& prm, const CurbView& cv, const double* 
   return k;
 }
 
-URF_HD int st_max(const ScanTab& tab, int dir, int lo, int hi) {                           // max reach over [lo, hi]
+// Reference formulation of the per-point window test (search for the window start range + range-max over reach); kept
+// for the CPU model, which checks that the threshold tables above give the same answer for every point.
+struct SparseMax { unsigned short st[2][kStLevels][kDegBins]; };
+URF_HD int st_max(const SparseMax& tab, int dir, int lo, int hi) {                           // max reach over [lo, hi]
   if (hi < lo) return 0;
   int l = 0;
   while ((2 << l) <= hi - lo + 1) l++;
@@ -278,9 +305,8 @@ URF_HD int st_max(const ScanTab& tab, int dir, int lo, int hi) {                
 }
 
 // road iff a forward or backward window start accepts ring k and contains azimuth a
-URF_HD bool covered_by_window(const DevParams& prm, const ScanTab& tab, int k, float a) {
+URF_HD bool covered_by_window(const DevParams& prm, const SparseMax& tab, double A, int k, float a) {
   if (!(a >= 0.0f)) return false;
-  const double A = tab.A[k];
   const double w = k == 0 ? (double)prm.beamZone : A;
   {  // forward: (float)i <= a and a <= hi(i); hi(i) >= a is monotone (false..false,true..true) in i
     int imax = (int)a; if (imax > prm.fwd_last) imax = prm.fwd_last;
@@ -306,6 +332,36 @@ URF_HD bool covered_by_window(const DevParams& prm, const ScanTab& tab, int k, f
   return false;
 }
 
+// Threshold tables: for ring k and integer degree j, Tf[j][k] = hi_k(i*) with i* the LARGEST accepted window start
+// i <= j (forward), Tb[j][k] = lo_k(i*) with i* the SMALLEST accepted start i >= j (backward). hi_k and lo_k are
+// non-decreasing in i, so a point of ring k with azimuth a is covered iff a <= Tf[floor(a)][k] or Tb[ceil(a)][k] <= a.
+// `accepted`: i inside the loop range, not blind, and reach[dir][i] > k. Column k of both tables (stride = channels).
+URF_HD void build_T_column(const DevParams& prm, const int* reach_f, const int* reach_b, const float* q, int k, double A,
+                           float* Tf, float* Tb, int stride) {
+  int last = -1;
+  for (int j = 0; j < kDegBins; j++) {
+    if (j <= prm.fwd_last && reach_f[j] > k && !is_blind(prm, q, j)) last = j;
+    Tf[(size_t)j * stride] = last >= 0 ? fwd_hi(prm, k, last, A) : -INFINITY;
+  }
+  int nxt = -1;
+  for (int j = kDegBins - 1; j >= 0; j--) {
+    if (j >= prm.bwd_first && reach_b[j] > k && !is_blind(prm, q, j)) nxt = j;
+    Tb[(size_t)j * stride] = nxt >= 0 ? bwd_lo(prm, k, nxt, A) : INFINITY;
+  }
+}
+URF_HD bool covered_T(const float* Tf, const float* Tb, int stride, int k, float a) {
+  if (!(a >= 0.0f)) return false;
+  int j = (int)a; if (j > 360) j = 360;
+  if (a <= Tf[(size_t)j * stride + k]) return true;
+  int jc = j; if ((float)jc < a) jc++;
+  return jc <= 360 && Tb[(size_t)jc * stride + k] <= a;
+}
+// first ring with a curb point inside window start i of direction dir, given the per-cell test (k_reach evaluates the
+// cells in parallel and keeps the minimum): true when ring k blocks window i
+URF_HD bool window_blocked(const DevParams& prm, const CurbView& cv, double A, int dir, int i, int k) {
+  return dir == 0 ? cv.fwd(k, i, fwd_hi(prm, k, i, A)) : cv.bwd(k, i, bwd_lo(prm, k, i, A));
+}
+
 // integer-degree bin of an azimuth (lidar_segmentation.cpp:318: `alpha >= i && alpha < i + 1`), a >= 0
 URF_HD int deg_bin(float a) { int bin = (int)a; return bin > 360 ? 360 : bin; }
 
@@ -314,11 +370,10 @@ URF_HD unsigned long long cut_key(unsigned az_bits, int p) { return ((unsigned l
 URF_HD unsigned long long best_key(int k, unsigned az_bits, int p) {
   return ((unsigned long long)k << 56) | ((unsigned long long)az_bits << 24) | (unsigned)p;
 }
-// road point (lab == 1) of ring k scanned before the first non-road point of its bin?
-URF_HD bool marker_candidate(const ScanTab& tab, int k, int lab, int bin, unsigned az_bits, int p) {
-  if (lab != 1) return false;
-  const int c = tab.cut[bin];
-  return k < c || (k == c && cut_key(az_bits, p) < tab.cutkey[bin]);
+// road point of ring k scanned before the first non-road point of its bin? cutbest = min best_key over the bin's
+// non-road points (~0 if none): (ring, azimuth, position) order is the reference's scan order (:313-316)
+URF_HD bool marker_candidate(unsigned long long cutbest, int k, unsigned az_bits, int p) {
+  return best_key(k, az_bits, p) < cutbest;
 }
 
 }  // namespace urf
