@@ -228,7 +228,7 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     for (int bin = 0; bin < kDegBins; bin++) { ne[(size_t)k * (kDegBins + 1) + bin] = run; run += cmin[(size_t)k * kDegBins + bin] != 0x7f800000u; }
     ne[(size_t)k * (kDegBins + 1) + kDegBins] = run;
   }
-  std::vector<float> Tf((size_t)kDegBins * prm.channels, 0.f), Tb((size_t)kDegBins * prm.channels, 0.f);
+  std::vector<float> Tf((size_t)kTStride * prm.channels, 0.f), Tb((size_t)kTStride * prm.channels, 0.f);
   SparseMax* spm = new SparseMax();
   {
     const float arc = arc_distance(prm, bitsf(tab.maxdist[0]));
@@ -242,7 +242,7 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
         for (int k = R - 1; k >= 0; k--) if (window_blocked(prm, cv, tab.A[k], dir, i, k)) tab.reach[dir][i] = k;
       }
     // k_tab2
-    for (int k = 0; k < R; k++) build_T_column(prm, tab.reach[0], tab.reach[1], tab.q, k, tab.A[k], Tf.data() + k, Tb.data() + k, prm.channels);
+    for (int k = 0; k < R; k++) build_T_row(prm, tab.reach[0], tab.reach[1], tab.q, k, tab.A[k], Tf.data() + (size_t)k * kTStride, Tb.data() + (size_t)k * kTStride);
     // cross-check tables: the sequential reach (window_reach) and the window-search formulation of the per-point test
     for (int dir = 0; dir < 2; dir++)
       for (int i = 0; i < kDegBins; i++) {
@@ -267,7 +267,7 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
   for (int p = 0; p < N; p++) {
     const int k = pring[p];
     int lab = blabel[p];
-    const bool cov = covered_T(Tf.data(), Tb.data(), prm.channels, k, az[p]);
+    const bool cov = covered_T(Tf.data(), Tb.data(), k, az[p]);
     if (cov != covered_by_window(prm, *spm, tab.A[k], k, az[p])) formulation_mismatch++;
     if (lab != 2 && cov) lab = 1;
     blabel[p] = (unsigned char)lab;

@@ -1,5 +1,6 @@
 // urf_api.cu — host side of liburf_b200.so: context, parameter narrowing, pipeline launcher and the C-ABI of include/urf.h.
 // There is no CPU fallback in this library: without a CUDA device every compute entry point returns an error.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -98,15 +99,16 @@ int launch_pipeline(urf_ctx* ctx, int B, int S, bool want_order) {
   K("k_scan_offsets", k_scan_offsets<<<B, 1024, 0, st>>>(buf, T));
   K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
   if (dp.star) {
-    K("k_star_bsort_warp", k_star_bsort_warp<<<dim3((kSectKeys + kStarWarps - 1) / kStarWarps, B), kStarWarps * 32, 0, st>>>(buf, S));
-    K("k_star_bsort_cta", k_star_bsort_cta<<<dim3(kSectKeys, B), 256, kStarCtaSmem, st>>>(buf, S));
-    K("k_star_sort", k_star_sort<<<dim3(kSectKeys, B), 128, 0, st>>>(buf, S));
+    const int gbig = std::max(4, std::min(kSectKeys, 2048 / B)), gslow = std::max(2, std::min(kSectKeys, 512 / B));
+    K("k_star_radix_warp", k_star_radix_warp<<<dim3((kSectKeys + kStarWarps - 1) / kStarWarps, B), kStarWarps * 32, 0, st>>>(buf, S));
+    K("k_star_radix_cta", k_star_radix_cta<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
+    K("k_star_sort", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S));
     K("k_star_scan", k_star_scan<<<dim3((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B), kScanWarps * 32, 0, st>>>(buf, dp, S));
   }
   K("k_ring_detect", k_ring_detect<<<gpts, 256, 0, st>>>(buf, dp, S));
   K("k_tab1", k_tab1<<<B, 256, 0, st>>>(buf, dp));
   K("k_reach", k_reach<<<dim3((2 * kDegBins * dp.channels + 255) / 256, B), 256, 0, st>>>(buf, dp));
-  K("k_tab2", k_tab2<<<dim3((dp.channels + 255) / 256, B), 256, 0, st>>>(buf, dp));
+  K("k_tab2", k_tab2<<<dim3((2 * dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
   K("k_label", k_label<<<gpts, 256, 0, st>>>(buf, dp, S));
   K("k_dmax", k_dmax<<<gpts, 256, 0, st>>>(buf, S));
   K("k_best", k_best<<<gpts, 256, 0, st>>>(buf, S));
@@ -207,8 +209,8 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   TRY(dalloc(ctx, &b.bring, P));
   TRY(dalloc(ctx, &b.bidx, P));
   TRY(dalloc(ctx, &b.roadlist, P));
-  TRY(dalloc(ctx, &b.Tf, (size_t)max_batch * kDegBins * URF_MAX_CHANNELS));
-  TRY(dalloc(ctx, &b.Tb, (size_t)max_batch * kDegBins * URF_MAX_CHANNELS));
+  TRY(dalloc(ctx, &b.Tf, (size_t)max_batch * kTStride * URF_MAX_CHANNELS));
+  TRY(dalloc(ctx, &b.Tb, (size_t)max_batch * kTStride * URF_MAX_CHANNELS));
   TRY(dalloc(ctx, &b.lut, (size_t)max_batch * (kElevBins + 1)));
   TRY(dalloc(ctx, &b.order, P));
   TRY(dalloc(ctx, &b.sortbuf, 2 * P));
@@ -237,7 +239,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
     CKF(cudaMemcpyToSymbol(c_beam_yx, byx, sizeof(byx)));
     ctx->dp.Kfi = Kfi;
   }
-  CKF(cudaFuncSetAttribute(k_star_bsort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
+  CKF(cudaFuncSetAttribute(k_star_radix_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
   CKF(cudaFuncSetAttribute(k_sort_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingSmemKeys * sizeof(unsigned long long))));
   urf_default_params(&ctx->params);
   const char* fe = std::getenv("URF_FORCE_EXACT_REGISTRATION");

@@ -62,7 +62,8 @@ struct ScanTab {
   int sect_start[kSectKeys + 1];
   int sect_cnt[kSectKeys];         // points per star sector (unstable partition: counted with atomics)
   int sect_cur[kSectKeys];         // scatter cursors
-  unsigned char sflag[kSectKeys];  // sector needs the slow sort path (degenerate radius distribution)
+  int nbig, nslow;                 // work lists of the star sort: sectors for the CTA radix sort / the bitonic fallback
+  unsigned short biglist[kSectKeys], slowlist[kSectKeys];
   float q[4];                      // q1..q4 (blind_spots.cpp:13-57)
   int reach[2][kDegBins];          // rings accepted by window start i, forward / backward (atomicMin over cells)
   unsigned long long cutbest[kDegBins];              // min (ring, azimuth bits, bucket pos) over the bin's non-road points
@@ -87,8 +88,8 @@ struct DevBuffers {
   unsigned char* bring;  // [P]   ring index per bucket position
   int* bidx;             // [P]   input index per bucket position
   uint4* roadlist;       // [P]   compact list of road points: (bin | ring << 16, azimuth bits, range bits, bucket pos)
-  float* Tf;             // [B][kDegBins][channels] forward threshold table (urf_logic.cuh build_T_column)
-  float* Tb;             // [B][kDegBins][channels] backward threshold table
+  float* Tf;             // [B][channels][kTStride] forward threshold table (urf_logic.cuh build_T_row)
+  float* Tb;             // [B][channels][kTStride] backward threshold table
   unsigned short* lut;   // [B][kElevBins + 1] ring-search start per fine elevation bin
   int* order;            // [P]   emission order (input indices), only when requested
   unsigned long long* sortbuf;   // [2P] scratch for segments too large for shared memory

@@ -7,7 +7,7 @@
 //
 // Pipeline (DESIGN.md has the picture):
 //   k_reset -> k_points -> k_register -> k_assign -> [k_register_exact -> k_assign(redo) -> k_mark_exact]
-//   -> k_scan_offsets -> k_scatter -> k_star_bsort_warp / k_star_bsort_cta / k_star_sort(fallback) -> k_star_scan
+//   -> k_scan_offsets -> k_scatter -> k_star_radix_warp / k_star_radix_cta / k_star_sort(fallback) -> k_star_scan
 //   -> k_ring_detect -> k_tab1 -> k_reach -> k_tab2 -> k_label -> k_dmax -> k_best -> k_verts
 //   [-> k_sort_rings when the emission order is requested]
 #pragma once
@@ -55,7 +55,8 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
   for (int i = tid; i <= kRingKeys; i += nth) o.ring_start[i] = 0;
   for (int i = tid; i < kRingKeys; i += nth) { t.maxdist[i] = 0u; t.angle[i] = 0.f; t.regidx[i] = 0x7fffffff; t.regorder[i] = 0x7fffffff; }
   for (int i = tid; i < kDegBins; i += nth) { t.cutbest[i] = ~0ull; t.dmax[i] = 0u; t.best[i] = ~0ull; }
-  for (int i = tid; i < kSectKeys; i += nth) { t.sect_cnt[i] = 0; t.sflag[i] = 0; }
+  for (int i = tid; i < kSectKeys; i += nth) t.sect_cnt[i] = 0;
+  if (tid == 0) { t.nbig = 0; t.nslow = 0; }
   unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1);
   for (int i = tid; i <= kElevBins; i += nth) fi[i] = 0xffffffffu;
   const size_t nb = (size_t)prm.channels * kDegBins;
@@ -450,155 +451,227 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
 // Star-shaped search, sort by planar radius (star_shaped_search.cpp:109). Order: (r, input index) — the reference's
 // introsort order for equal r is unspecified; ties raise F_TIE_SECTOR.
 //
-// Fast path: one-pass bucket sort. Radius bits are mapped onto ~n buckets with an adaptive shift, counted and scattered
-// in shared memory, and every element ranks itself inside its (tiny) bucket. A sector whose radii pile up in one bucket
-// (more than kBucketMax) is flagged for the bitonic fallback below. GROUP = 32: one warp per sector (n <= kWarpCap);
-// GROUP = 256: one CTA per sector (n <= kCtaCap).
-constexpr int kWarpCap = 512, kCtaCap = 8192, kBucketMax = 48, kStarWarps = 6;
+// Stable LSD radix sort in shared memory on (radius bits - sector minimum), 9 bits per pass, only as many passes as the
+// sector's radius range needs (3 for a street scene). Independent of how the radii are distributed (wall returns pile up
+// within millimetres). Equal radii are then ordered by input index in a tiny fix-up. GROUP = 32: one warp per sector
+// (n <= kWarpCap); GROUP = 256: one CTA per sector from a work list (n <= kCtaCap); anything else (or a sector with a
+// run of more than kTieMax equal radii) goes to the bitonic fallback.
+constexpr int kWarpCap = 512, kCtaCap = 8192, kTieMax = 128, kStarWarps = 6, kRadix = 512, kRadixBits = 9;
 
 template <int GROUP>
 __device__ __forceinline__ void group_sync() { if (GROUP == 32) __syncwarp(); else __syncthreads(); }
 
+// returns true if the sector must be redone by the fallback
 template <int GROUP, int CAP>
-__device__ void bucket_sort_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid,
-                                   unsigned* s_cnt /*CAP + 2*/, unsigned long long* s_key /*CAP*/, unsigned short* s_el /*CAP*/,
-                                   unsigned* s_w /*GROUP / 32*/, int* tie_out, unsigned char* slow_flag) {
-  // (1) range of the radius bits
+__device__ bool radix_sort_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid, unsigned* keyA,
+                                  unsigned* keyB, unsigned short* elA, unsigned short* elB, unsigned short* cnt /*[W][kRadix]*/,
+                                  unsigned* s_misc /*[2 + W]*/, int* tie_out) {
+  constexpr int W = GROUP / 32;
+  const int warp = tid >> 5, lane = tid & 31;
+  // (1) keys relative to the sector minimum
   unsigned mn = 0xffffffffu, mx = 0u;
-  for (int e = tid; e < n; e += GROUP) { const unsigned v = fbits(src[e].x); mn = min(mn, v); mx = max(mx, v); }
-  if (tid == 0) { s_cnt[CAP] = 0xffffffffu; s_cnt[CAP + 1] = 0u; }
+  for (int e = tid; e < n; e += GROUP) { const unsigned v = fbits(src[e].x); keyA[e] = v; elA[e] = (unsigned short)e; mn = min(mn, v); mx = max(mx, v); }
+  if (tid == 0) { s_misc[0] = 0xffffffffu; s_misc[1] = 0u; }
   group_sync<GROUP>();
   for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-  if ((tid & 31) == 0) { atomicMin(&s_cnt[CAP], mn); atomicMax(&s_cnt[CAP + 1], mx); }
+  if (lane == 0) { atomicMin(&s_misc[0], mn); atomicMax(&s_misc[1], mx); }
   group_sync<GROUP>();
-  mn = s_cnt[CAP]; mx = s_cnt[CAP + 1];
-  int nb = next_pow2(n); if (nb > CAP) nb = CAP;
-  int shift = 0;
-  while (((mx - mn) >> shift) >= (unsigned)nb) shift++;
-  // (2) count
-  for (int t = tid; t < nb; t += GROUP) s_cnt[t] = 0;
+  mn = s_misc[0]; mx = s_misc[1];
+  for (int e = tid; e < n; e += GROUP) keyA[e] -= mn;
   group_sync<GROUP>();
-  for (int e = tid; e < n; e += GROUP) atomicAdd(&s_cnt[(fbits(src[e].x) - mn) >> shift], 1u);
-  group_sync<GROUP>();
-  // (3) exclusive scan over nb buckets (each thread owns a contiguous run of nb / GROUP buckets)
-  {
-    const int per = (nb + GROUP - 1) / GROUP;
-    const int t0 = min(nb, tid * per), t1 = min(nb, t0 + per);
-    unsigned sum = 0;
-    for (int t = t0; t < t1; t++) sum += s_cnt[t];
-    unsigned inc = sum;
-    for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += v; }
-    unsigned woff = 0;
-    if (GROUP > 32) {
-      if ((tid & 31) == 31) s_w[tid >> 5] = inc;
-      __syncthreads();
-      for (int w = 0; w < (tid >> 5); w++) woff += s_w[w];
+  const unsigned range = mx - mn;
+  const int nbits = range ? 32 - __clz(range) : 0;
+  const int passes = (nbits + kRadixBits - 1) / kRadixBits;
+  const int per = (((n + W - 1) / W) + 31) & ~31;              // contiguous slice per warp, multiple of 32
+  const int s0 = min(n, warp * per), s1 = min(n, s0 + per);
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned short* mycnt = cnt + warp * kRadix;
+  for (int pass = 0; pass < passes; pass++) {
+    const int shift = pass * kRadixBits;
+    for (int t = tid; t < W * kRadix; t += GROUP) cnt[t] = 0;
+    group_sync<GROUP>();
+    unsigned packed[CAP / GROUP];
+#pragma unroll
+    for (int it = 0; it < CAP / GROUP; it++) {
+      const int e = s0 + it * 32 + lane;
+      const bool valid = e < s1;
+      const int d = valid ? (int)((keyA[e] >> shift) & (kRadix - 1)) : -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      unsigned pk = 0xffffffffu;
+      if (valid) pk = ((unsigned)d << 16) | (mycnt[d] + __popc(peers & lt));
+      __syncwarp();
+      if (valid && lane == __ffs(peers) - 1) mycnt[d] += (unsigned short)__popc(peers);
+      __syncwarp();
+      packed[it] = pk;
     }
-    unsigned run = woff + inc - sum;
-    for (int t = t0; t < t1; t++) { unsigned v = s_cnt[t]; s_cnt[t] = run; run += v; }
+    group_sync<GROUP>();
+    // digit-major, warp-minor exclusive offsets: each thread owns kRadix / GROUP consecutive digits
+    {
+      constexpr int DPT = kRadix / GROUP;
+      unsigned tot[DPT], sum = 0;
+#pragma unroll
+      for (int j = 0; j < DPT; j++) {
+        unsigned t = 0;
+        for (int w = 0; w < W; w++) t += cnt[w * kRadix + tid * DPT + j];
+        tot[j] = t; sum += t;
+      }
+      unsigned inc = sum;
+      for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      unsigned woff = 0;
+      if (W > 1) {
+        if (lane == 31) s_misc[2 + warp] = inc;
+        __syncthreads();
+        for (int w = 0; w < warp; w++) woff += s_misc[2 + w];
+      }
+      unsigned run = woff + inc - sum;
+#pragma unroll
+      for (int j = 0; j < DPT; j++) {
+        unsigned r2 = run;
+        for (int w = 0; w < W; w++) { unsigned short* c = &cnt[w * kRadix + tid * DPT + j]; unsigned v = *c; *c = (unsigned short)r2; r2 += v; }
+        run += tot[j];
+      }
+    }
+    group_sync<GROUP>();
+#pragma unroll
+    for (int it = 0; it < CAP / GROUP; it++) {
+      const unsigned pk = packed[it];
+      if (pk != 0xffffffffu) {
+        const int e = s0 + it * 32 + lane;
+        const unsigned dstp = mycnt[pk >> 16] + (pk & 0xffffu);
+        keyB[dstp] = keyA[e];
+        elB[dstp] = elA[e];
+      }
+    }
+    group_sync<GROUP>();
+    unsigned* tk = keyA; keyA = keyB; keyB = tk;
+    unsigned short* te = elA; elA = elB; elB = te;
   }
-  group_sync<GROUP>();
-  // (4) scatter into bucket order (the cursor of bucket b ends at the start of bucket b + 1)
-  for (int e = tid; e < n; e += GROUP) {
-    const float4 p = src[e];
-    const unsigned v = fbits(p.x);
-    const unsigned slot = atomicAdd(&s_cnt[(v - mn) >> shift], 1u);
-    s_key[slot] = ((unsigned long long)v << 32) | (unsigned)__float_as_int(p.z);
-    s_el[slot] = (unsigned short)e;
-  }
-  group_sync<GROUP>();
-  // (5) rank inside the bucket and write out
+  // (2) write out; runs of equal radius are ordered by input index
   bool tie = false, slow = false;
   for (int q = tid; q < n; q += GROUP) {
-    const unsigned long long key = s_key[q];
-    const unsigned bkt = ((unsigned)(key >> 32) - mn) >> shift;
-    const int s = bkt ? (int)s_cnt[bkt - 1] : 0, e = (int)s_cnt[bkt];
-    if (e - s > kBucketMax) { slow = true; continue; }
+    const unsigned k = keyA[q];
+    const bool eq_l = q > 0 && keyA[q - 1] == k, eq_r = q + 1 < n && keyA[q + 1] == k;
+    if (!eq_l && !eq_r) { dst[q] = src[elA[q]]; continue; }
+    tie = true;
+    int s = q, e = q + 1;
+    while (s > 0 && keyA[s - 1] == k && q - s <= kTieMax) s--;
+    while (e < n && keyA[e] == k && e - q <= kTieMax) e++;
+    if (e - s > kTieMax) { slow = true; continue; }
+    const float4 me = src[elA[q]];
+    const int myidx = __float_as_int(me.z);
     int rank = 0;
-    for (int j = s; j < e; j++) {
-      const unsigned long long o = s_key[j];
-      rank += o < key;
-      tie |= (j != q) && ((unsigned)(o >> 32) == (unsigned)(key >> 32));
-    }
-    dst[s + rank] = src[s_el[q]];
+    for (int j = s; j < e; j++) rank += __float_as_int(src[elA[j]].z) < myidx;
+    dst[s + rank] = me;
   }
-  if (slow) *slow_flag = 1;
   if (tie) *tie_out = 1;
+  return slow;
 }
 
-__global__ void __launch_bounds__(kStarWarps * 32) k_star_bsort_warp(DevBuffers buf, int S) {
-  const int b = blockIdx.y, warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(kStarWarps * 32) k_star_radix_warp(DevBuffers buf, int S) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = lane_id();
   const int s = blockIdx.x * kStarWarps + warp;
-  __shared__ unsigned s_cnt[kStarWarps][kWarpCap + 2];
-  __shared__ unsigned long long s_key[kStarWarps][kWarpCap];
-  __shared__ unsigned short s_el[kStarWarps][kWarpCap];
+  __shared__ unsigned s_key[kStarWarps][2][kWarpCap];
+  __shared__ unsigned short s_el[kStarWarps][2][kWarpCap];
+  __shared__ unsigned short s_cnt[kStarWarps][kRadix];
+  __shared__ unsigned s_misc[kStarWarps][4];
   if (s >= kSectKeys) return;
   ScanTab& tab = buf.tab[b];
   const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
-  if (n <= 0 || n > kWarpCap) return;
+  if (n <= 0) return;
   const float4* src = buf.spt + (size_t)b * S + base;
   float4* dst = buf.ssorted + (size_t)b * S + base;
-  if (n == 1) { if (lane_id() == 0) dst[0] = src[0]; return; }
+  if (n == 1) { if (lane == 0) dst[0] = src[0]; return; }
+  if (n > kWarpCap) {                                                   // hand over to the CTA sort / the fallback
+    if (lane == 0) {
+      if (n <= kCtaCap) tab.biglist[atomicAdd(&tab.nbig, 1)] = (unsigned short)s;
+      else tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;
+    }
+    return;
+  }
   int tie = 0;
-  bucket_sort_sector<32, kWarpCap>(src, dst, n, lane_id(), s_cnt[warp], s_key[warp], s_el[warp], nullptr, &tie, &tab.sflag[s]);
-  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+  const bool slow = radix_sort_sector<32, kWarpCap>(src, dst, n, lane, s_key[warp][0], s_key[warp][1], s_el[warp][0], s_el[warp][1],
+                                                     s_cnt[warp], s_misc[warp], &tie);
+  if (__any_sync(0xffffffffu, slow) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;
+  if (__any_sync(0xffffffffu, tie) && lane == 0) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
 }
 
-constexpr size_t kStarCtaSmem = sizeof(unsigned long long) * kCtaCap + sizeof(unsigned) * (kCtaCap + 2) + sizeof(unsigned short) * kCtaCap + 64;
-__global__ void __launch_bounds__(256) k_star_bsort_cta(DevBuffers buf, int S) {
-  extern __shared__ unsigned long long s_raw64[];
-  const int b = blockIdx.y, s = blockIdx.x;
+constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap + 2 * sizeof(unsigned short) * kCtaCap + sizeof(unsigned short) * 8 * kRadix + 64;
+__global__ void __launch_bounds__(256) k_star_radix_cta(DevBuffers buf, int S) {
+  extern __shared__ unsigned s_dyn[];
+  const int b = blockIdx.y;
   ScanTab& tab = buf.tab[b];
-  const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
-  if (n <= kWarpCap || n > kCtaCap) return;
-  unsigned long long* s_key = s_raw64;
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(s_key + kCtaCap);
-  unsigned short* s_el = reinterpret_cast<unsigned short*>(s_cnt + kCtaCap + 2);
-  unsigned* s_w = reinterpret_cast<unsigned*>(s_el + kCtaCap);
-  int tie = 0;
-  bucket_sort_sector<256, kCtaCap>(buf.spt + (size_t)b * S + base, buf.ssorted + (size_t)b * S + base, n, threadIdx.x, s_cnt,
-                                   s_key, s_el, s_w, &tie, &tab.sflag[s]);
-  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+  unsigned* keyA = s_dyn;
+  unsigned* keyB = keyA + kCtaCap;
+  unsigned short* elA = reinterpret_cast<unsigned short*>(keyB + kCtaCap);
+  unsigned short* elB = elA + kCtaCap;
+  unsigned short* cnt = elB + kCtaCap;
+  unsigned* s_misc = reinterpret_cast<unsigned*>(cnt + 8 * kRadix);
+  __shared__ int s_flags[2];
+  const int nbig = tab.nbig;
+  for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
+    const int s = tab.biglist[w];
+    const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+    if (threadIdx.x < 2) s_flags[threadIdx.x] = 0;
+    __syncthreads();
+    int tie = 0;
+    const bool slow = radix_sort_sector<256, kCtaCap>(buf.spt + (size_t)b * S + base, buf.ssorted + (size_t)b * S + base, n, threadIdx.x,
+                                                       keyA, keyB, elA, elB, cnt, s_misc, &tie);
+    if (slow) s_flags[0] = 1;
+    if (tie) s_flags[1] = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_flags[0]) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;
+      if (s_flags[1]) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+    }
+    __syncthreads();
+  }
 }
 
-// Fallback: CTA-wide bitonic sort (shared memory up to 4096 keys, global scratch beyond) for sectors that are too large
-// for the bucket kernels or whose radii collapse into one bucket.
+// Fallback: CTA-wide bitonic sort on (radius bits, input index) keys (shared memory up to 4096 keys, global scratch
+// beyond) for sectors larger than kCtaCap or holding long runs of identical radii.
 constexpr int kStarSmemKeys = 4096;
 __global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S) {
-  const int b = blockIdx.y, s = blockIdx.x;
+  const int b = blockIdx.y;
   const ScanTab& tab = buf.tab[b];
-  const int base = tab.sect_start[s];
-  const int n = tab.sect_start[s + 1] - base;
-  if (n <= 1 || !(n > kCtaCap || tab.sflag[s])) return;
-  const float4* src = buf.spt + (size_t)b * S + base;
-  float4* dst = buf.ssorted + (size_t)b * S + base;
   __shared__ unsigned long long s_keys[kStarSmemKeys];
-  const int npad = next_pow2(n);
-  unsigned long long* keys = npad <= kStarSmemKeys ? s_keys : buf.sortbuf + 2 * ((size_t)b * S + base);
-  for (int t = threadIdx.x; t < npad; t += blockDim.x)
-    keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
-  __syncthreads();
-  cta_bitonic(keys, npad);
-  // keys hold (radius bits, input index) ascending: rebuild the records (z comes from the input record of that index)
-  bool tie = false;
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    const unsigned long long k = keys[t];
-    if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
-    const int idx = (int)(unsigned)k;
-    dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
+  const int nslow = tab.nslow;
+  for (int w = blockIdx.x; w < nslow; w += gridDim.x) {
+    const int s = tab.slowlist[w];
+    const int base = tab.sect_start[s];
+    const int n = tab.sect_start[s + 1] - base;
+    const float4* src = buf.spt + (size_t)b * S + base;
+    float4* dst = buf.ssorted + (size_t)b * S + base;
+    const int npad = next_pow2(n);
+    unsigned long long* keys = npad <= kStarSmemKeys ? s_keys : buf.sortbuf + 2 * ((size_t)b * S + base);
+    for (int t = threadIdx.x; t < npad; t += blockDim.x)
+      keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
+    __syncthreads();
+    cta_bitonic(keys, npad);
+    // keys hold (radius bits, input index) ascending: rebuild the records (z comes from the input record of that index)
+    bool tie = false;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      const unsigned long long k = keys[t];
+      if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
+      const int idx = (int)(unsigned)k;
+      dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
+    }
+    if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+    __syncthreads();
   }
-  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
 }
 
 // k_star_scan: one lane per sector walks its radius-sorted points with the reference's running mean / average absolute
-// deviation recurrence (star_shaped_search.cpp:112-150) and marks the first edge point. The warp stages 32-point tiles
-// of its 32 sectors in shared memory with coalesced loads; the serial walk then reads shared memory only.
-constexpr int kScanWarps = 4;
+// deviation recurrence (star_shaped_search.cpp:112-150) and marks the first edge point. Per 32-point tile the warp first
+// computes, 32 points of one sector at a time, everything that does not depend on the recurrence (slope, radius step,
+// 1 / i — including the IEEE divisions) into shared memory; the serial walk is then a dozen dependent float operations
+// per point.
+constexpr int kScanWarps = 2;
 __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = lane_id();
   const int s = (blockIdx.x * kScanWarps + warp) * 32 + lane;
-  __shared__ float s_r[kScanWarps][32][33];
-  __shared__ float s_z[kScanWarps][32][33];
+  __shared__ float s_slp[kScanWarps][32][33];
+  __shared__ float s_dxk[kScanWarps][32][33];
+  __shared__ float s_inv[kScanWarps][32][33];
   const ScanTab& tab = buf.tab[b];
   int base = 0, n = 0;
   if (s < kSectKeys) { base = tab.sect_start[s]; n = tab.sect_start[s + 1] - base; }
@@ -610,22 +683,25 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
   int nmax = n;
   for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
   for (int t0 = 0; t0 < nmax; t0 += 32) {
-    // stage tile [t0, t0 + 32) of every sector of this warp whose lane is still walking
-    for (int q = 0; q < 32; q++) {
+    for (int q = 0; q < 32; q++) {                                      // stage tile [t0, t0 + 32) of sector row q
       const int qn = __shfl_sync(0xffffffffu, n, q), qbase = __shfl_sync(0xffffffffu, base, q);
       const int qdone = __shfl_sync(0xffffffffu, (int)done, q);
       if (qdone || t0 >= qn) continue;
       const int e = t0 + lane;
-      if (e < qn) { const float4 p = all[qbase + e]; s_r[warp][q][lane] = p.x; s_z[warp][q][lane] = p.y; }
+      if (e < qn && e >= 1) {
+        const float4 p = all[qbase + e], pp = all[qbase + e - 1];
+        float dx;
+        s_slp[warp][q][lane] = star_slope(pp.x, pp.y, p.x, p.y, &dx);
+        s_dxk[warp][q][lane] = __fmul_rn(dx, prm.kdist);
+        s_inv[warp][q][lane] = star_inv(e);
+      }
     }
     __syncwarp();
     if (!done) {
       const int e1 = min(32, n - t0);
-      for (int e = 0; e < e1; e++) {
+      for (int e = (t0 == 0 ? 1 : 0); e < e1; e++) {
         const int i = t0 + e;
-        const float r = s_r[warp][lane][e], z = s_z[warp][lane][e];
-        if (i == 0) { star_init(st, r, z); continue; }
-        if (star_step(prm, st, i, r, z)) { hit = i; done = true; break; }
+        if (star_update(prm, st, i, s_slp[warp][lane][e], s_dxk[warp][lane][e], s_inv[warp][lane][e])) { hit = i; done = true; break; }
       }
       if (t0 + 32 >= n) done = true;
     }
@@ -667,9 +743,7 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
   if (act) {
     k = buf.bring[(size_t)b * S + p];
     const int base = s_rs[k], n = s_rs[k + 1] - base, m = p - base;
-    // ring[q] must address bucket position base + q: through the tile, or straight from global memory
-    const float4* ring = tiled ? (s_tile + (base - (p0 - kHalo))) : (bucket + base);
-    const float4 me = ring[m];
+    const float4 me = tiled ? s_tile[threadIdx.x + kHalo] : bucket[p];
     const int idx = __float_as_int(me.w);
     float d, az;
     planar_az(me.x, me.y, &d, &az);                                     // lidar_segmentation.cpp:245-269
@@ -677,8 +751,17 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
     buf.d2[(size_t)b * S + p] = d;
     dbits = fbits(d);
     int lab = prm.star ? buf.mark[(size_t)b * S + idx] : 0;             // :241-242
-    if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;   // x_zero_method.cpp:66
-    if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, n, m)) lab = 2;             // z_zero_method.cpp:71
+    // ring[q] must address bucket position base + q: through the shared tile, or straight from global memory (two code
+    // paths so that the compiler keeps the address space of the loads)
+    if (tiled) {
+      const float4* ring = s_tile + (base - (p0 - kHalo));
+      if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;   // x_zero_method.cpp:66
+      if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, n, m)) lab = 2;             // z_zero_method.cpp:71
+    } else {
+      const float4* ring = bucket + base;
+      if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;
+      if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, n, m)) lab = 2;
+    }
     buf.blabel[(size_t)b * S + p] = (unsigned char)lab;
     if (lab == 2 && az >= 0.0f) {            // curb aggregates per (ring, integer-degree bin); NaN azimuths fall out
       const size_t o = ((size_t)b * prm.channels + k) * kDegBins + deg_bin(az);
@@ -746,15 +829,39 @@ __global__ void __launch_bounds__(256) k_reach(DevBuffers buf, DevParams prm) {
   if (window_blocked(prm, cv, tab.A[k], dir, i, k)) atomicMin(&tab.reach[dir][i], k);
 }
 
-// k_tab2: one thread per ring builds its column of the two threshold tables.
+// k_tab2: one warp per (ring, direction) builds a row of a threshold table with a warp max/min scan over the 361
+// window starts (same result as the sequential build_T_row of urf_logic.cuh).
 __global__ void __launch_bounds__(256) k_tab2(DevBuffers buf, DevParams prm) {
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
   const ScanTab& tab = buf.tab[b];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id();
+  const int k = w >> 1, dir = w & 1;
   if (k >= out.n_rings) return;
-  const size_t o = (size_t)b * kDegBins * prm.channels + k;
-  build_T_column(prm, tab.reach[0], tab.reach[1], tab.q, k, tab.A[k], buf.Tf + o, buf.Tb + o, prm.channels);
+  const double A = tab.A[k];
+  const size_t o = ((size_t)b * prm.channels + k) * kTStride;
+  constexpr int NCH = (kDegBins + 31) / 32;
+  if (dir == 0) {
+    int carry = -1;
+    for (int c = 0; c < NCH; c++) {
+      const int j = c * 32 + lane;
+      int m = (j < kDegBins && accepted_fwd(prm, tab.reach[0], tab.q, k, j)) ? j : -1;
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, m, d); if (lane >= d) m = max(m, v); }
+      m = max(m, carry);
+      if (j < kDegBins) buf.Tf[o + j] = T_fwd_value(prm, k, m, A);
+      carry = __shfl_sync(0xffffffffu, m, 31);
+    }
+  } else {
+    int carry = 361;
+    for (int c = NCH - 1; c >= 0; c--) {
+      const int j = c * 32 + lane;
+      int m = (j < kDegBins && accepted_bwd(prm, tab.reach[1], tab.q, k, j)) ? j : 361;
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_down_sync(0xffffffffu, m, d); if (lane + d < 32) m = min(m, v); }
+      m = min(m, carry);
+      if (j < kDegBins) buf.Tb[o + j] = T_bwd_value(prm, k, m, A);
+      carry = __shfl_sync(0xffffffffu, m, 0);
+    }
+  }
 }
 
 // k_label: final label per ring-bucket position, scattered back to input order; counts; per degree bin the first
@@ -773,8 +880,8 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
     k = buf.bring[g];
     a = buf.az[g];
     lab = buf.blabel[g];
-    const size_t o = (size_t)b * kDegBins * prm.channels;
-    if (lab != 2 && covered_T(buf.Tf + o, buf.Tb + o, prm.channels, k, a)) lab = 1;
+    const size_t o = (size_t)b * prm.channels * kTStride;
+    if (lab != 2 && covered_T(buf.Tf + o, buf.Tb + o, k, a)) lab = 1;
     buf.blabel[g] = (unsigned char)lab;
     buf.label[(size_t)b * S + buf.bidx[g]] = lab;
     if (a >= 0.0f) {

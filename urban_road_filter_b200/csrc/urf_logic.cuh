@@ -179,22 +179,30 @@ URF_HD bool zzero_mark(const DevParams& prm, const float4* ring, int n, int m) {
 // i-1, fed point i (planar radius r, height z); returns true when point i gets marked (the scan then stops).
 struct StarState { float avg, dev, nan, bx, by; };
 URF_HD void star_init(StarState& s, float r0, float z0) { s.avg = 0.f; s.dev = 0.f; s.nan = 0.f; s.bx = r0; s.by = z0; }   // :118-121
-URF_HD bool star_step(const DevParams& prm, StarState& s, int i, float r, float z) {
-  const float ax = s.bx, ay = s.by;                                     // :125-128
-  s.bx = r; s.by = z;
-  const float dx = URF_FSUB(r, ax);
-  const float slp = URF_FDIV(URF_FSUB(z, ay), dx);                      // :27-30
+// slope between consecutive radius-sorted points (:27-30,125-129); *dx = r - r_prev
+URF_HD float star_slope(float r_prev, float z_prev, float r, float z, float* dx) {
+  *dx = URF_FSUB(r, r_prev);
+  return URF_FDIV(URF_FSUB(z, z_prev), *dx);
+}
+URF_HD float star_inv(int i) { return URF_FDIV(1.0f, (float)i); }       // 1 / (i - nan) while nan == 0
+// running mean / average absolute deviation update and edge test for point i (:131-148); inv_i = star_inv(i)
+URF_HD bool star_update(const DevParams& prm, StarState& s, int i, float slp, float dxk /* (bx - ax) * kdist */, float inv_i) {
   if (isnan(slp)) s.nan = URF_FADD(s.nan, 1.0f);                        // :131-132
   else {
     const float im = URF_FSUB((float)i, s.nan);                         // i - nan
     const float c1 = URF_FSUB(im, 1.0f);                                // i - nan - 1
-    const float c2 = URF_FDIV(1.0f, im);                                // 1 / (i - nan)
+    const float c2 = s.nan == 0.0f ? inv_i : URF_FDIV(1.0f, im);        // 1 / (i - nan)
     s.avg = URF_FMUL(s.avg, c1); s.avg = URF_FADD(s.avg, slp); s.avg = URF_FMUL(s.avg, c2);                    // :135-137
     s.dev = URF_FMUL(s.dev, c1); s.dev = URF_FADD(s.dev, fabsf(URF_FSUB(slp, s.avg))); s.dev = URF_FMUL(s.dev, c2);   // :138-140
   }
-  const float lhs = URF_FMUL(URF_FMUL(URF_FSUB(URF_FMUL(slp, slp), URF_FMUL(s.avg, s.avg)), prm.kdev),
-                             URF_FMUL(dx, prm.kdist));                  // :143
+  const float lhs = URF_FMUL(URF_FMUL(URF_FSUB(URF_FMUL(slp, slp), URF_FMUL(s.avg, s.avg)), prm.kdev), dxk);   // :143
   return slp > prm.slope_param || (i > prm.dmin && lhs > s.dev);        // :142-143
+}
+URF_HD bool star_step(const DevParams& prm, StarState& s, int i, float r, float z) {
+  float dx;
+  const float slp = star_slope(s.bx, s.by, r, z, &dx);
+  s.bx = r; s.by = z;
+  return star_update(prm, s, i, slp, URF_FMUL(dx, prm.kdist), star_inv(i));
 }
 // whole sector at once: pts[i] = (r, z, -, -); returns the local index of the marked point or -1
 URF_HD int star_scan_sector(const DevParams& prm, const float4* pts, int n) {
@@ -332,29 +340,38 @@ URF_HD bool covered_by_window(const DevParams& prm, const SparseMax& tab, double
   return false;
 }
 
-// Threshold tables: for ring k and integer degree j, Tf[j][k] = hi_k(i*) with i* the LARGEST accepted window start
-// i <= j (forward), Tb[j][k] = lo_k(i*) with i* the SMALLEST accepted start i >= j (backward). hi_k and lo_k are
-// non-decreasing in i, so a point of ring k with azimuth a is covered iff a <= Tf[floor(a)][k] or Tb[ceil(a)][k] <= a.
-// `accepted`: i inside the loop range, not blind, and reach[dir][i] > k. Column k of both tables (stride = channels).
-URF_HD void build_T_column(const DevParams& prm, const int* reach_f, const int* reach_b, const float* q, int k, double A,
-                           float* Tf, float* Tb, int stride) {
+// Threshold tables: for ring k and integer degree j, Tf[k][j] = hi_k(i*) with i* the LARGEST accepted window start
+// i <= j (forward), Tb[k][j] = lo_k(i*) with i* the SMALLEST accepted start i >= j (backward). hi_k and lo_k are
+// non-decreasing in i, so a point of ring k with azimuth a is covered iff a <= Tf[k][floor(a)] or Tb[k][ceil(a)] <= a.
+// `accepted`: i inside the loop range, not blind, and reach[dir][i] > k. Row stride kTStride.
+constexpr int kTStride = kDegBins + 3;
+URF_HD bool accepted_fwd(const DevParams& prm, const int* reach_f, const float* q, int k, int j) {
+  return j <= prm.fwd_last && reach_f[j] > k && !is_blind(prm, q, j);
+}
+URF_HD bool accepted_bwd(const DevParams& prm, const int* reach_b, const float* q, int k, int j) {
+  return j >= prm.bwd_first && reach_b[j] > k && !is_blind(prm, q, j);
+}
+URF_HD float T_fwd_value(const DevParams& prm, int k, int last, double A) { return last >= 0 ? fwd_hi(prm, k, last, A) : -INFINITY; }
+URF_HD float T_bwd_value(const DevParams& prm, int k, int nxt, double A) { return nxt <= 360 ? bwd_lo(prm, k, nxt, A) : INFINITY; }
+URF_HD void build_T_row(const DevParams& prm, const int* reach_f, const int* reach_b, const float* q, int k, double A,
+                        float* Tf, float* Tb) {
   int last = -1;
   for (int j = 0; j < kDegBins; j++) {
-    if (j <= prm.fwd_last && reach_f[j] > k && !is_blind(prm, q, j)) last = j;
-    Tf[(size_t)j * stride] = last >= 0 ? fwd_hi(prm, k, last, A) : -INFINITY;
+    if (accepted_fwd(prm, reach_f, q, k, j)) last = j;
+    Tf[j] = T_fwd_value(prm, k, last, A);
   }
-  int nxt = -1;
+  int nxt = 361;
   for (int j = kDegBins - 1; j >= 0; j--) {
-    if (j >= prm.bwd_first && reach_b[j] > k && !is_blind(prm, q, j)) nxt = j;
-    Tb[(size_t)j * stride] = nxt >= 0 ? bwd_lo(prm, k, nxt, A) : INFINITY;
+    if (accepted_bwd(prm, reach_b, q, k, j)) nxt = j;
+    Tb[j] = T_bwd_value(prm, k, nxt, A);
   }
 }
-URF_HD bool covered_T(const float* Tf, const float* Tb, int stride, int k, float a) {
+URF_HD bool covered_T(const float* Tf, const float* Tb, int k, float a) {
   if (!(a >= 0.0f)) return false;
   int j = (int)a; if (j > 360) j = 360;
-  if (a <= Tf[(size_t)j * stride + k]) return true;
+  if (a <= Tf[(size_t)k * kTStride + j]) return true;
   int jc = j; if ((float)jc < a) jc++;
-  return jc <= 360 && Tb[(size_t)jc * stride + k] <= a;
+  return jc <= 360 && Tb[(size_t)k * kTStride + jc] <= a;
 }
 // first ring with a curb point inside window start i of direction dir, given the per-cell test (k_reach evaluates the
 // cells in parallel and keeps the minimum): true when ring k blocks window i
