@@ -567,13 +567,66 @@ __device__ bool radix_sort_sector(const float4* __restrict__ src, float4* __rest
   return slow;
 }
 
-__global__ void __launch_bounds__(kStarWarps * 32) k_star_radix_warp(DevBuffers buf, int S) {
+// Warp sort for sectors of up to 32 * EPL points: bitonic network held in registers (blocked layout: lane l owns elements
+// l*EPL .. l*EPL+EPL-1), 64-bit keys (radius bits, input index) with the point's z as payload. Strides below EPL are
+// register-only compare-exchanges, larger strides go through shuffles; no shared memory, no dependent memory chain.
+template <int EPL>
+__device__ __forceinline__ void warp_bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int lane, int* tie_out) {
+  unsigned long long key[EPL];
+  float pay[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; r++) {
+    const int e = lane * EPL + r;
+    key[r] = ~0ull; pay[r] = 0.f;
+    if (e < n) { const float4 p = src[e]; key[r] = ((unsigned long long)fbits(p.x) << 32) | (unsigned)__float_as_int(p.z); pay[r] = p.y; }
+  }
+  constexpr int N = 32 * EPL;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < EPL) {
+#pragma unroll
+        for (int r = 0; r < EPL; r++) {
+          if ((r & j) == 0) {
+            const bool asc = k < EPL ? ((r & k) == 0) : ((lane & (k / EPL)) == 0 || k == N);
+            const bool sw = (key[r] > key[r | j]) == asc;
+            const unsigned long long ka = sw ? key[r | j] : key[r], kb = sw ? key[r] : key[r | j];
+            const float pa = sw ? pay[r | j] : pay[r], pb = sw ? pay[r] : pay[r | j];
+            key[r] = ka; key[r | j] = kb; pay[r] = pa; pay[r | j] = pb;
+          }
+        }
+      } else {
+        const int lj = j / EPL;
+        const bool lower = (lane & lj) == 0;
+        const bool asc = (lane & (k / EPL)) == 0 || k == N;
+        const bool keep_min = lower == asc;
+#pragma unroll
+        for (int r = 0; r < EPL; r++) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, key[r], lj);
+          const float op = __shfl_xor_sync(0xffffffffu, pay[r], lj);
+          const bool take = keep_min ? (o < key[r]) : (o > key[r]);
+          if (take) { key[r] = o; pay[r] = op; }
+        }
+      }
+    }
+  }
+  bool tie = false;
+#pragma unroll
+  for (int r = 0; r < EPL; r++) {
+    const int e = lane * EPL + r;
+    unsigned long long prev = r > 0 ? key[r - 1] : __shfl_up_sync(0xffffffffu, key[EPL - 1], 1);
+    if (e < n) {
+      dst[e] = make_float4(bitsf((unsigned)(key[r] >> 32)), pay[r], __int_as_float((int)(unsigned)key[r]), 0.f);
+      if (e > 0 && (unsigned)(prev >> 32) == (unsigned)(key[r] >> 32)) tie = true;
+    }
+  }
+  if (tie) *tie_out = 1;
+}
+
+__global__ void __launch_bounds__(kStarWarps * 32) k_star_sort_warp(DevBuffers buf, int S) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = lane_id();
   const int s = blockIdx.x * kStarWarps + warp;
-  __shared__ unsigned s_key[kStarWarps][2][kWarpCap];
-  __shared__ unsigned short s_el[kStarWarps][2][kWarpCap];
-  __shared__ unsigned short s_cnt[kStarWarps][kRadix];
-  __shared__ unsigned s_misc[kStarWarps][4];
   if (s >= kSectKeys) return;
   ScanTab& tab = buf.tab[b];
   const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
@@ -589,9 +642,9 @@ __global__ void __launch_bounds__(kStarWarps * 32) k_star_radix_warp(DevBuffers 
     return;
   }
   int tie = 0;
-  const bool slow = radix_sort_sector<32, kWarpCap>(src, dst, n, lane, s_key[warp][0], s_key[warp][1], s_el[warp][0], s_el[warp][1],
-                                                     s_cnt[warp], s_misc[warp], &tie);
-  if (__any_sync(0xffffffffu, slow) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;
+  if (n <= 128) warp_bitonic_sector<4>(src, dst, n, lane, &tie);
+  else if (n <= 256) warp_bitonic_sector<8>(src, dst, n, lane, &tie);
+  else warp_bitonic_sector<16>(src, dst, n, lane, &tie);
   if (__any_sync(0xffffffffu, tie) && lane == 0) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
 }
 
@@ -683,17 +736,29 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
   int nmax = n;
   for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
   for (int t0 = 0; t0 < nmax; t0 += 32) {
-    for (int q = 0; q < 32; q++) {                                      // stage tile [t0, t0 + 32) of sector row q
-      const int qn = __shfl_sync(0xffffffffu, n, q), qbase = __shfl_sync(0xffffffffu, base, q);
-      const int qdone = __shfl_sync(0xffffffffu, (int)done, q);
-      if (qdone || t0 >= qn) continue;
-      const int e = t0 + lane;
-      if (e < qn && e >= 1) {
-        const float4 p = all[qbase + e], pp = all[qbase + e - 1];
-        float dx;
-        s_slp[warp][q][lane] = star_slope(pp.x, pp.y, p.x, p.y, &dx);
-        s_dxk[warp][q][lane] = __fmul_rn(dx, prm.kdist);
-        s_inv[warp][q][lane] = star_inv(e);
+    // stage tile [t0, t0 + 32) of all 32 sector rows: 8 rows at a time so that the 16 loads of a group are in flight
+    // together (one L2 round trip per group instead of one per row)
+    for (int q0 = 0; q0 < 32; q0 += 8) {
+      float4 p[8], pp[8];
+      bool ok[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int q = q0 + u;
+        const int qn = __shfl_sync(0xffffffffu, n, q), qbase = __shfl_sync(0xffffffffu, base, q);
+        const int qdone = __shfl_sync(0xffffffffu, (int)done, q);
+        const int e = t0 + lane;
+        ok[u] = !qdone && e < qn && e >= 1;
+        const int at = ok[u] ? qbase + e : 1;
+        p[u] = all[at]; pp[u] = all[at - 1];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (ok[u]) {
+          float dx;
+          s_slp[warp][q0 + u][lane] = star_slope(pp[u].x, pp[u].y, p[u].x, p[u].y, &dx);
+          s_dxk[warp][q0 + u][lane] = __fmul_rn(dx, prm.kdist);
+          s_inv[warp][q0 + u][lane] = star_inv(t0 + lane);
+        }
       }
     }
     __syncwarp();
@@ -723,10 +788,8 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
   const ScanOut& out = buf.out[b];
   const int N = out.n_order;
   __shared__ float4 s_tile[256 + 2 * kHalo];
-  __shared__ int s_rs[kRingKeys + 1];
   const int p0 = blockIdx.x * blockDim.x;
   if (p0 >= N) return;
-  for (int t = threadIdx.x; t <= kRingKeys; t += blockDim.x) s_rs[t] = out.ring_start[t];
   const float4* bucket = buf.bpt + (size_t)b * S;
   const bool tiled = prm.curbPoints <= kHalo;
   if (tiled) {
@@ -742,7 +805,7 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
   unsigned dbits = 0;
   if (act) {
     k = buf.bring[(size_t)b * S + p];
-    const int base = s_rs[k], n = s_rs[k + 1] - base, m = p - base;
+    const int base = out.ring_start[k], n = out.ring_start[k + 1] - base, m = p - base;
     const float4 me = tiled ? s_tile[threadIdx.x + kHalo] : bucket[p];
     const int idx = __float_as_int(me.w);
     float d, az;

@@ -116,6 +116,8 @@ URF_HD int assign_ring_from(const float* angle, int R, float a, float interval, 
 // lidar_segmentation.cpp:170-196 would have behaved differently at this point, i.e. the speculation is wrong.
 URF_HD bool registration_violation(const float* angle, const int* regidx, const int* regorder, int R, int channels,
                                    float interval, float a, int i, int lo) {
+  // common case first: the first covering angle was itself registered at or before point i
+  if (lo < R && regidx[lo] <= i && fabsf(URF_FSUB(angle[lo], a)) <= interval) return false;
   int minreg = 0x7fffffff;
   for (int j = lo; j < R && fabsf(URF_FSUB(angle[j], a)) <= interval; j++) minreg = regidx[j] < minreg ? regidx[j] : minreg;
   if (minreg <= i) return false;           // covered by an angle registered at or before i (== i: i is the registrant)
