@@ -187,3 +187,22 @@ def test_gpu_full_size_c5_and_properties(port):
         assert a.n_roi == b.n_roi
     finally:
         d.close()
+
+
+def test_gpu_pipelined_host_batch(port):
+    """Batches of 16+ scans go through the chunked three-stream pipeline (H2D / kernels / D2H overlap): same results."""
+    d = api.Detector(max_points=30_000, max_batch=24)
+    try:
+        prm = make_params(**FULL_ROI)
+        d.set_params(prm)
+        clouds = [make_scan("C1", 40 + s, order=("column", "ring")[s % 2])[: 28800 - 997 * (s % 5)] for s in range(21)]
+        clouds[7] = clouds[7][:20]                      # fewer than 30 ROI points: nothing published for this one
+        clouds[13] = random_cloud(5000, 5)              # speculation failure inside a chunk
+        rs = d.filtered_batch(clouds)
+        for c, r in zip(clouds, rs):
+            o = port.run(c, prm)
+            assert o.status == r.status
+            if o.status == 0:
+                assert stage_diffs(o, r, c.shape[0]) == []
+    finally:
+        d.close()

@@ -19,7 +19,9 @@ struct urf_ctx {
   int max_batch = 0;
   size_t P = 0;            // max_batch * max_points
   int Tmax = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams of the pipelined host-buffer path
+  std::vector<cudaEvent_t> ev_in, ev_comp;        // per chunk: input landed / results ready
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuffers buf{};
   float4* own_in = nullptr;
@@ -65,9 +67,23 @@ __global__ void k_ring32(DevBuffers buf, int* dst, int S) {
   if (i < buf.n[b]) dst[(size_t)b * S + i] = buf.ringid[(size_t)b * S + i];
 }
 
-int launch_pipeline(urf_ctx* ctx, int B, int S, bool want_order) {
+// All per-scan arrays of `buf` advanced by b0 scans (S points of stride, T histogram rows per scan).
+DevBuffers offset_view(const DevBuffers& a, int b0, int S, int T, int channels) {
+  DevBuffers v = a;
+  const size_t o = (size_t)b0 * S;
+  v.in += o; v.alpha_v += o; v.mark += o; v.ringid += o; v.sect += o; v.label += o; v.bpt += o; v.spt += o; v.ssorted += o;
+  v.az += o; v.d2 += o; v.blabel += o; v.bring += o; v.bidx += o; v.roadlist += o; v.order += o; v.sortbuf += 2 * o;
+  v.Tf += (size_t)b0 * channels * kTStride; v.Tb += (size_t)b0 * channels * kTStride;
+  v.lut += (size_t)b0 * (kElevBins + 1); v.firstidx += (size_t)b0 * (kElevBins + 1);
+  v.hist += (size_t)b0 * T * kRingKeys;
+  v.cmin += (size_t)b0 * channels * kDegBins; v.cmax += (size_t)b0 * channels * kDegBins;
+  v.ne += (size_t)b0 * channels * (kDegBins + 1);
+  v.n += b0; v.out += b0; v.tab += b0;
+  return v;
+}
+
+int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want_order, bool first = true, bool last = true) {
   const DevParams dp = ctx->dp;
-  const DevBuffers buf = ctx->buf;
   cudaStream_t st = ctx->stream;
   const int T = (S + kChunk - 1) / kChunk;
   if (T > ctx->Tmax) return URF_ERR_CAPACITY;
@@ -86,7 +102,7 @@ int launch_pipeline(urf_ctx* ctx, int B, int S, bool want_order) {
     __VA_ARGS__;                                                                             \
     L++;                                                                                     \
   } while (0)
-  CK(cudaEventRecord(ctx->ev0, st));
+  if (first) CK(cudaEventRecord(ctx->ev0, st));
   K("k_reset", k_reset<<<dim3(8, B), 256, 0, st>>>(buf, dp));
   K("k_points", k_points<<<gpts, 256, 0, st>>>(buf, dp, S));
   K("k_register", k_register<<<B, 256, 0, st>>>(buf, dp, S));
@@ -115,10 +131,9 @@ int launch_pipeline(urf_ctx* ctx, int B, int S, bool want_order) {
   K("k_verts", k_verts<<<B, 384, 0, st>>>(buf, S));
   if (want_order) K("k_sort_rings", k_sort_rings<<<dim3(dp.channels, B), 256, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S));
 #undef K
-  CK(cudaEventRecord(ctx->ev1, st));
+  if (last) CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaGetLastError());
-  ctx->launches = L;
-  ctx->last_B = B; ctx->last_S = S;
+  ctx->launches = first ? L : ctx->launches + L;
   ctx->timing_valid = true;
   return URF_OK;
 }
@@ -190,6 +205,8 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
 #define TRY(x) do { rc = (x); if (rc != URF_OK) return fail(rc); } while (0)
 #define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = cudaGetErrorString(e_); return fail(URF_ERR_CUDA); } } while (0)
   CKF(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CKF(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  CKF(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
   CKF(cudaEventCreate(&ctx->ev0));
   CKF(cudaEventCreate(&ctx->ev1));
   const size_t P = ctx->P;
@@ -258,6 +275,10 @@ void urf_destroy(urf_ctx* ctx) {
   if (ctx->h_n) cudaFreeHost(ctx->h_n);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_comp) cudaEventDestroy(e);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -323,9 +344,10 @@ int urf_enqueue_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_point
   CK(cudaMemcpyAsync(ctx->buf.n, ctx->h_n, sizeof(int) * batch, cudaMemcpyHostToDevice, ctx->stream));
   ctx->buf.in = reinterpret_cast<float4*>(const_cast<float*>(d_xyzi));
   ctx->buf.label = d_label;
-  int rc = launch_pipeline(ctx, batch, stride_points, false);
+  int rc = launch_pipeline(ctx, ctx->buf, batch, stride_points, false);
   ctx->buf.in = ctx->own_in;
   ctx->buf.label = ctx->own_label;
+  ctx->last_B = batch; ctx->last_S = stride_points;
   return rc;
 }
 
@@ -367,22 +389,43 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
     ctx->h_n[b] = n[b];
   }
   const int S = ((nmax + 255) / 256) * 256;
+  const int T = (S + kChunk - 1) / kChunk;
   cudaStream_t st = ctx->stream;
-  CK(cudaMemcpyAsync(ctx->buf.n, ctx->h_n, sizeof(int) * batch, cudaMemcpyHostToDevice, st));
-  for (int b = 0; b < batch; b++)
-    if (n[b] > 0) CK(cudaMemcpyAsync(ctx->own_in + (size_t)b * S, xyzi[b], sizeof(float) * 4 * (size_t)n[b], cudaMemcpyHostToDevice, st));
-  int rc = launch_pipeline(ctx, batch, S, want_order);
-  if (rc != URF_OK) return rc;
-  int* ring32 = reinterpret_cast<int*>(ctx->buf.sortbuf);
-  if (want_ring) k_ring32<<<dim3((S + 255) / 256, batch), 256, 0, st>>>(ctx->buf, ring32, S);
-  CK(cudaMemcpyAsync(ctx->h_out, ctx->buf.out, sizeof(ScanOut) * batch, cudaMemcpyDeviceToHost, st));
-  for (int b = 0; b < batch; b++) {
-    if (n[b] <= 0) continue;
-    if (outs[b].label) CK(cudaMemcpyAsync(outs[b].label, ctx->own_label + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, st));
-    if (outs[b].ring) CK(cudaMemcpyAsync(outs[b].ring, ring32 + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, st));
-    if (outs[b].order) CK(cudaMemcpyAsync(outs[b].order, ctx->buf.order + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, st));
+  // Software pipeline over chunks of scans: H2D of chunk c+1 (s_in), kernels of chunk c (stream) and D2H of chunk c-1
+  // (s_out) overlap; scans are independent, every chunk owns its slice of every buffer.
+  const int chunk = batch >= 16 ? (batch + 7) / 8 : batch;
+  const int nchunks = (batch + chunk - 1) / chunk;
+  while ((int)ctx->ev_in.size() < nchunks) {
+    cudaEvent_t a, c;
+    CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+    ctx->ev_in.push_back(a); ctx->ev_comp.push_back(c);
   }
+  int* ring32 = reinterpret_cast<int*>(ctx->buf.sortbuf);     // free once the sorts of a chunk are done (chunk-private slice)
+  for (int c = 0; c < nchunks; c++) {
+    const int b0 = c * chunk, nb = std::min(chunk, batch - b0);
+    CK(cudaMemcpyAsync(ctx->buf.n + b0, ctx->h_n + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->s_in));
+    for (int b = b0; b < b0 + nb; b++)
+      if (n[b] > 0) CK(cudaMemcpyAsync(ctx->own_in + (size_t)b * S, xyzi[b], sizeof(float) * 4 * (size_t)n[b], cudaMemcpyHostToDevice, ctx->s_in));
+    CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    CK(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
+    const DevBuffers view = offset_view(ctx->buf, b0, S, T, ctx->dp.channels);
+    int rc = launch_pipeline(ctx, view, nb, S, want_order, c == 0, c == nchunks - 1);
+    if (rc != URF_OK) return rc;
+    if (want_ring) k_ring32<<<dim3((S + 255) / 256, nb), 256, 0, st>>>(view, ring32 + (size_t)b0 * S * 4, S);
+    CK(cudaEventRecord(ctx->ev_comp[c], st));
+    CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[c], 0));
+    CK(cudaMemcpyAsync(ctx->h_out + b0, ctx->buf.out + b0, sizeof(ScanOut) * nb, cudaMemcpyDeviceToHost, ctx->s_out));
+    for (int b = b0; b < b0 + nb; b++) {
+      if (n[b] <= 0) continue;
+      if (outs[b].label) CK(cudaMemcpyAsync(outs[b].label, ctx->own_label + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, ctx->s_out));
+      if (outs[b].ring) CK(cudaMemcpyAsync(outs[b].ring, ring32 + (size_t)b0 * S * 4 + (size_t)(b - b0) * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, ctx->s_out));
+      if (outs[b].order) CK(cudaMemcpyAsync(outs[b].order, ctx->buf.order + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->s_out));
   CK(cudaStreamSynchronize(st));
+  ctx->last_B = batch; ctx->last_S = S;
   for (int b = 0; b < batch; b++) {
     fill_result(ctx->h_out[b], &outs[b]);
     if (outs[b].status == URF_TOO_FEW_POINTS && outs[b].ring) for (int i = 0; i < n[b]; i++) outs[b].ring[i] = -1;

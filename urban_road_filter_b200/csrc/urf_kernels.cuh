@@ -568,17 +568,18 @@ __device__ bool radix_sort_sector(const float4* __restrict__ src, float4* __rest
 }
 
 // Warp sort for sectors of up to 32 * EPL points: bitonic network held in registers (blocked layout: lane l owns elements
-// l*EPL .. l*EPL+EPL-1), 64-bit keys (radius bits, input index) with the point's z as payload. Strides below EPL are
-// register-only compare-exchanges, larger strides go through shuffles; no shared memory, no dependent memory chain.
+// l*EPL .. l*EPL+EPL-1), 32-bit keys (radius bits) with the element's slot in the unsorted sector as payload. Strides
+// below EPL are register-only compare-exchanges, larger strides go through shuffles; no shared memory, no dependent
+// memory chain. Returns true when two points share a radius: their order must follow the input index, which this
+// network does not see — the sector is then redone by the 64-bit fallback sort.
 template <int EPL>
-__device__ __forceinline__ void warp_bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int lane, int* tie_out) {
-  unsigned long long key[EPL];
-  float pay[EPL];
+__device__ __forceinline__ bool warp_bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int lane) {
+  unsigned key[EPL], el[EPL];
 #pragma unroll
   for (int r = 0; r < EPL; r++) {
     const int e = lane * EPL + r;
-    key[r] = ~0ull; pay[r] = 0.f;
-    if (e < n) { const float4 p = src[e]; key[r] = ((unsigned long long)fbits(p.x) << 32) | (unsigned)__float_as_int(p.z); pay[r] = p.y; }
+    key[r] = 0xffffffffu; el[r] = 0u;
+    if (e < n) { key[r] = fbits(src[e].x); el[r] = (unsigned)e; }
   }
   constexpr int N = 32 * EPL;
 #pragma unroll
@@ -591,22 +592,20 @@ __device__ __forceinline__ void warp_bitonic_sector(const float4* __restrict__ s
           if ((r & j) == 0) {
             const bool asc = k < EPL ? ((r & k) == 0) : ((lane & (k / EPL)) == 0 || k == N);
             const bool sw = (key[r] > key[r | j]) == asc;
-            const unsigned long long ka = sw ? key[r | j] : key[r], kb = sw ? key[r] : key[r | j];
-            const float pa = sw ? pay[r | j] : pay[r], pb = sw ? pay[r] : pay[r | j];
-            key[r] = ka; key[r | j] = kb; pay[r] = pa; pay[r | j] = pb;
+            const unsigned ka = sw ? key[r | j] : key[r], kb = sw ? key[r] : key[r | j];
+            const unsigned ea = sw ? el[r | j] : el[r], eb = sw ? el[r] : el[r | j];
+            key[r] = ka; key[r | j] = kb; el[r] = ea; el[r | j] = eb;
           }
         }
       } else {
         const int lj = j / EPL;
-        const bool lower = (lane & lj) == 0;
-        const bool asc = (lane & (k / EPL)) == 0 || k == N;
-        const bool keep_min = lower == asc;
+        const bool keep_min = ((lane & lj) == 0) == ((lane & (k / EPL)) == 0 || k == N);
 #pragma unroll
         for (int r = 0; r < EPL; r++) {
-          const unsigned long long o = __shfl_xor_sync(0xffffffffu, key[r], lj);
-          const float op = __shfl_xor_sync(0xffffffffu, pay[r], lj);
+          const unsigned o = __shfl_xor_sync(0xffffffffu, key[r], lj);
+          const unsigned oe = __shfl_xor_sync(0xffffffffu, el[r], lj);
           const bool take = keep_min ? (o < key[r]) : (o > key[r]);
-          if (take) { key[r] = o; pay[r] = op; }
+          if (take) { key[r] = o; el[r] = oe; }
         }
       }
     }
@@ -615,13 +614,13 @@ __device__ __forceinline__ void warp_bitonic_sector(const float4* __restrict__ s
 #pragma unroll
   for (int r = 0; r < EPL; r++) {
     const int e = lane * EPL + r;
-    unsigned long long prev = r > 0 ? key[r - 1] : __shfl_up_sync(0xffffffffu, key[EPL - 1], 1);
+    const unsigned prev = r > 0 ? key[r - 1] : __shfl_up_sync(0xffffffffu, key[EPL - 1], 1);
     if (e < n) {
-      dst[e] = make_float4(bitsf((unsigned)(key[r] >> 32)), pay[r], __int_as_float((int)(unsigned)key[r]), 0.f);
-      if (e > 0 && (unsigned)(prev >> 32) == (unsigned)(key[r] >> 32)) tie = true;
+      dst[e] = src[el[r]];
+      if (e > 0 && prev == key[r]) tie = true;
     }
   }
-  if (tie) *tie_out = 1;
+  return tie;
 }
 
 __global__ void __launch_bounds__(kStarWarps * 32) k_star_sort_warp(DevBuffers buf, int S) {
@@ -641,11 +640,11 @@ __global__ void __launch_bounds__(kStarWarps * 32) k_star_sort_warp(DevBuffers b
     }
     return;
   }
-  int tie = 0;
-  if (n <= 128) warp_bitonic_sector<4>(src, dst, n, lane, &tie);
-  else if (n <= 256) warp_bitonic_sector<8>(src, dst, n, lane, &tie);
-  else warp_bitonic_sector<16>(src, dst, n, lane, &tie);
-  if (__any_sync(0xffffffffu, tie) && lane == 0) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+  bool tie;
+  if (n <= 128) tie = warp_bitonic_sector<4>(src, dst, n, lane);
+  else if (n <= 256) tie = warp_bitonic_sector<8>(src, dst, n, lane);
+  else tie = warp_bitonic_sector<16>(src, dst, n, lane);
+  if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;   // sets F_TIE_SECTOR there
 }
 
 constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap + 2 * sizeof(unsigned short) * kCtaCap + sizeof(unsigned short) * 8 * kRadix + 64;
