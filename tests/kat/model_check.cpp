@@ -194,7 +194,7 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
       const int idx = URF_F2I(ring[t].w);
       int lab = prm.star ? mark[idx] : 0;
       if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, m, t, newY.data())) lab = 2;
-      if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, m, t)) lab = 2;
+      if (prm.z_zero && lab != 2 && (prm.curbPoints == 5 ? zzero_mark_t<5>(prm, ring, m, t) : zzero_mark_t<0>(prm, ring, m, t))) lab = 2;
       blabel[base + t] = (unsigned char)lab;
       if (lab == 2 && a >= 0.0f) {
         const size_t o = (size_t)k * kDegBins + deg_bin(a);

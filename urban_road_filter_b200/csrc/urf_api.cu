@@ -116,7 +116,7 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
   if (dp.star) {
     const int gbig = std::max(4, std::min(kSectKeys, 2048 / B)), gslow = std::max(2, std::min(kSectKeys, 512 / B));
-    K("k_star_sort_warp", k_star_sort_warp<<<dim3((kSectKeys + kStarWarps - 1) / kStarWarps, B), kStarWarps * 32, 0, st>>>(buf, S));
+    K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, S));
     K("k_star_radix_cta", k_star_radix_cta<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
     K("k_star_sort", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S));
     K("k_star_scan", k_star_scan<<<dim3((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B), kScanWarps * 32, 0, st>>>(buf, dp, S));

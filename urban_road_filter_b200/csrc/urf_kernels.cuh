@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, i
   const int b = blockIdx.y;
   const int n = buf.n[b];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int keep = 0;
+  int keep = 0, sec = -1;
   if (i < n) {
     const size_t g = (size_t)b * S + i;
     const float4 p = __ldg(&buf.in[g]);
@@ -83,12 +83,17 @@ __global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, i
       unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1) + elev_bin(a);
       if (*fi > (unsigned)i) atomicMin(fi, (unsigned)i);      // plain (possibly stale) read: a stale value is only larger
       if (a == 0.0f) atomicOr(&buf.out[b].flags, F_ZERO_ALPHA);
+      if (prm.star) sec = star_sector(prm, p.x, p.y, c_beam_d, c_beam_o, c_beam_yx);   // star_shaped_search.cpp:164-173
     }
     buf.alpha_v[g] = a;
     buf.mark[g] = 0;
+    buf.sect[g] = (short)sec;
   }
   const unsigned bal = __ballot_sync(0xffffffffu, keep);
   if (lane_id() == 0 && bal) atomicAdd(&buf.out[b].n_roi, __popc(bal));
+  // per-sector point counts of the (unordered) sector partition: one atomic per group of equal sectors in the warp
+  const unsigned peers = __match_any_sync(0xffffffffu, sec);
+  if (sec >= 0 && lane_id() == __ffs(peers) - 1) atomicAdd(&buf.tab[b].sect_cnt[sec], __popc(peers));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -239,7 +244,6 @@ __global__ void __launch_bounds__(256) k_register_exact(DevBuffers buf, DevParam
   __shared__ unsigned long long s_keys[kRingKeys];
   __shared__ int s_red[8];
   __shared__ int s_m;
-  for (int t = threadIdx.x; t < kSectKeys; t += blockDim.x) buf.tab[b].sect_cnt[t] = 0;   // the redo pass counts again
   int m;
   register_exact_cta(buf.alpha_v + (size_t)b * S, buf.n[b], prm.interval, prm.channels, s_vis, s_reg, s_idx, s_red, &m);
   if (threadIdx.x == 0) s_m = m;
@@ -249,9 +253,8 @@ __global__ void __launch_bounds__(256) k_register_exact(DevBuffers buf, DevParam
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_assign: per input point — ring index (lidar_segmentation.cpp:226-233: first sorted angle within `interval`),
-// star-shaped sector (star_shaped_search.cpp:164-173 + rectangular beam filter :73-107), default label, the per-warp-
-// chunk ring histogram of the stable ring partition and the per-sector counts of the (unordered) sector partition.
+// k_assign: per input point — ring index (lidar_segmentation.cpp:226-233: first sorted angle within `interval`), default
+// label and the per-warp-chunk ring histogram of the stable ring partition.
 // redo=1 re-runs only for scans whose registration was repaired.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, DevParams prm, int S, int T, int redo) {
   const int b = blockIdx.y;
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, 
   bool violation = false;
   for (int it = 0; it < kChunk / 32; it++) {
     const int i = chunk * kChunk + it * 32 + lane;
-    int ring = -1, sec = -1;
+    int ring = -1;
     if (i < n) {
       const size_t g = (size_t)b * S + i;
       const float a = buf.alpha_v[g];
@@ -287,19 +290,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, 
         ring = assign_ring_from(s_angle, R, a, prm.interval, lut[elev_bin(a)], &lo);
         if (verify && registration_violation(s_angle, s_regidx, tab.regorder, R, prm.channels, prm.interval, a, i, lo))
           violation = true;
-        if (prm.star) {
-          const float4 p = __ldg(&buf.in[g]);
-          sec = star_sector(prm, p.x, p.y, c_beam_d, c_beam_o, c_beam_yx);
-        }
       }
       buf.ringid[g] = (short)ring;
-      buf.sect[g] = (short)sec;
       buf.label[g] = kept ? URF_LABEL_NONE : URF_LABEL_OUTSIDE;
     }
-    unsigned peers = __match_any_sync(0xffffffffu, ring);
+    const unsigned peers = __match_any_sync(0xffffffffu, ring);
     if (ring >= 0 && lane == __ffs(peers) - 1) cnt[ring] += __popc(peers);
-    peers = __match_any_sync(0xffffffffu, sec);
-    if (sec >= 0 && lane == __ffs(peers) - 1) atomicAdd(&tab.sect_cnt[sec], __popc(peers));
     __syncwarp();
   }
   if (__any_sync(0xffffffffu, violation) && lane == 0) atomicOr(&out.flags, F_SPEC_VIOLATION);
@@ -604,8 +600,9 @@ __device__ __forceinline__ bool warp_bitonic_sector(const float4* __restrict__ s
         for (int r = 0; r < EPL; r++) {
           const unsigned o = __shfl_xor_sync(0xffffffffu, key[r], lj);
           const unsigned oe = __shfl_xor_sync(0xffffffffu, el[r], lj);
-          const bool take = keep_min ? (o < key[r]) : (o > key[r]);
-          if (take) { key[r] = o; el[r] = oe; }
+          const bool take = (o < key[r]) == keep_min;          // branch-free; taking an equal key is harmless
+          key[r] = take ? o : key[r];
+          el[r] = take ? oe : el[r];
         }
       }
     }
@@ -623,10 +620,10 @@ __device__ __forceinline__ bool warp_bitonic_sector(const float4* __restrict__ s
   return tie;
 }
 
-__global__ void __launch_bounds__(kStarWarps * 32) k_star_sort_warp(DevBuffers buf, int S) {
-  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = lane_id();
-  const int s = blockIdx.x * kStarWarps + warp;
-  if (s >= kSectKeys) return;
+// One 32-thread CTA per sector: sector index and size derive from blockIdx, so the compiler knows the control flow
+// around the shuffles is warp-uniform (no convergence barriers around every SHFL).
+__global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, int S) {
+  const int b = blockIdx.y, s = blockIdx.x, lane = threadIdx.x;
   ScanTab& tab = buf.tab[b];
   const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
   if (n <= 0) return;
@@ -818,7 +815,7 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
     if (tiled) {
       const float4* ring = s_tile + (base - (p0 - kHalo));
       if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;   // x_zero_method.cpp:66
-      if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, n, m)) lab = 2;             // z_zero_method.cpp:71
+      if (prm.z_zero && lab != 2 && (prm.curbPoints == 5 ? zzero_mark_t<5>(prm, ring, n, m) : zzero_mark_t<0>(prm, ring, n, m))) lab = 2;   // z_zero_method.cpp:71
     } else {
       const float4* ring = bucket + base;
       if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;

@@ -150,9 +150,11 @@ URF_HD bool xzero_mark(const DevParams& prm, const float4* ring, int n, int m, c
   return al <= prm.angleFilter1;                                                                              // :61
 }
 
-// z-zero test centred on local index m (z_zero_method.cpp:21-72)
-URF_HD bool zzero_mark(const DevParams& prm, const float4* ring, int n, int m) {
-  const int cp = prm.curbPoints;
+// z-zero test centred on local index m (z_zero_method.cpp:21-72). CP > 0: curb_points known at compile time (loops
+// unroll); CP == 0: taken from the parameters. Same arithmetic either way.
+template <int CP>
+URF_HD bool zzero_mark_t(const DevParams& prm, const float4* ring, int n, int m) {
+  const int cp = CP > 0 ? CP : prm.curbPoints;
   if (!(m >= cp && m <= (n - 1) - cp)) return false;
   const float4 me = ring[m];
   const float az0 = fabsf(me.z);
@@ -176,6 +178,8 @@ URF_HD bool zzero_mark(const DevParams& prm, const float4* ring, int n, int m) {
   const float al = URF_D2F(deg_d(urfm::acosf_glibc(bk)));                                                     // :63
   return al <= prm.angleFilter2;                                                                              // :66
 }
+
+URF_HD bool zzero_mark(const DevParams& prm, const float4* ring, int n, int m) { return zzero_mark_t<0>(prm, ring, n, m); }
 
 // Edge search along one radius-sorted sector (star_shaped_search.cpp:112-150) as a step function: state after point
 // i-1, fed point i (planar radius r, height z); returns true when point i gets marked (the scan then stops).
