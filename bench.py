@@ -33,6 +33,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from urban_road_filter_b200 import FULL_ROI, UrfResult, make_params  # noqa: E402
+from urban_road_filter_b200.shard import allreduce_max, allreduce_sum, seeds_for_rank  # noqa: E402
 from urban_road_filter_b200.synth import SHAPES, make_scan  # noqa: E402
 
 ALGO_BYTES_PER_POINT = 20          # 16 B float4 read + 4 B int32 label written, per input point
@@ -85,7 +86,7 @@ def usable_cores() -> int:
         cores = min(cores, max(1, int(psutil.virtual_memory().available / (1.5 * 2**30))))   # ~0.5 GB per reference process
     except Exception:
         pass
-    return max(1, min(cores, 64))
+    return max(1, cores)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -226,7 +227,7 @@ def main():
     sh = SHAPES[args.shape]
     B, n = args.batch, sh.rings * sh.cols
     prm = bench_params(args.shape)
-    clouds = [make_scan(args.shape, 1000 * rank + b) for b in range(B)]
+    clouds = [make_scan(args.shape, seed) for seed in seeds_for_rank(B, rank)]
     det = api.Detector(max_points=n, max_batch=B, device=local, params=prm)
     lib, ctx = det.lib, det._ctx
     S = n
@@ -297,10 +298,8 @@ def main():
     assert sum(r.n_road for r in res) == n_road, "device-resident and host-buffer paths disagree"
 
     # max over ranks
-    tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(tt[0]), float(tt[1])
+    dev_ms, e2e_ms = allreduce_max([dev_ms, e2e_s * 1e3], device="cuda")
+    total_road = allreduce_sum([n_road], device="cuda")[0]
 
     if rank == 0:
         K = args.steps
@@ -324,7 +323,7 @@ def main():
                        "parallelism": f"scan-batch sharding x{world}, no data-path collective"},
             "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": B * n * 16,
                     "d2h_bytes_per_step": B * n * 4 + B * C.sizeof(UrfResult), "mpoints_per_sec": e2e * n / 1e6},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "road_points_labelled": total_road,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": dom_ms,

@@ -19,4 +19,5 @@ def _build_everything():
     build.build_lib()
     build.build_oracle()
     build.build_kat()
+    build.build_glue()
     yield

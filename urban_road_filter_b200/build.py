@@ -75,6 +75,20 @@ def build_kat() -> None:
                         "-o", tgt, os.path.join(kat, "model_check.cpp")], check=True)
 
 
+def build_glue() -> str:
+    """ros/urf_node.cpp (the ROS glue) compiled against the shim ROS/PCL headers of oracle/shim + a C test entry."""
+    bdir = os.path.join(ROOT, "build")
+    os.makedirs(bdir, exist_ok=True)
+    tgt = os.path.join(bdir, "libglue.so")
+    deps = [os.path.join(ROOT, "ros", "urf_node.cpp"), os.path.join(ROOT, "tests", "kat", "glue_entry.cpp"),
+            os.path.join(ROOT, "include", "urf.h"), LIB]
+    if _stale(tgt, deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "oracle", "shim"),
+                        "-I" + os.path.join(ROOT, "include"), "-o", tgt, os.path.join(ROOT, "tests", "kat", "glue_entry.cpp"),
+                        "-L" + PKG, "-l:liburf_b200.so", "-Wl,-rpath,$ORIGIN/../urban_road_filter_b200"], check=True)
+    return tgt
+
+
 if __name__ == "__main__":
     print(build_lib(force=True, verbose=True))
     build_oracle()
