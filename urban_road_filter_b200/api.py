@@ -65,7 +65,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.urf_debug_fetch.argtypes = [vp, ip, ip, vp, C.c_size_t]
     lib.urf_debug_sizeof_tab.restype = C.c_size_t
     lib.urf_profile_count.argtypes = [vp]
-    lib.urf_profile_get.argtypes = [vp, ip, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
+    lib.urf_profile_slots.argtypes = [vp]
+    lib.urf_profile_get.argtypes = [vp, ip, ip, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -203,12 +204,12 @@ class Detector:
     def last_launch_count(self) -> int:
         return int(self.lib.urf_last_launch_count(self._ctx))
 
-    def kernel_times(self) -> list[tuple[str, float]]:
-        """(kernel name, device ms) of the last call; needs set_option(1, 1) before the call."""
+    def kernel_times(self, slot: int = 0) -> list[tuple[str, float]]:
+        """(kernel name, device ms) of the call recorded in event slot `slot`; needs set_option(1, nslots) beforehand."""
         out = []
         for i in range(self.lib.urf_profile_count(self._ctx)):
             name, ms = C.c_char_p(), C.c_float()
-            self._check(self.lib.urf_profile_get(self._ctx, i, C.byref(name), C.byref(ms)), "urf_profile_get")
+            self._check(self.lib.urf_profile_get(self._ctx, slot, i, C.byref(name), C.byref(ms)), "urf_profile_get")
             out.append((name.value.decode(), float(ms.value)))
         return out
 

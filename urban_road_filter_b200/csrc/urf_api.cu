@@ -21,6 +21,10 @@ struct urf_ctx {
   int Tmax = 0;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams of the pipelined host-buffer path
+  static constexpr int kGroups = 4;               // sub-batches of a device-resident call run on separate streams: scans are
+  cudaStream_t s_grp[kGroups] = {};               // independent, so their (short, partly latency-bound) kernels overlap
+  cudaEvent_t ev_fork = nullptr, ev_join[kGroups] = {};
+  int groups = kGroups;
   std::vector<cudaEvent_t> ev_in, ev_comp;        // per chunk: input landed / results ready
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuffers buf{};
@@ -38,8 +42,10 @@ struct urf_ctx {
   std::vector<void*> allocs;
   // optional per-kernel CUDA-event timing (urf_set_option(ctx, 1, 1)); events live on the ctx stream
   bool profile = false;
-  std::vector<cudaEvent_t> kev;
+  int kslots = 1, kslot = 0;           // event slots: consecutive calls cycle through them so K steps can be timed without syncing
+  std::vector<cudaEvent_t> kev;        // [kslots][kMaxKernels + 1]; the last event of a slot closes the pipeline
   std::vector<const char*> knames;
+  std::vector<int> kcounts;            // kernels recorded per slot
   int kcount = 0;
 };
 
@@ -82,9 +88,12 @@ DevBuffers offset_view(const DevBuffers& a, int b0, int S, int T, int channels) 
   return v;
 }
 
-int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want_order, bool first = true, bool last = true) {
+constexpr int kMaxKernels = 32;
+
+int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want_order, bool first = true, bool last = true,
+                    cudaStream_t st_override = nullptr) {
   const DevParams dp = ctx->dp;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = st_override ? st_override : ctx->stream;
   const int T = (S + kChunk - 1) / kChunk;
   if (T > ctx->Tmax) return URF_ERR_CAPACITY;
   int L = 0;
@@ -93,10 +102,9 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   // K(name, launch): one kernel launch; with profiling on, an event is recorded in front of it
 #define K(name, ...)                                                                         \
   do {                                                                                       \
-    if (ctx->profile) {                                                                      \
-      if ((int)ctx->kev.size() <= ctx->kcount) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->kev.push_back(e); ctx->knames.push_back(name); } \
+    if (ctx->profile && ctx->kcount < kMaxKernels) {                                         \
       ctx->knames[ctx->kcount] = name;                                                       \
-      CK(cudaEventRecord(ctx->kev[ctx->kcount], st));                                        \
+      CK(cudaEventRecord(ctx->kev[(size_t)ctx->kslot * (kMaxKernels + 1) + ctx->kcount], st)); \
       ctx->kcount++;                                                                         \
     }                                                                                        \
     __VA_ARGS__;                                                                             \
@@ -122,18 +130,24 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
     K("k_star_scan", k_star_scan<<<dim3((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B), kScanWarps * 32, 0, st>>>(buf, dp, S));
   }
   K("k_ring_detect", k_ring_detect<<<gpts, 256, 0, st>>>(buf, dp, S));
-  K("k_tab1", k_tab1<<<B, 256, 0, st>>>(buf, dp));
+  K("k_tab1", k_tab1<<<dim3((dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
   K("k_reach", k_reach<<<dim3((2 * kDegBins * dp.channels + 255) / 256, B), 256, 0, st>>>(buf, dp));
   K("k_tab2", k_tab2<<<dim3((2 * dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
   K("k_label", k_label<<<gpts, 256, 0, st>>>(buf, dp, S));
-  K("k_dmax", k_dmax<<<gpts, 256, 0, st>>>(buf, S));
-  K("k_best", k_best<<<gpts, 256, 0, st>>>(buf, S));
+  const dim3 groad(std::max(1, std::min((S + 255) / 256, 96)), B);        // grid-stride over the compact road list
+  K("k_dmax", k_dmax<<<groad, 256, 0, st>>>(buf, S));
+  K("k_best", k_best<<<groad, 256, 0, st>>>(buf, S));
   K("k_verts", k_verts<<<B, 384, 0, st>>>(buf, S));
   if (want_order) K("k_sort_rings", k_sort_rings<<<dim3(dp.channels, B), 256, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S));
 #undef K
   if (last) CK(cudaEventRecord(ctx->ev1, st));
+  if (ctx->profile) {
+    CK(cudaEventRecord(ctx->kev[(size_t)ctx->kslot * (kMaxKernels + 1) + kMaxKernels], st));
+    ctx->kcounts[ctx->kslot] = ctx->kcount;
+    ctx->kslot = (ctx->kslot + 1) % ctx->kslots;
+  }
   CK(cudaGetLastError());
-  ctx->launches = first ? L : ctx->launches + L;
+  ctx->launches = (first || st_override) ? L : ctx->launches + L;
   ctx->timing_valid = true;
   return URF_OK;
 }
@@ -207,6 +221,11 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   CKF(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CKF(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
   CKF(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  for (int g = 0; g < urf_ctx::kGroups; g++) {
+    CKF(cudaStreamCreateWithFlags(&ctx->s_grp[g], cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&ctx->ev_join[g], cudaEventDisableTiming));
+  }
+  CKF(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CKF(cudaEventCreate(&ctx->ev0));
   CKF(cudaEventCreate(&ctx->ev1));
   const size_t P = ctx->P;
@@ -277,6 +296,8 @@ void urf_destroy(urf_ctx* ctx) {
   for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_comp) cudaEventDestroy(e);
+  for (int g = 0; g < urf_ctx::kGroups; g++) { if (ctx->s_grp[g]) cudaStreamDestroy(ctx->s_grp[g]); if (ctx->ev_join[g]) cudaEventDestroy(ctx->ev_join[g]); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -300,11 +321,26 @@ int urf_get_params(const urf_ctx* ctx, urf_params* p) {
   return URF_OK;
 }
 
-// test/diagnostic options: 0 = force exact ring registration (0/1); 1 = per-kernel CUDA-event timing (0/1)
+// test/diagnostic options: 0 = force exact ring registration (0/1); 1 = per-kernel CUDA-event timing (slots, 0 = off);
+// 2 = number of compute streams a device-resident batch is spread over (1..4)
 int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (!ctx) return URF_ERR_INVALID;
   if (option == 0) { ctx->dp.force_exact = value != 0; return URF_OK; }
-  if (option == 1) { ctx->profile = value != 0; return URF_OK; }
+  if (option == 2) { ctx->groups = value < 1 ? 1 : (value > urf_ctx::kGroups ? urf_ctx::kGroups : value); return URF_OK; }
+  if (option == 1) {                   // value = number of event slots (0 = off)
+    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+    ctx->kev.clear();
+    ctx->profile = value > 0;
+    ctx->kslots = value > 0 ? value : 1;
+    ctx->kslot = 0;
+    if (ctx->profile) {
+      ctx->kev.resize((size_t)ctx->kslots * (kMaxKernels + 1));
+      for (cudaEvent_t& e : ctx->kev) CK(cudaEventCreate(&e));
+      ctx->knames.assign(kMaxKernels, "");
+      ctx->kcounts.assign(ctx->kslots, 0);
+    }
+    return URF_OK;
+  }
   return URF_ERR_INVALID;
 }
 
@@ -323,12 +359,15 @@ int urf_last_launch_count(const urf_ctx* ctx) { return ctx ? ctx->launches : 0; 
 
 // With option 1 on: number of kernels of the last call, and name / device milliseconds of kernel `idx` (event before it to
 // the event before the next kernel, or to the end-of-pipeline event for the last one). Waits for the stream.
-int urf_profile_count(const urf_ctx* ctx) { return ctx && ctx->profile ? ctx->kcount : 0; }
-int urf_profile_get(urf_ctx* ctx, int idx, const char** name, float* ms) {
-  if (!ctx || !ctx->profile || idx < 0 || idx >= ctx->kcount) return URF_ERR_INVALID;
-  CK(cudaEventSynchronize(ctx->ev1));
-  cudaEvent_t next = idx + 1 < ctx->kcount ? ctx->kev[idx + 1] : ctx->ev1;
-  CK(cudaEventElapsedTime(ms, ctx->kev[idx], next));
+int urf_profile_count(const urf_ctx* ctx) { return ctx && ctx->profile ? ctx->kcounts[0] : 0; }
+int urf_profile_slots(const urf_ctx* ctx) { return ctx && ctx->profile ? ctx->kslots : 0; }
+// name / device milliseconds of kernel `idx` in event slot `slot` (the slot's calls must have completed)
+int urf_profile_get(urf_ctx* ctx, int slot, int idx, const char** name, float* ms) {
+  if (!ctx || !ctx->profile || slot < 0 || slot >= ctx->kslots || idx < 0 || idx >= ctx->kcounts[slot]) return URF_ERR_INVALID;
+  const size_t o = (size_t)slot * (kMaxKernels + 1);
+  cudaEvent_t next = idx + 1 < ctx->kcounts[slot] ? ctx->kev[o + idx + 1] : ctx->kev[o + kMaxKernels];
+  CK(cudaEventSynchronize(next));
+  CK(cudaEventElapsedTime(ms, ctx->kev[o + idx], next));
   if (name) *name = ctx->knames[idx];
   return URF_OK;
 }
@@ -344,7 +383,27 @@ int urf_enqueue_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_point
   CK(cudaMemcpyAsync(ctx->buf.n, ctx->h_n, sizeof(int) * batch, cudaMemcpyHostToDevice, ctx->stream));
   ctx->buf.in = reinterpret_cast<float4*>(const_cast<float*>(d_xyzi));
   ctx->buf.label = d_label;
-  int rc = launch_pipeline(ctx, ctx->buf, batch, stride_points, false);
+  int rc = URF_OK;
+  const int G = (ctx->profile || batch < 2 * ctx->groups) ? 1 : ctx->groups;     // per-kernel event timing needs one stream
+  if (G == 1) rc = launch_pipeline(ctx, ctx->buf, batch, stride_points, false);
+  else {
+    // fork: the ctx stream hands sub-batches to the group streams and joins them again, so callers still see ONE stream
+    const int T = (stride_points + kChunk - 1) / kChunk;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    int launches = 0;
+    for (int g = 0; g < G && rc == URF_OK; g++) {
+      const int b0 = (int)((long long)batch * g / G), b1 = (int)((long long)batch * (g + 1) / G);
+      CK(cudaStreamWaitEvent(ctx->s_grp[g], ctx->ev_fork, 0));
+      rc = launch_pipeline(ctx, offset_view(ctx->buf, b0, stride_points, T, ctx->dp.channels), b1 - b0, stride_points, false, false, false,
+                           ctx->s_grp[g]);
+      launches += ctx->launches;
+      CK(cudaEventRecord(ctx->ev_join[g], ctx->s_grp[g]));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches = launches;
+  }
   ctx->buf.in = ctx->own_in;
   ctx->buf.label = ctx->own_label;
   ctx->last_B = batch; ctx->last_S = stride_points;

@@ -842,17 +842,17 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
 // blindSpots as tables (urf_logic.cuh: CurbView, window_blocked, build_T_column, covered_T).
 // k_tab1: per scan — prefix counts of non-empty curb bins per ring, arc widths, q1..q4, reach := n_rings.
 __global__ void __launch_bounds__(256) k_tab1(DevBuffers buf, DevParams prm) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
   const int R = out.n_rings;
   const int warp = threadIdx.x >> 5, lane = lane_id();
-  for (int t = threadIdx.x; t < 2 * kDegBins; t += blockDim.x) tab.reach[t / kDegBins][t % kDegBins] = R;
+  if (blockIdx.x == 0) for (int t = threadIdx.x; t < 2 * kDegBins; t += blockDim.x) tab.reach[t / kDegBins][t % kDegBins] = R;
   if (R <= 0) return;
   const size_t nb = (size_t)prm.channels * kDegBins;
   const unsigned* cmin = buf.cmin + (size_t)b * nb;
   unsigned short* ne = buf.ne + (size_t)b * prm.channels * (kDegBins + 1);
-  for (int k = warp; k < R; k += blockDim.x >> 5) {        // one warp per ring: 12 x 32 bins with a running carry
+  for (int k = blockIdx.x * 8 + warp; k < R; k += gridDim.x * 8) {        // one warp per ring: 12 x 32 bins with a running carry
     unsigned carry = 0;
     for (int c = 0; c < (kDegBins + 31) / 32; c++) {
       const int bin = c * 32 + lane;
@@ -863,6 +863,7 @@ __global__ void __launch_bounds__(256) k_tab1(DevBuffers buf, DevParams prm) {
     }
     if (lane == 0) ne[(size_t)k * (kDegBins + 1) + kDegBins] = (unsigned short)carry;
   }
+  if (blockIdx.x != 0) return;
   const float arc = arc_distance(prm, bitsf(tab.maxdist[0]));            // blind_spots.cpp:65
   for (int k = threadIdx.x; k < R; k += blockDim.x) tab.A[k] = ring_width(arc, bitsf(tab.maxdist[k]));   // :142
   if (threadIdx.x < 4) {
@@ -973,24 +974,26 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
 __global__ void __launch_bounds__(256) k_dmax(DevBuffers buf, int S) {
   const int b = blockIdx.y;
   ScanTab& tab = buf.tab[b];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= buf.out[b].n_road) return;
-  const uint4 e = buf.roadlist[(size_t)b * S + t];
-  if (e.x == 0xffffffffu) return;
-  const int bin = e.x & 0xffff, k = e.x >> 16;
-  if (marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w) && tab.dmax[bin] < e.z) atomicMax(&tab.dmax[bin], e.z);
+  const int nroad = buf.out[b].n_road;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nroad; t += gridDim.x * blockDim.x) {
+    const uint4 e = buf.roadlist[(size_t)b * S + t];
+    if (e.x == 0xffffffffu) continue;
+    const int bin = e.x & 0xffff, k = e.x >> 16;
+    if (marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w) && tab.dmax[bin] < e.z) atomicMax(&tab.dmax[bin], e.z);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_best(DevBuffers buf, int S) {
   const int b = blockIdx.y;
   ScanTab& tab = buf.tab[b];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= buf.out[b].n_road) return;
-  const uint4 e = buf.roadlist[(size_t)b * S + t];
-  if (e.x == 0xffffffffu) return;
-  const int bin = e.x & 0xffff, k = e.x >> 16;
-  if (e.z != 0u && e.z == tab.dmax[bin] && marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w))
-    atomicMin(&tab.best[bin], best_key(k, e.y, (int)e.w));
+  const int nroad = buf.out[b].n_road;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nroad; t += gridDim.x * blockDim.x) {
+    const uint4 e = buf.roadlist[(size_t)b * S + t];
+    if (e.x == 0xffffffffu) continue;
+    const int bin = e.x & 0xffff, k = e.x >> 16;
+    if (e.z != 0u && e.z == tab.dmax[bin] && marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w))
+      atomicMin(&tab.best[bin], best_key(k, e.y, (int)e.w));
+  }
 }
 
 // k_verts: compact the per-bin winners in bin order into markerPointsArray (lidar_segmentation.cpp:343-350).
