@@ -25,6 +25,12 @@ struct urf_ctx {
   cudaStream_t s_grp[kGroups] = {};               // independent, so their (short, partly latency-bound) kernels overlap
   cudaEvent_t ev_fork = nullptr, ev_join[kGroups] = {};
   int groups = kGroups;
+  // CUDA graph of the kernel sequence for small host-buffer batches (launch latency dominates there); re-captured when
+  // the shape, the parameters or an option change
+  bool use_graph = true;
+  cudaGraphExec_t gexec = nullptr;
+  int g_B = -1, g_S = -1, g_order = -1, g_launches = 0;
+  unsigned long long g_version = 0, version = 1;
   std::vector<cudaEvent_t> ev_in, ev_comp;        // per chunk: input landed / results ready
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuffers buf{};
@@ -148,6 +154,31 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   }
   CK(cudaGetLastError());
   ctx->launches = (first || st_override) ? L : ctx->launches + L;
+  ctx->timing_valid = true;
+  return URF_OK;
+}
+
+// Small batches: replay the whole kernel sequence as one CUDA graph (buf must be ctx->buf itself: constant pointers).
+int launch_pipeline_graphed(urf_ctx* ctx, int B, int S, bool want_order) {
+  if (!ctx->use_graph || ctx->profile) return launch_pipeline(ctx, ctx->buf, B, S, want_order);
+  cudaStream_t st = ctx->stream;
+  if (!ctx->gexec || ctx->g_B != B || ctx->g_S != S || ctx->g_order != (int)want_order || ctx->g_version != ctx->version) {
+    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    ctx->launches = 0;
+    const int rc = launch_pipeline(ctx, ctx->buf, B, S, want_order, false, false);
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != URF_OK || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); ctx->err = "graph capture failed"; return rc != URF_OK ? rc : URF_ERR_CUDA; }
+    const cudaError_t ei = cudaGraphInstantiate(&ctx->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { ctx->gexec = nullptr; ctx->err = cudaGetErrorString(ei); return URF_ERR_CUDA; }
+    ctx->g_B = B; ctx->g_S = S; ctx->g_order = (int)want_order; ctx->g_version = ctx->version; ctx->g_launches = ctx->launches;
+  }
+  CK(cudaEventRecord(ctx->ev0, st));
+  CK(cudaGraphLaunch(ctx->gexec, st));
+  CK(cudaEventRecord(ctx->ev1, st));
+  ctx->launches = ctx->g_launches;
   ctx->timing_valid = true;
   return URF_OK;
 }
@@ -293,6 +324,7 @@ void urf_destroy(urf_ctx* ctx) {
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->h_n) cudaFreeHost(ctx->h_n);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
   for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_comp) cudaEventDestroy(e);
@@ -312,6 +344,7 @@ int urf_set_params(urf_ctx* ctx, const urf_params* p) {
   if (rc != URF_OK) return rc;
   ctx->params = *p;
   narrow_params(p, &ctx->dp, ctx->dp.Kfi, ctx->dp.force_exact, 0);
+  ctx->version++;
   return URF_OK;
 }
 
@@ -322,13 +355,16 @@ int urf_get_params(const urf_ctx* ctx, urf_params* p) {
 }
 
 // test/diagnostic options: 0 = force exact ring registration (0/1); 1 = per-kernel CUDA-event timing (slots, 0 = off);
-// 2 = number of compute streams a device-resident batch is spread over (1..4)
+// 2 = number of compute streams a device-resident batch is spread over (1..4); 3 = CUDA graph for small batches (0/1)
 int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (!ctx) return URF_ERR_INVALID;
+  ctx->version++;
   if (option == 0) { ctx->dp.force_exact = value != 0; return URF_OK; }
+  if (option == 3) { ctx->use_graph = value != 0; return URF_OK; }
   if (option == 2) { ctx->groups = value < 1 ? 1 : (value > urf_ctx::kGroups ? urf_ctx::kGroups : value); return URF_OK; }
   if (option == 1) {                   // value = number of event slots (0 = off)
-    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+    if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
+  for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
     ctx->kev.clear();
     ctx->profile = value > 0;
     ctx->kslots = value > 0 ? value : 1;
@@ -469,7 +505,8 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
     CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
     CK(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
     const DevBuffers view = offset_view(ctx->buf, b0, S, T, ctx->dp.channels);
-    int rc = launch_pipeline(ctx, view, nb, S, want_order, c == 0, c == nchunks - 1);
+    int rc = (nchunks == 1 && batch <= 8) ? launch_pipeline_graphed(ctx, nb, S, want_order)
+                                          : launch_pipeline(ctx, view, nb, S, want_order, c == 0, c == nchunks - 1);
     if (rc != URF_OK) return rc;
     if (want_ring) k_ring32<<<dim3((S + 255) / 256, nb), 256, 0, st>>>(view, ring32 + (size_t)b0 * S * 4, S);
     CK(cudaEventRecord(ctx->ev_comp[c], st));

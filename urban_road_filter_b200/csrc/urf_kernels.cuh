@@ -784,8 +784,15 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
   const ScanOut& out = buf.out[b];
   const int N = out.n_order;
   __shared__ float4 s_tile[256 + 2 * kHalo];
+  __shared__ int s_rs[kRingKeys + 1];                     // ring_start of the rings this CTA touches, indexed by ring - k_lo
+  __shared__ int s_klo;
   const int p0 = blockIdx.x * blockDim.x;
   if (p0 >= N) return;
+  if (threadIdx.x < 32) {                                 // rings are contiguous in bucket order: first .. last ring of the CTA
+    const int k_lo = buf.bring[(size_t)b * S + p0], k_hi = buf.bring[(size_t)b * S + min(p0 + 255, N - 1)];
+    if (threadIdx.x == 0) s_klo = k_lo;
+    for (int t = threadIdx.x; t <= k_hi - k_lo + 1; t += 32) s_rs[t] = out.ring_start[k_lo + t];
+  }
   const float4* bucket = buf.bpt + (size_t)b * S;
   const bool tiled = prm.curbPoints <= kHalo;
   if (tiled) {
@@ -801,7 +808,7 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
   unsigned dbits = 0;
   if (act) {
     k = buf.bring[(size_t)b * S + p];
-    const int base = out.ring_start[k], n = out.ring_start[k + 1] - base, m = p - base;
+    const int base = s_rs[k - s_klo], n = s_rs[k - s_klo + 1] - base, m = p - base;
     const float4 me = tiled ? s_tile[threadIdx.x + kHalo] : bucket[p];
     const int idx = __float_as_int(me.w);
     float d, az;
@@ -833,7 +840,7 @@ __global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams p
   if (__all_sync(0xffffffffu, k == k0)) {
     if (k0 >= 0) {
       const unsigned mx = __reduce_max_sync(0xffffffffu, dbits);
-      if (lane_id() == 0 && buf.tab[b].maxdist[k0] < mx) atomicMax(&buf.tab[b].maxdist[k0], mx);
+      if (lane_id() == 0) atomicMax(&buf.tab[b].maxdist[k0], mx);      // result unused: a fire-and-forget RED
     }
   } else if (act) atomicMax(&buf.tab[b].maxdist[k], dbits);
 }
@@ -940,16 +947,22 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
     k = buf.bring[g];
     a = buf.az[g];
     lab = buf.blabel[g];
-    const size_t o = (size_t)b * prm.channels * kTStride;
-    if (lab != 2 && covered_T(buf.Tf + o, buf.Tb + o, k, a)) lab = 1;
+    const int idx = buf.bidx[g];
+    // everything the decision needs is loaded up front (independent loads, one round trip): the two threshold entries
+    // and the bin's current first-non-road key
+    const size_t o = ((size_t)b * prm.channels + k) * kTStride;
+    const bool valid = a >= 0.0f;
+    int j = 0, jc = 0;
+    if (valid) T_indices(a, &j, &jc);
+    const float tf = buf.Tf[o + j], tb = buf.Tb[o + jc];
+    bin = j;                                          // == deg_bin(a)
+    const unsigned long long cb = tab.cutbest[bin];
+    if (lab != 2 && valid && covered_from(a, tf, tb)) lab = 1;       // covered_T of urf_logic.cuh with the loads hoisted
     buf.blabel[g] = (unsigned char)lab;
-    buf.label[(size_t)b * S + buf.bidx[g]] = lab;
-    if (a >= 0.0f) {
-      bin = deg_bin(a);
-      if (lab != 1) {                               // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
-        const unsigned long long key = best_key(k, fbits(a), p);
-        if (tab.cutbest[bin] > key) atomicMin(&tab.cutbest[bin], key);
-      }
+    buf.label[(size_t)b * S + idx] = lab;
+    if (valid && lab != 1) {                          // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
+      const unsigned long long key = best_key(k, fbits(a), p);
+      if (cb > key) atomicMin(&tab.cutbest[bin], key);
     }
   }
   const unsigned br = __ballot_sync(0xffffffffu, lab == 1), bc = __ballot_sync(0xffffffffu, lab == 2);

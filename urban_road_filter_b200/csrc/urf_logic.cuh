@@ -372,12 +372,18 @@ URF_HD void build_T_row(const DevParams& prm, const int* reach_f, const int* rea
     Tb[j] = T_bwd_value(prm, k, nxt, A);
   }
 }
+// table columns an azimuth a in [0, 360] looks at: j = floor(a) (also its degree bin), jc = ceil(a)
+URF_HD void T_indices(float a, int* j_out, int* jc_out) {
+  int j = (int)a; if (j > 360) j = 360;
+  int jc = j; if ((float)jc < a) jc++; if (jc > 360) jc = 360;
+  *j_out = j; *jc_out = jc;
+}
+URF_HD bool covered_from(float a, float tf, float tb) { return a <= tf || tb <= a; }
 URF_HD bool covered_T(const float* Tf, const float* Tb, int k, float a) {
   if (!(a >= 0.0f)) return false;
-  int j = (int)a; if (j > 360) j = 360;
-  if (a <= Tf[(size_t)k * kTStride + j]) return true;
-  int jc = j; if ((float)jc < a) jc++;
-  return jc <= 360 && Tb[(size_t)k * kTStride + jc] <= a;
+  int j, jc;
+  T_indices(a, &j, &jc);
+  return covered_from(a, Tf[(size_t)k * kTStride + j], Tb[(size_t)k * kTStride + jc]);
 }
 // first ring with a curb point inside window start i of direction dir, given the per-cell test (k_reach evaluates the
 // cells in parallel and keeps the minimum): true when ring k blocks window i
