@@ -206,3 +206,40 @@ def test_gpu_pipelined_host_batch(port):
                 assert stage_diffs(o, r, c.shape[0]) == []
     finally:
         d.close()
+
+
+def _model():
+    from util import CpuModel
+    return CpuModel()
+
+
+def test_gpu_fallback_paths_big_sector_big_ring_large_cp(det, port):
+    """Rarely taken code paths: a star sector with > 8192 points (global-memory bitonic fallback), a ring with ~60k points
+    (emission-order sort beyond shared memory), curb_points beyond the shared-memory halo of k_ring_detect."""
+    rng = np.random.default_rng(7)
+    n = 60000
+    az = np.deg2rad(rng.uniform(10.02, 10.98, n))                 # one star sector, one elevation -> one ring
+    t = np.sort(rng.uniform(2.0, 50.0, n))[rng.permutation(n)]
+    e = np.deg2rad(-12.0)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = t * np.cos(e) * np.cos(az); pts[:, 1] = t * np.cos(e) * np.sin(az); pts[:, 2] = t * np.sin(e) + rng.normal(0, 0.02, n)
+    from urban_road_filter_b200.synth import _detie_radius
+    _detie_radius(pts, 7)
+    check(det, port, pts, make_params(interval=3.0, **FULL_ROI))
+    check(det, port, make_scan("C1", 5), make_params(curb_points=40, **FULL_ROI))
+    check(det, port, make_scan("C2", 6, order="ring"), make_params(curb_points=33, beamZone=12.5, **FULL_ROI))
+
+
+def test_gpu_radius_ties_follow_input_order(det):
+    """Exact radius ties inside a sector: the reference's order is whatever its introsort leaves; ours is (radius, input
+    index) — flagged in urf_result.flags bit1 and identical to the CPU model of the same policy."""
+    pts = make_scan("C1", 8).copy()
+    pts[1000:1400, :3] = pts[3000:3400, :3]                        # 400 exact duplicates -> same sector, same radius
+    prm = make_params(**FULL_ROI)
+    det.set_params(prm)
+    r = det.filtered(pts)
+    m = _model().run(pts, prm)
+    assert r.flags & 2 and m.flags & 2
+    assert np.array_equal(r.label, m.label) and np.array_equal(r.ring, m.ring)
+    if not (r.flags & 4):
+        assert np.array_equal(r.order, m.order) and np.array_equal(r.vert, m.vert)
