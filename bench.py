@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--shape", default="C2", choices=sorted(SHAPES))
     ap.add_argument("--cpu-repeat", type=int, default=3, help="scans per host core in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--groups", type=int, default=0, help="compute streams per device-resident batch (0 = library default)")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the host-buffer region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "urf" else args.warmup
 
@@ -229,6 +231,10 @@ def main():
     prm = bench_params(args.shape)
     clouds = [make_scan(args.shape, seed) for seed in seeds_for_rank(B, rank)]
     det = api.Detector(max_points=n, max_batch=B, device=local, params=prm)
+    if args.groups:
+        det.set_option(2, args.groups)
+    if os.environ.get("URF_TUNE_A"):
+        det.set_option(4, int(os.environ["URF_TUNE_A"]))
     lib, ctx = det.lib, det._ctx
     S = n
     x = torch.empty((B, S, 4), dtype=torch.float32, device="cuda")
@@ -284,6 +290,14 @@ def main():
             ktimes[name] = ktimes.get(name, 0.0) + ms / kprof
     det.set_option(1, 0)
     # ---- timed region 2: end to end through the host-buffer C-ABI call ---------------------------------------------
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"tuning": True, "groups": args.groups, "ms_per_step": dev_ms / args.steps, "serial_ms_per_step": serial_ms,
+                              "kernel_ms": {k: round(v, 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])[:8]}}), flush=True)
+        det.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     h_in = [torch.from_numpy(c).pin_memory() for c in clouds]
     h_lab = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(B)]
     ptrs = (C.c_void_p * B)(*[t.data_ptr() for t in h_in])

@@ -779,7 +779,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
 // bucket positions plus a halo of curb_points on each side in shared memory (plain global reads when curb_points
 // exceeds kHalo).
 constexpr int kHalo = 32;
-__global__ void __launch_bounds__(256) k_ring_detect(DevBuffers buf, DevParams prm, int S) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
   const int N = out.n_order;
