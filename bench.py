@@ -132,6 +132,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(torch, local: int) -> None:
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off (sysfs), so that pinned host buffers and the copy
+    threads are local to the PCIe root of the GPU. Best effort: silently does nothing where sysfs says nothing."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return
+        cpus: set[int] = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -223,6 +243,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl urf needs a CUDA device: urban_road_filter_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    pin_to_gpu_numa_node(torch, local)      # before any pinned allocation: host buffers land next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -233,8 +254,6 @@ def main():
     det = api.Detector(max_points=n, max_batch=B, device=local, params=prm)
     if args.groups:
         det.set_option(2, args.groups)
-    if os.environ.get("URF_TUNE_A"):
-        det.set_option(4, int(os.environ["URF_TUNE_A"]))
     lib, ctx = det.lib, det._ctx
     S = n
     x = torch.empty((B, S, 4), dtype=torch.float32, device="cuda")
