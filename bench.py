@@ -79,11 +79,15 @@ def _cuda_initialised() -> bool:
         return False
 
 
-def usable_cores() -> int:
+def usable_cores(shape_key: str = "C2") -> int:
+    """One single-threaded reference process per host core, capped by memory: the reference allocates
+    channels x N x 48 B per scan (lidar_segmentation.cpp:207) — 0.4 GB at C2, 12.9 GB at C5."""
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    sh = SHAPES[shape_key]
+    per_proc = 1.5 * sh.channels * sh.rings * sh.cols * 48 + 2**30
     try:
         import psutil
-        cores = min(cores, max(1, int(psutil.virtual_memory().available / (1.5 * 2**30))))   # ~0.5 GB per reference process
+        cores = min(cores, max(1, int(psutil.virtual_memory().available / per_proc)))
     except Exception:
         pass
     return max(1, cores)
@@ -178,7 +182,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0            # the reference arm is a host-CPU measurement: rank 0 alone runs and prints it
-    cores = usable_cores()
+    cores = usable_cores(args.shape)
     n = SHAPES[args.shape].rings * SHAPES[args.shape].cols
     for _ in range(args.warmup):
         cpu_reference_rate(args.shape, cores, 1)
@@ -194,7 +198,7 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
         "config": {"workload": f"{SHAPES[args.shape].name} {n}-pt scans, all three detectors + blindSpots, full-ROI preset "
-                               f"(BASELINE config 2); one step = {cores} scans, one per host core",
+                               f"({args.shape}); one step = {cores} scans, one per host core",
                    "points_per_scan": n, "mpoints_per_sec": value * n / 1e6},
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": kind,
                          "sample": f"{cores} single-threaded processes x 1 scan per step, median of {args.steps} steps"},
@@ -230,7 +234,7 @@ def main():
     # CPU baseline first (rank 0, N == 1 only), before CUDA is initialised in this process
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = usable_cores()
+        cores = usable_cores(args.shape)
         rate, per_scan_ms, kind = cpu_reference_rate(args.shape, cores, args.cpu_repeat)
         cpu_baseline = {"value": rate, "unit": "scans/s", "cores": cores, "kind": kind,
                         "sample": f"{cores} single-threaded processes x {args.cpu_repeat} scans each (after one untimed scan), "
