@@ -131,7 +131,7 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   if (dp.star) {
     const int gbig = std::max(4, std::min(kSectKeys, 2048 / B)), gslow = std::max(2, std::min(kSectKeys, 512 / B));
     K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, S));
-    K("k_star_radix_cta", k_star_radix_cta<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
+    K("k_star_sort_cta", k_star_sort_cta<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
     K("k_star_sort", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S));
     K("k_star_scan", k_star_scan<<<dim3((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B), kScanWarps * 32, 0, st>>>(buf, dp, S));
   }
@@ -306,7 +306,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
     CKF(cudaMemcpyToSymbol(c_beam_yx, byx, sizeof(byx)));
     ctx->dp.Kfi = Kfi;
   }
-  CKF(cudaFuncSetAttribute(k_star_radix_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
+  CKF(cudaFuncSetAttribute(k_star_sort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
   CKF(cudaFuncSetAttribute(k_sort_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingSmemKeys * sizeof(unsigned long long))));
   urf_default_params(&ctx->params);
   const char* fe = std::getenv("URF_FORCE_EXACT_REGISTRATION");

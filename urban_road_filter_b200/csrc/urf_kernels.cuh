@@ -7,10 +7,12 @@
 //
 // Pipeline (DESIGN.md has the picture):
 //   k_reset -> k_points -> k_register -> k_assign -> [k_register_exact -> k_assign(redo) -> k_mark_exact]
-//   -> k_scan_offsets -> k_scatter -> k_star_radix_warp / k_star_radix_cta / k_star_sort(fallback) -> k_star_scan
+//   -> k_scan_offsets -> k_scatter -> k_star_sort_warp / k_star_sort_cta / k_star_sort(fallback) -> k_star_scan
 //   -> k_ring_detect -> k_tab1 -> k_reach -> k_tab2 -> k_label -> k_dmax -> k_best -> k_verts
 //   [-> k_sort_rings when the emission order is requested]
 #pragma once
+#include <type_traits>
+
 #include "urf_device.cuh"
 #include "urf_logic.cuh"
 
@@ -447,171 +449,91 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
 // Star-shaped search, sort by planar radius (star_shaped_search.cpp:109). Order: (r, input index) — the reference's
 // introsort order for equal r is unspecified; ties raise F_TIE_SECTOR.
 //
-// Stable LSD radix sort in shared memory on (radius bits - sector minimum), 9 bits per pass, only as many passes as the
-// sector's radius range needs (3 for a street scene). Independent of how the radii are distributed (wall returns pile up
-// within millimetres). Equal radii are then ordered by input index in a tiny fix-up. GROUP = 32: one warp per sector
-// (n <= kWarpCap); GROUP = 256: one CTA per sector from a work list (n <= kCtaCap); anything else (or a sector with a
-// run of more than kTieMax equal radii) goes to the bitonic fallback.
-constexpr int kWarpCap = 512, kCtaCap = 8192, kTieMax = 128, kStarWarps = 6, kRadix = 512, kRadixBits = 9;
+// Register-resident bitonic network: thread t owns elements t*EPL .. t*EPL+EPL-1 (32-bit radius bits + the element's slot
+// in the unsorted sector as payload). Strides below EPL are register-only compare-exchanges, strides below 32*EPL go
+// through warp shuffles, larger strides (multi-warp CTAs only) exchange through shared memory. One warp sorts up to 1024
+// points (k_star_sort_warp, one 32-thread CTA per sector so that all control flow around the shuffles is provably
+// uniform), eight warps up to 8192 (k_star_sort_cta, work list). Returns true when two points share a radius: their
+// order must follow the input index, which the network does not see — such a sector, like any sector beyond 8192
+// points, is redone by the 64-bit bitonic fallback k_star_sort.
+constexpr int kWarpCap = 1024, kCtaCap = 8192;
 
-template <int GROUP>
-__device__ __forceinline__ void group_sync() { if (GROUP == 32) __syncwarp(); else __syncthreads(); }
-
-// returns true if the sector must be redone by the fallback
-template <int GROUP, int CAP>
-__device__ bool radix_sort_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid, unsigned* keyA,
-                                  unsigned* keyB, unsigned short* elA, unsigned short* elB, unsigned short* cnt /*[W][kRadix]*/,
-                                  unsigned* s_misc /*[2 + W]*/, int* tie_out) {
-  constexpr int W = GROUP / 32;
-  const int warp = tid >> 5, lane = tid & 31;
-  // (1) keys relative to the sector minimum
-  unsigned mn = 0xffffffffu, mx = 0u;
-  for (int e = tid; e < n; e += GROUP) { const unsigned v = fbits(src[e].x); keyA[e] = v; elA[e] = (unsigned short)e; mn = min(mn, v); mx = max(mx, v); }
-  if (tid == 0) { s_misc[0] = 0xffffffffu; s_misc[1] = 0u; }
-  group_sync<GROUP>();
-  for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-  if (lane == 0) { atomicMin(&s_misc[0], mn); atomicMax(&s_misc[1], mx); }
-  group_sync<GROUP>();
-  mn = s_misc[0]; mx = s_misc[1];
-  for (int e = tid; e < n; e += GROUP) keyA[e] -= mn;
-  group_sync<GROUP>();
-  const unsigned range = mx - mn;
-  const int nbits = range ? 32 - __clz(range) : 0;
-  const int passes = (nbits + kRadixBits - 1) / kRadixBits;
-  const int per = (((n + W - 1) / W) + 31) & ~31;              // contiguous slice per warp, multiple of 32
-  const int s0 = min(n, warp * per), s1 = min(n, s0 + per);
-  const unsigned lt = (1u << lane) - 1u;
-  unsigned short* mycnt = cnt + warp * kRadix;
-  for (int pass = 0; pass < passes; pass++) {
-    const int shift = pass * kRadixBits;
-    for (int t = tid; t < W * kRadix; t += GROUP) cnt[t] = 0;
-    group_sync<GROUP>();
-    unsigned packed[CAP / GROUP];
-#pragma unroll
-    for (int it = 0; it < CAP / GROUP; it++) {
-      const int e = s0 + it * 32 + lane;
-      const bool valid = e < s1;
-      const int d = valid ? (int)((keyA[e] >> shift) & (kRadix - 1)) : -1;
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
-      unsigned pk = 0xffffffffu;
-      if (valid) pk = ((unsigned)d << 16) | (mycnt[d] + __popc(peers & lt));
-      __syncwarp();
-      if (valid && lane == __ffs(peers) - 1) mycnt[d] += (unsigned short)__popc(peers);
-      __syncwarp();
-      packed[it] = pk;
-    }
-    group_sync<GROUP>();
-    // digit-major, warp-minor exclusive offsets: each thread owns kRadix / GROUP consecutive digits
-    {
-      constexpr int DPT = kRadix / GROUP;
-      unsigned tot[DPT], sum = 0;
-#pragma unroll
-      for (int j = 0; j < DPT; j++) {
-        unsigned t = 0;
-        for (int w = 0; w < W; w++) t += cnt[w * kRadix + tid * DPT + j];
-        tot[j] = t; sum += t;
-      }
-      unsigned inc = sum;
-      for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-      unsigned woff = 0;
-      if (W > 1) {
-        if (lane == 31) s_misc[2 + warp] = inc;
-        __syncthreads();
-        for (int w = 0; w < warp; w++) woff += s_misc[2 + w];
-      }
-      unsigned run = woff + inc - sum;
-#pragma unroll
-      for (int j = 0; j < DPT; j++) {
-        unsigned r2 = run;
-        for (int w = 0; w < W; w++) { unsigned short* c = &cnt[w * kRadix + tid * DPT + j]; unsigned v = *c; *c = (unsigned short)r2; r2 += v; }
-        run += tot[j];
-      }
-    }
-    group_sync<GROUP>();
-#pragma unroll
-    for (int it = 0; it < CAP / GROUP; it++) {
-      const unsigned pk = packed[it];
-      if (pk != 0xffffffffu) {
-        const int e = s0 + it * 32 + lane;
-        const unsigned dstp = mycnt[pk >> 16] + (pk & 0xffffu);
-        keyB[dstp] = keyA[e];
-        elB[dstp] = elA[e];
-      }
-    }
-    group_sync<GROUP>();
-    unsigned* tk = keyA; keyA = keyB; keyB = tk;
-    unsigned short* te = elA; elA = elB; elB = te;
-  }
-  // (2) write out; runs of equal radius are ordered by input index
-  bool tie = false, slow = false;
-  for (int q = tid; q < n; q += GROUP) {
-    const unsigned k = keyA[q];
-    const bool eq_l = q > 0 && keyA[q - 1] == k, eq_r = q + 1 < n && keyA[q + 1] == k;
-    if (!eq_l && !eq_r) { dst[q] = src[elA[q]]; continue; }
-    tie = true;
-    int s = q, e = q + 1;
-    while (s > 0 && keyA[s - 1] == k && q - s <= kTieMax) s--;
-    while (e < n && keyA[e] == k && e - q <= kTieMax) e++;
-    if (e - s > kTieMax) { slow = true; continue; }
-    const float4 me = src[elA[q]];
-    const int myidx = __float_as_int(me.z);
-    int rank = 0;
-    for (int j = s; j < e; j++) rank += __float_as_int(src[elA[j]].z) < myidx;
-    dst[s + rank] = me;
-  }
-  if (tie) *tie_out = 1;
-  return slow;
-}
-
-// Warp sort for sectors of up to 32 * EPL points: bitonic network held in registers (blocked layout: lane l owns elements
-// l*EPL .. l*EPL+EPL-1), 32-bit keys (radius bits) with the element's slot in the unsorted sector as payload. Strides
-// below EPL are register-only compare-exchanges, larger strides go through shuffles; no shared memory, no dependent
-// memory chain. Returns true when two points share a radius: their order must follow the input index, which this
-// network does not see — the sector is then redone by the 64-bit fallback sort.
-template <int EPL>
-__device__ __forceinline__ bool warp_bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int lane) {
+template <int EPL, int WARPS>
+__device__ __forceinline__ bool bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid,
+                                               unsigned* s_xk, unsigned* s_xe) {
+  constexpr int THREADS = WARPS * 32, N = THREADS * EPL;
+  const int lane = tid & 31;
   unsigned key[EPL], el[EPL];
 #pragma unroll
   for (int r = 0; r < EPL; r++) {
-    const int e = lane * EPL + r;
+    const int e = tid * EPL + r;
     key[r] = 0xffffffffu; el[r] = 0u;
     if (e < n) { key[r] = fbits(src[e].x); el[r] = (unsigned)e; }
   }
-  constexpr int N = 32 * EPL;
+  // intra-thread compare-exchange network for strides EPL/2 .. 1 of merge phase k (compile-time register indices)
+  auto intra = [&](int k_over_epl, auto kc) {
+    constexpr int K = decltype(kc)::value;             // K > 0: merge phase k = K < EPL (direction depends on r only)
 #pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = (K > 0 ? K : EPL) >> 1; j > 0; j >>= 1) {
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j < EPL) {
-#pragma unroll
-        for (int r = 0; r < EPL; r++) {
-          if ((r & j) == 0) {
-            const bool asc = k < EPL ? ((r & k) == 0) : ((lane & (k / EPL)) == 0 || k == N);
-            const bool sw = (key[r] > key[r | j]) == asc;
-            const unsigned ka = sw ? key[r | j] : key[r], kb = sw ? key[r] : key[r | j];
-            const unsigned ea = sw ? el[r | j] : el[r], eb = sw ? el[r] : el[r | j];
-            key[r] = ka; key[r | j] = kb; el[r] = ea; el[r | j] = eb;
-          }
+      for (int r = 0; r < EPL; r++) {
+        if ((r & j) == 0) {
+          const bool asc = K > 0 ? ((r & K) == 0) : ((tid & k_over_epl) == 0);
+          const bool sw = (key[r] > key[r | j]) == asc;
+          const unsigned ka = sw ? key[r | j] : key[r], kb = sw ? key[r] : key[r | j];
+          const unsigned ea = sw ? el[r | j] : el[r], eb = sw ? el[r] : el[r | j];
+          key[r] = ka; key[r | j] = kb; el[r] = ea; el[r | j] = eb;
         }
-      } else {
-        const int lj = j / EPL;
-        const bool keep_min = ((lane & lj) == 0) == ((lane & (k / EPL)) == 0 || k == N);
+      }
+    }
+  };
+  // phases k = 2 .. EPL/2: entirely inside the thread
+  if (EPL > 2) intra(0, std::integral_constant<int, 2>());
+  if (EPL > 4) intra(0, std::integral_constant<int, 4>());
+  if (EPL > 8) intra(0, std::integral_constant<int, 8>());
+  if (EPL > 16) intra(0, std::integral_constant<int, 16>());
+  // phases k = EPL .. N: thread-level strides (shuffles / shared memory, runtime loop), then the intra-thread strides
+  for (int ke = 1; ke <= THREADS; ke <<= 1) {          // ke = k / EPL
+    for (int tj = ke >> 1; tj > 0; tj >>= 1) {         // partner thread = tid ^ tj
+      const bool keep_min = ((tid & tj) == 0) == ((tid & ke) == 0);
+      if (tj < 32) {
 #pragma unroll
         for (int r = 0; r < EPL; r++) {
-          const unsigned o = __shfl_xor_sync(0xffffffffu, key[r], lj);
-          const unsigned oe = __shfl_xor_sync(0xffffffffu, el[r], lj);
-          const bool take = (o < key[r]) == keep_min;          // branch-free; taking an equal key is harmless
+          const unsigned o = __shfl_xor_sync(0xffffffffu, key[r], tj);
+          const unsigned oe = __shfl_xor_sync(0xffffffffu, el[r], tj);
+          const bool take = (o < key[r]) == keep_min;            // branch-free; taking an equal key is harmless
+          key[r] = take ? o : key[r];
+          el[r] = take ? oe : el[r];
+        }
+      } else {                                         // partner in another warp: exchange through shared memory
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < EPL; r++) { s_xk[r * THREADS + tid] = key[r]; s_xe[r * THREADS + tid] = el[r]; }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < EPL; r++) {
+          const unsigned o = s_xk[r * THREADS + (tid ^ tj)], oe = s_xe[r * THREADS + (tid ^ tj)];
+          const bool take = (o < key[r]) == keep_min;
           key[r] = take ? o : key[r];
           el[r] = take ? oe : el[r];
         }
       }
     }
+    intra(ke, std::integral_constant<int, 0>());
+  }
+  // write out + tie detection against the predecessor in sorted order
+  unsigned prev0 = __shfl_up_sync(0xffffffffu, key[EPL - 1], 1);
+  if (WARPS > 1) {
+    __syncthreads();
+    if (lane == 31) s_xk[tid >> 5] = key[EPL - 1];
+    __syncthreads();
+    if (lane == 0 && tid > 0) prev0 = s_xk[(tid >> 5) - 1];
   }
   bool tie = false;
 #pragma unroll
   for (int r = 0; r < EPL; r++) {
-    const int e = lane * EPL + r;
-    const unsigned prev = r > 0 ? key[r - 1] : __shfl_up_sync(0xffffffffu, key[EPL - 1], 1);
+    const int e = tid * EPL + r;
+    const unsigned prev = r > 0 ? key[r - 1] : prev0;
     if (e < n) {
       dst[e] = src[el[r]];
       if (e > 0 && prev == key[r]) tie = true;
@@ -638,40 +560,36 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, int S) {
     return;
   }
   bool tie;
-  if (n <= 128) tie = warp_bitonic_sector<4>(src, dst, n, lane);
-  else if (n <= 256) tie = warp_bitonic_sector<8>(src, dst, n, lane);
-  else tie = warp_bitonic_sector<16>(src, dst, n, lane);
+  if (n <= 128) tie = bitonic_sector<4, 1>(src, dst, n, lane, nullptr, nullptr);
+  else if (n <= 256) tie = bitonic_sector<8, 1>(src, dst, n, lane, nullptr, nullptr);
+  else if (n <= 512) tie = bitonic_sector<16, 1>(src, dst, n, lane, nullptr, nullptr);
+  else tie = bitonic_sector<32, 1>(src, dst, n, lane, nullptr, nullptr);
   if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;   // sets F_TIE_SECTOR there
 }
 
-constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap + 2 * sizeof(unsigned short) * kCtaCap + sizeof(unsigned short) * 8 * kRadix + 64;
-__global__ void __launch_bounds__(256) k_star_radix_cta(DevBuffers buf, int S) {
+constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap;
+__global__ void __launch_bounds__(256) k_star_sort_cta(DevBuffers buf, int S) {
   extern __shared__ unsigned s_dyn[];
   const int b = blockIdx.y;
   ScanTab& tab = buf.tab[b];
-  unsigned* keyA = s_dyn;
-  unsigned* keyB = keyA + kCtaCap;
-  unsigned short* elA = reinterpret_cast<unsigned short*>(keyB + kCtaCap);
-  unsigned short* elB = elA + kCtaCap;
-  unsigned short* cnt = elB + kCtaCap;
-  unsigned* s_misc = reinterpret_cast<unsigned*>(cnt + 8 * kRadix);
-  __shared__ int s_flags[2];
+  unsigned* s_xk = s_dyn;
+  unsigned* s_xe = s_dyn + kCtaCap;
+  __shared__ int s_tie;
   const int nbig = tab.nbig;
   for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
     const int s = tab.biglist[w];
     const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
-    if (threadIdx.x < 2) s_flags[threadIdx.x] = 0;
+    const float4* src = buf.spt + (size_t)b * S + base;
+    float4* dst = buf.ssorted + (size_t)b * S + base;
+    if (threadIdx.x == 0) s_tie = 0;
+    bool tie;
+    if (n <= 2048) tie = bitonic_sector<8, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
+    else if (n <= 4096) tie = bitonic_sector<16, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
+    else tie = bitonic_sector<32, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
     __syncthreads();
-    int tie = 0;
-    const bool slow = radix_sort_sector<256, kCtaCap>(buf.spt + (size_t)b * S + base, buf.ssorted + (size_t)b * S + base, n, threadIdx.x,
-                                                       keyA, keyB, elA, elB, cnt, s_misc, &tie);
-    if (slow) s_flags[0] = 1;
-    if (tie) s_flags[1] = 1;
+    if (tie) s_tie = 1;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      if (s_flags[0]) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;
-      if (s_flags[1]) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
-    }
+    if (threadIdx.x == 0 && s_tie) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;
     __syncthreads();
   }
 }
