@@ -135,6 +135,15 @@ int urf_get_params(const urf_ctx* ctx, urf_params* p);
  * 16 bytes of each pcl::PointXYZI record once the PointCloud2 has been deserialised. Synchronous. */
 int urf_process(urf_ctx* ctx, const float* xyzi, int n, urf_result* out);
 
+/* Same as urf_process, but takes the raw `data` bytes of a sensor_msgs/PointCloud2 message (what pcl_ros deserialises
+ * for the reference's callback, lidar_segmentation.cpp:53,95): n_points records of point_step bytes in HOST memory, with
+ * x / y / z (FLOAT32) at byte offsets off_x / off_y / off_z inside a record (Ouster: 48-byte records, Velodyne: 22 or 32).
+ * Records need not be 4-byte aligned. The bytes are copied to the device as they are and unpacked there;
+ * point_step must be in [12, URF_MAX_POINT_STEP]. Synchronous. */
+#define URF_MAX_POINT_STEP 64
+int urf_process_cloud2(urf_ctx* ctx, const void* data, int n_points, int point_step, int off_x, int off_y, int off_z,
+                       urf_result* out);
+
 /* `batch` independent scans (distinct clouds, same params), HOST buffers. xyzi[b] has n[b] points; outs[b] as above. */
 int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int batch, urf_result* outs);
 

@@ -243,3 +243,54 @@ def test_gpu_radius_ties_follow_input_order(det):
     assert np.array_equal(r.label, m.label) and np.array_equal(r.ring, m.ring)
     if not (r.flags & 4):
         assert np.array_equal(r.order, m.order) and np.array_equal(r.vert, m.vert)
+
+
+def test_gpu_device_resident_multi_stream_groups(port):
+    """A device-resident batch of >= 8 scans is spread over four compute streams (offset buffer views, fork/join on the
+    context's stream): every scan must still get exactly the oracle's labels, with a ragged batch and a stride larger
+    than any scan."""
+    d = api.Detector(max_points=30_000, max_batch=20)
+    try:
+        prm = make_params(**FULL_ROI)
+        d.set_params(prm)
+        clouds = [make_scan("C1", 60 + s, order=("column", "ring")[s % 2])[: 28800 - 1013 * (s % 4)] for s in range(19)]
+        clouds[11] = random_cloud(5000, 5)
+        S = 29_696
+        x = torch.zeros((19, S, 4), dtype=torch.float32, device="cuda")
+        for b, c in enumerate(clouds):
+            x[b, : c.shape[0]] = torch.from_numpy(c).cuda()
+        lab = torch.full((19, S), -7, dtype=torch.int32, device="cuda")
+        n = (C.c_int * 19)(*[c.shape[0] for c in clouds])
+        from urban_road_filter_b200 import UrfResult
+        outs = (UrfResult * 19)()
+        torch.cuda.synchronize()
+        for groups in (4, 1):
+            d.set_option(2, groups)
+            lab.fill_(-7)
+            assert d.lib.urf_process_batch_device(d._ctx, x.data_ptr(), S, n, 19, lab.data_ptr(), outs) == 0
+            host = lab.cpu().numpy()
+            for b, c in enumerate(clouds):
+                o = port.run(c, prm)
+                assert np.array_equal(host[b, : c.shape[0]], o.label), (groups, b)
+                assert np.all(host[b, c.shape[0]:] == -7)            # nothing written beyond the scan
+                assert (outs[b].n_road, outs[b].n_curb, outs[b].n_vert, outs[b].n_rings) == (o.n_road, o.n_curb, o.n_vert, o.n_rings)
+                assert np.array_equal(np.ctypeslib.as_array(outs[b].vert).reshape(-1, 4)[: o.n_vert], o.vert)
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("step,ox,oy,oz", [(16, 0, 4, 8), (32, 0, 4, 8), (48, 0, 4, 8), (22, 0, 4, 8), (22, 8, 4, 12), (64, 40, 12, 28)])
+def test_gpu_pointcloud2_unpack_on_device(det, port, step, ox, oy, oz):
+    """urf_process_cloud2: raw PointCloud2 records (Ouster 48 B, Velodyne 22/32 B incl. records that are not 4-byte aligned,
+    shuffled field offsets) unpacked on the device give the same result as the repacked float4 cloud."""
+    pts = make_scan("C1", 9)
+    n = pts.shape[0]
+    raw = np.random.default_rng(step).integers(0, 256, n * step, dtype=np.uint8)      # garbage in the other fields
+    rec = raw.reshape(n, step)
+    for k, off in enumerate((ox, oy, oz)):
+        rec[:, off: off + 4] = pts[:, k: k + 1].copy().view(np.uint8)
+    prm = make_params(**FULL_ROI)
+    det.set_params(prm)
+    r = det.filtered_cloud2(raw, n, step, ox, oy, oz)
+    o = port.run(pts, prm)
+    assert stage_diffs(o, r, n) == []

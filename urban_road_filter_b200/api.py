@@ -14,7 +14,7 @@ from .ctypes_abi import (URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_TOO_FEW_PO
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liburf_b200.so")
 
-EXPORTS = ["urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
+EXPORTS = ["urf_process_cloud2", "urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
            "urf_set_params", "urf_get_params", "urf_process", "urf_process_batch", "urf_process_batch_device",
            "urf_enqueue_batch_device", "urf_finish_batch_device", "urf_stream", "urf_last_device_ms",
            "urf_last_launch_count", "urf_build_markers"]
@@ -51,6 +51,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.urf_set_option.argtypes = [vp, ip, ip]
     lib.urf_process.argtypes = [vp, vp, ip, C.POINTER(UrfResult)]
     lib.urf_process_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(ip), ip, C.POINTER(UrfResult)]
+    lib.urf_process_cloud2.argtypes = [vp, vp, ip, ip, ip, ip, ip, C.POINTER(UrfResult)]
     lib.urf_process_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp, C.POINTER(UrfResult)]
     lib.urf_enqueue_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp]
     lib.urf_finish_batch_device.argtypes = [vp, C.POINTER(UrfResult)]
@@ -185,6 +186,25 @@ class Detector:
             r.vert = np.ctypeslib.as_array(res[b].vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()
             out.append(r)
         return out
+
+    def filtered_cloud2(self, data: bytes | np.ndarray, n_points: int, point_step: int, off_x: int, off_y: int, off_z: int) -> ScanResult:
+        """One scan from the raw `data` bytes of a sensor_msgs/PointCloud2 (unpacked on the device)."""
+        raw = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        m = max(n_points, 1)
+        lab, ring, order = np.full(m, -1, np.int32), np.full(m, -1, np.int32), np.zeros(m, np.int32)
+        rs = np.zeros(URF_MAX_CHANNELS + 1, np.int32)
+        res = UrfResult()
+        res.label = lab.ctypes.data_as(C.POINTER(C.c_int32)); res.ring = ring.ctypes.data_as(C.POINTER(C.c_int32))
+        res.order = order.ctypes.data_as(C.POINTER(C.c_int32)); res.ring_start = rs.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(self.lib.urf_process_cloud2(self._ctx, raw.ctypes.data, n_points, point_step, off_x, off_y, off_z, C.byref(res)),
+                    "urf_process_cloud2")
+        r = ScanResult()
+        for f in ("status", "n_in", "n_roi", "n_rings", "n_order", "n_road", "n_curb", "n_vert", "flags"):
+            setattr(r, f, int(getattr(res, f)))
+        r.label, r.ring, r.order = lab[:n_points], ring[:n_points], order[: r.n_order].copy()
+        r.ring_start = rs[: r.n_rings + 1].copy()
+        r.vert = np.ctypeslib.as_array(res.vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()
+        return r
 
     def filtered(self, cloud, **kw) -> ScanResult:
         """One Detector::filtered() call."""

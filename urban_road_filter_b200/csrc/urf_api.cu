@@ -35,6 +35,7 @@ struct urf_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuffers buf{};
   float4* own_in = nullptr;
+  unsigned char* raw = nullptr;        // PointCloud2 staging: max_points * URF_MAX_POINT_STEP bytes (urf_process_cloud2)
   int* own_label = nullptr;
   urf_params params{};
   DevParams dp{};
@@ -262,6 +263,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   const size_t P = ctx->P;
   DevBuffers& b = ctx->buf;
   TRY(dalloc(ctx, &ctx->own_in, P));
+  TRY(dalloc(ctx, &ctx->raw, (size_t)ctx->max_points * URF_MAX_POINT_STEP));
   TRY(dalloc(ctx, &b.alpha_v, P));
   TRY(dalloc(ctx, &b.mark, P));
   TRY(dalloc(ctx, &b.ringid, P));
@@ -526,6 +528,38 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
     fill_result(ctx->h_out[b], &outs[b]);
     if (outs[b].status == URF_TOO_FEW_POINTS && outs[b].ring) for (int i = 0; i < n[b]; i++) outs[b].ring[i] = -1;
   }
+  return URF_OK;
+}
+
+int urf_process_cloud2(urf_ctx* ctx, const void* data, int n, int point_step, int off_x, int off_y, int off_z, urf_result* out) {
+  if (!ctx || !out || n < 0 || (n > 0 && !data)) return URF_ERR_INVALID;
+  if (point_step < 12 || point_step > URF_MAX_POINT_STEP) return URF_ERR_INVALID;
+  for (int o : {off_x, off_y, off_z}) if (o < 0 || o + 4 > point_step) return URF_ERR_INVALID;
+  if (n > ctx->max_points) return URF_ERR_CAPACITY;
+  CK(cudaSetDevice(ctx->device));
+  const int S = ((std::max(n, 1) + 255) / 256) * 256;
+  cudaStream_t st = ctx->stream;
+  ctx->h_n[0] = n;
+  CK(cudaMemcpyAsync(ctx->buf.n, ctx->h_n, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (n > 0) {
+    CK(cudaMemcpyAsync(ctx->raw, data, (size_t)n * point_step, cudaMemcpyHostToDevice, st));
+    k_unpack_cloud2<<<(n + 255) / 256, 256, 0, st>>>(ctx->raw, ctx->own_in, n, point_step, off_x, off_y, off_z);
+  }
+  const bool want_order = out->order != nullptr;
+  int rc = launch_pipeline_graphed(ctx, 1, S, want_order);
+  if (rc != URF_OK) return rc;
+  int* ring32 = reinterpret_cast<int*>(ctx->buf.sortbuf);
+  if (out->ring) k_ring32<<<dim3((S + 255) / 256, 1), 256, 0, st>>>(ctx->buf, ring32, S);
+  CK(cudaMemcpyAsync(ctx->h_out, ctx->buf.out, sizeof(ScanOut), cudaMemcpyDeviceToHost, st));
+  if (n > 0) {
+    if (out->label) CK(cudaMemcpyAsync(out->label, ctx->own_label, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (out->ring) CK(cudaMemcpyAsync(out->ring, ring32, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (out->order) CK(cudaMemcpyAsync(out->order, ctx->buf.order, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  ctx->last_B = 1; ctx->last_S = S;
+  fill_result(ctx->h_out[0], out);
+  if (out->status == URF_TOO_FEW_POINTS && out->ring) for (int i = 0; i < n; i++) out->ring[i] = -1;
   return URF_OK;
 }
 

@@ -461,7 +461,7 @@ constexpr int kWarpCap = 1024, kCtaCap = 8192;
 template <int EPL, int WARPS>
 __device__ __forceinline__ bool bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid,
                                                unsigned* s_xk, unsigned* s_xe) {
-  constexpr int THREADS = WARPS * 32, N = THREADS * EPL;
+  constexpr int THREADS = WARPS * 32;                // sorts up to THREADS * EPL elements
   const int lane = tid & 31;
   unsigned key[EPL], el[EPL];
 #pragma unroll
@@ -977,6 +977,21 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
     if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(key >> 32)) tie = true;
   }
   if (tie) atomicOr(&out.flags, F_TIE_AZIMUTH);
+}
+
+// k_unpack_cloud2: PointCloud2 record -> (x, y, z, 0) float4. Byte-wise loads when a field is not
+// 4-byte aligned (Velodyne's 22-byte records).
+__device__ __forceinline__ float load_f32_unaligned(const unsigned char* p) {
+  if ((reinterpret_cast<size_t>(p) & 3) == 0) return *reinterpret_cast<const float*>(p);
+  const unsigned v = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+  return __uint_as_float(v);
+}
+__global__ void __launch_bounds__(256) k_unpack_cloud2(const unsigned char* __restrict__ raw, float4* __restrict__ dst, int n,
+                                                        int point_step, int off_x, int off_y, int off_z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* rec = raw + (size_t)i * point_step;
+  dst[i] = make_float4(load_f32_unaligned(rec + off_x), load_f32_unaligned(rec + off_y), load_f32_unaligned(rec + off_z), 0.f);
 }
 
 // Device-side evaluation of the emulated libm (test hook: urf_test_math).
