@@ -280,33 +280,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, 
   const unsigned short* lut = buf.lut + (size_t)b * (kElevBins + 1);
   unsigned* cnt = s_cnt[warp];
   bool violation = false;
-  constexpr int NIT = kChunk / 32;
-  // all loads of the chunk first (independent, coalesced), then the dependent look-ups: 16 points in flight per lane
-  float av[NIT];
-  unsigned short start[NIT];
-  const size_t g0 = (size_t)b * S + (size_t)chunk * kChunk;
-#pragma unroll
-  for (int it = 0; it < NIT; it++) {
-    const int i = chunk * kChunk + it * 32 + lane;
-    av[it] = i < n ? buf.alpha_v[g0 + it * 32 + lane] : -1.0f;
-  }
-#pragma unroll
-  for (int it = 0; it < NIT; it++) start[it] = (live && av[it] >= 0.0f) ? lut[elev_bin(av[it])] : (unsigned short)0;
-#pragma unroll
-  for (int it = 0; it < NIT; it++) {
+  for (int it = 0; it < kChunk / 32; it++) {
     const int i = chunk * kChunk + it * 32 + lane;
     int ring = -1;
     if (i < n) {
-      const float a = av[it];
+      const size_t g = (size_t)b * S + i;
+      const float a = buf.alpha_v[g];
       const bool kept = live && a >= 0.0f;
       if (kept) {
         int lo;
-        ring = assign_ring_from(s_angle, R, a, prm.interval, start[it], &lo);
+        ring = assign_ring_from(s_angle, R, a, prm.interval, lut[elev_bin(a)], &lo);
         if (verify && registration_violation(s_angle, s_regidx, tab.regorder, R, prm.channels, prm.interval, a, i, lo))
           violation = true;
       }
-      buf.ringid[g0 + it * 32 + lane] = (short)ring;
-      buf.label[g0 + it * 32 + lane] = kept ? URF_LABEL_NONE : URF_LABEL_OUTSIDE;
+      buf.ringid[g] = (short)ring;
+      buf.label[g] = kept ? URF_LABEL_NONE : URF_LABEL_OUTSIDE;
     }
     const unsigned peers = __match_any_sync(0xffffffffu, ring);
     if (ring >= 0 && lane == __ffs(peers) - 1) cnt[ring] += __popc(peers);
@@ -883,63 +871,51 @@ __global__ void __launch_bounds__(256) k_tab2(DevBuffers buf, DevParams prm) {
 
 // k_label: final label per ring-bucket position, scattered back to input order; counts; per degree bin the first
 // non-road point in the reference's scan order; road points are appended to a compact list for the marker search.
-constexpr int kLabelPts = 4;          // bucket positions per thread: their loads are issued together (latency-bound kernel)
 __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
   const int N = out.n_order;
-  const int p0 = blockIdx.x * (256 * kLabelPts);
-  if (p0 >= N) return;
-  const size_t gb = (size_t)b * S;
-  int k[kLabelPts], lab[kLabelPts], idx[kLabelPts], j[kLabelPts], jc[kLabelPts];
-  float a[kLabelPts], tf[kLabelPts], tb[kLabelPts];
-  unsigned long long cb[kLabelPts];
-  unsigned dbits[kLabelPts];
-#pragma unroll
-  for (int u = 0; u < kLabelPts; u++) {
-    const int p = p0 + u * 256 + threadIdx.x;
-    const bool in = p < N;
-    const size_t g = gb + (in ? p : 0);
-    k[u] = buf.bring[g]; a[u] = buf.az[g]; lab[u] = in ? buf.blabel[g] : -1; idx[u] = buf.bidx[g]; dbits[u] = fbits(buf.d2[g]);
+  if ((int)(blockIdx.x * blockDim.x) >= N) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  int lab = -1, k = 0, bin = 0;
+  float a = 0.f;
+  const size_t g = (size_t)b * S + p;
+  if (p < N) {
+    k = buf.bring[g];
+    a = buf.az[g];
+    lab = buf.blabel[g];
+    const int idx = buf.bidx[g];
+    // everything the decision needs is loaded up front (independent loads, one round trip): the two threshold entries
+    // and the bin's current first-non-road key
+    const size_t o = ((size_t)b * prm.channels + k) * kTStride;
+    const bool valid = a >= 0.0f;
+    int j = 0, jc = 0;
+    if (valid) T_indices(a, &j, &jc);
+    const float tf = buf.Tf[o + j], tb = buf.Tb[o + jc];
+    bin = j;                                          // == deg_bin(a)
+    const unsigned long long cb = tab.cutbest[bin];
+    if (lab != 2 && valid && covered_from(a, tf, tb)) lab = 1;       // covered_T of urf_logic.cuh with the loads hoisted
+    buf.blabel[g] = (unsigned char)lab;
+    buf.label[(size_t)b * S + idx] = lab;
+    if (valid && lab != 1) {                          // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
+      const unsigned long long key = best_key(k, fbits(a), p);
+      if (cb > key) atomicMin(&tab.cutbest[bin], key);
+    }
   }
-#pragma unroll
-  for (int u = 0; u < kLabelPts; u++) {
-    // everything the decision needs (independent loads): the two threshold entries and the bin's first-non-road key
-    const bool valid = a[u] >= 0.0f;
-    j[u] = 0; jc[u] = 0;
-    if (valid) T_indices(a[u], &j[u], &jc[u]);
-    const size_t o = ((size_t)b * prm.channels + k[u]) * kTStride;
-    tf[u] = buf.Tf[o + j[u]]; tb[u] = buf.Tb[o + jc[u]];
-    cb[u] = tab.cutbest[j[u]];
+  const unsigned br = __ballot_sync(0xffffffffu, lab == 1), bc = __ballot_sync(0xffffffffu, lab == 2);
+  int base = 0;
+  if (lane_id() == 0) {
+    if (br) base = atomicAdd(&out.n_road, __popc(br));
+    if (bc) atomicAdd(&out.n_curb, __popc(bc));
   }
-#pragma unroll
-  for (int u = 0; u < kLabelPts; u++) {
-    const int p = p0 + u * 256 + threadIdx.x;
-    const bool valid = a[u] >= 0.0f;
-    if (p < N) {
-      if (lab[u] != 2 && valid && covered_from(a[u], tf[u], tb[u])) lab[u] = 1;   // covered_T of urf_logic.cuh, loads hoisted
-      buf.blabel[gb + p] = (unsigned char)lab[u];
-      buf.label[gb + idx[u]] = lab[u];
-      if (valid && lab[u] != 1) {                     // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
-        const unsigned long long key = best_key(k[u], fbits(a[u]), p);
-        if (cb[u] > key) atomicMin(&tab.cutbest[j[u]], key);
-      }
-    }
-    const unsigned br = __ballot_sync(0xffffffffu, lab[u] == 1), bc = __ballot_sync(0xffffffffu, lab[u] == 2);
-    int base = 0;
-    if (lane_id() == 0) {
-      if (br) base = atomicAdd(&out.n_road, __popc(br));
-      if (bc) atomicAdd(&out.n_curb, __popc(bc));
-    }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (lab[u] == 1) {
-      // one list slot per road point, handed out per warp from the running road count; a road point whose azimuth is NaN
-      // belongs to no degree bin and is listed as a placeholder
-      const int slot = base + __popc(br & ((1u << lane_id()) - 1u));
-      buf.roadlist[gb + slot] = valid ? make_uint4((unsigned)j[u] | ((unsigned)k[u] << 16), fbits(a[u]), dbits[u], (unsigned)p)
-                                      : make_uint4(0xffffffffu, 0u, 0u, 0u);
-    }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (lab == 1) {
+    // one list slot per road point, handed out per warp from the running road count; a road point whose azimuth is NaN
+    // belongs to no degree bin and is listed as a placeholder
+    const int slot = base + __popc(br & ((1u << lane_id()) - 1u));
+    buf.roadlist[(size_t)b * S + slot] = a >= 0.0f ? make_uint4((unsigned)bin | ((unsigned)k << 16), fbits(a), fbits(buf.d2[g]), (unsigned)p)
+                                                   : make_uint4(0xffffffffu, 0u, 0u, 0u);
   }
 }
 
