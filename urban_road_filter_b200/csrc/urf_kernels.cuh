@@ -733,10 +733,12 @@ __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevPa
   }
   const float4* bucket = buf.bpt + (size_t)b * S;
   const bool tiled = prm.curbPoints <= kHalo;
-  if (tiled) {
-    for (int t = threadIdx.x; t < 256 + 2 * kHalo; t += blockDim.x) {
-      const int p = p0 - kHalo + t;
-      if (p >= 0 && p < N) s_tile[t] = bucket[p];
+  if (tiled) {                                            // one bucket record per thread + a halo record for the first 64 threads
+    const int pc = p0 + (int)threadIdx.x;
+    if (pc < N) s_tile[kHalo + threadIdx.x] = bucket[pc];
+    if (threadIdx.x < 2 * kHalo) {
+      const int ph = threadIdx.x < kHalo ? p0 - kHalo + (int)threadIdx.x : p0 + 256 + (int)threadIdx.x - kHalo;
+      if (ph >= 0 && ph < N) s_tile[threadIdx.x < kHalo ? threadIdx.x : 256 + threadIdx.x] = bucket[ph];
     }
   }
   __syncthreads();

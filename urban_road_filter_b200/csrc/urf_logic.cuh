@@ -159,8 +159,10 @@ URF_HD bool zzero_mark_t(const DevParams& prm, const float4* ring, int n, int m)
   const float4 me = ring[m];
   const float az0 = fabsf(me.z);
   float max1 = az0, max2 = az0;
-  for (int q = m - 1; q >= m - cp; q--) { const float v = fabsf(ring[q].z); if (v > max1) max1 = v; }        // :38-40
-  for (int q = m + 1; q <= m + cp; q++) { const float v = fabsf(ring[q].z); if (v > max2) max2 = v; }        // :47-49
+#pragma unroll
+  for (int u = 1; u <= cp; u++) { const float v = fabsf(ring[m - u].z); if (v > max1) max1 = v; }            // :38-40 (k = j-1 .. j-cp)
+#pragma unroll
+  for (int u = 1; u <= cp; u++) { const float v = fabsf(ring[m + u].z); if (v > max2) max2 = v; }            // :47-49 (k = j+1 .. j+cp)
   const bool h = (URF_FSUB(max1, az0) >= prm.curbHeight || URF_FSUB(max2, az0) >= prm.curbHeight) &&
                  (double)fabsf(URF_FSUB(max1, max2)) >= 0.05;                                                 // :67-69
   if (!h) return false;
@@ -168,8 +170,10 @@ URF_HD bool zzero_mark_t(const DevParams& prm, const float4* ring, int n, int m)
   const float dd = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(hi.x, lo.x)), dsq(URF_FSUB(hi.y, lo.y)))));        // :23-25
   if (!((double)dd < 5.0)) return false;                                                                      // :28
   float va1 = 0.f, va2 = 0.f, vb1 = 0.f, vb2 = 0.f;
-  for (int q = m - 1; q >= m - cp; q--) { const float4 o = ring[q]; va1 = URF_FADD(va1, URF_FSUB(o.x, me.x)); va2 = URF_FADD(va2, URF_FSUB(o.y, me.y)); }   // :35-37
-  for (int q = m + 1; q <= m + cp; q++) { const float4 o = ring[q]; vb1 = URF_FADD(vb1, URF_FSUB(o.x, me.x)); vb2 = URF_FADD(vb2, URF_FSUB(o.y, me.y)); }   // :44-46
+#pragma unroll
+  for (int u = 1; u <= cp; u++) { const float4 o = ring[m - u]; va1 = URF_FADD(va1, URF_FSUB(o.x, me.x)); va2 = URF_FADD(va2, URF_FSUB(o.y, me.y)); }   // :35-37, same order
+#pragma unroll
+  for (int u = 1; u <= cp; u++) { const float4 o = ring[m + u]; vb1 = URF_FADD(vb1, URF_FSUB(o.x, me.x)); vb2 = URF_FADD(vb2, URF_FSUB(o.y, me.y)); }   // :44-46
   const float sc = URF_FDIV(1.0f, (float)cp);
   va1 = URF_FMUL(sc, va1); va2 = URF_FMUL(sc, va2); vb1 = URF_FMUL(sc, vb1); vb2 = URF_FMUL(sc, vb2);        // :52-55
   const float dot = URF_FADD(URF_FMUL(va1, vb1), URF_FMUL(va2, vb2));
