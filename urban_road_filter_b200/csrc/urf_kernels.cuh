@@ -23,6 +23,9 @@ __constant__ float c_beam_o[kSectKeys];
 __constant__ unsigned char c_beam_yx[kSectKeys];
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// 32-bit offset of scan b inside the batch-major arrays (urf_create keeps max_batch * max_points below 2^31): array
+// accesses then cost one IMAD.WIDE instead of 64-bit multiply/add chains
+__device__ __forceinline__ unsigned scan_base(int b, int S) { return (unsigned)b * (unsigned)S; }
 
 // CTA-wide bitonic sort of npad (power of two) keys in shared or global memory; all threads must call.
 template <class T>
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, i
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int keep = 0, sec = -1;
   if (i < n) {
-    const size_t g = (size_t)b * S + i;
+    const unsigned g = scan_base(b, S) + (unsigned)i;
     const float4 p = __ldg(&buf.in[g]);
     keep = roi_keep(prm, p.x, p.y, p.z);
     float a = -1.0f;
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, 
     const int i = chunk * kChunk + it * 32 + lane;
     int ring = -1;
     if (i < n) {
-      const size_t g = (size_t)b * S + i;
+      const unsigned g = scan_base(b, S) + (unsigned)i;
       const float a = buf.alpha_v[g];
       const bool kept = live && a >= 0.0f;
       if (kept) {
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
   unsigned packed[kChunk / 32];                 // (ring + 1) << 16 | rank inside the chunk's ring group
-  const size_t g0 = (size_t)b * S + (size_t)chunk * kChunk;
+  const unsigned gb = scan_base(b, S), g0 = gb + (unsigned)chunk * kChunk;
   // two halves of 8 iterations: the loads of a half (ring, sector, and the point itself where a sector record has to be
   // written) are issued together before the dependent ranking work
   constexpr int HALF = kChunk / 64;
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
         int base = 0;
         if (lane == leader) base = atomicAdd(&tab.sect_cur[sec], __popc(peers));
         base = __shfl_sync(peers, base, leader);
-        buf.spt[(size_t)b * S + base + __popc(peers & lt)] = make_float4(star_radius(pp[u].x, pp[u].y), pp[u].z, __int_as_float(i), 0.f);
+        buf.spt[gb + (unsigned)(base + __popc(peers & lt))] = make_float4(star_radius(pp[u].x, pp[u].y), pp[u].z, __int_as_float(i), 0.f);
       }
       __syncwarp();
     }
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   for (int t = lane; t < total; t += 32) {
     const int li = perm[t], ring = pring[t];
     const float4 p = __ldg(&buf.in[g0 + li]);
-    const size_t dst = (size_t)b * S + goff[ring] + (t - lcnt[ring]);
+    const unsigned dst = gb + goff[ring] + (unsigned)(t - lcnt[ring]);
     buf.bpt[dst] = make_float4(p.x, p.y, p.z, __int_as_float(chunk * kChunk + li));
     buf.bring[dst] = (unsigned char)ring;
     buf.bidx[dst] = chunk * kChunk + li;
@@ -706,7 +709,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
     __syncwarp();
     if (__all_sync(0xffffffffu, done)) break;
   }
-  if (hit >= 0) buf.mark[(size_t)b * S + __float_as_int(all[base + hit].z)] = 2;   // star_shaped_search.cpp:146
+  if (hit >= 0) buf.mark[scan_base(b, S) + (unsigned)__float_as_int(all[base + hit].z)] = 2;   // star_shaped_search.cpp:146
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -727,11 +730,12 @@ __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevPa
   const int p0 = blockIdx.x * blockDim.x;
   if (p0 >= N) return;
   if (threadIdx.x < 32) {                                 // rings are contiguous in bucket order: first .. last ring of the CTA
-    const int k_lo = buf.bring[(size_t)b * S + p0], k_hi = buf.bring[(size_t)b * S + min(p0 + 255, N - 1)];
+    const int k_lo = buf.bring[scan_base(b, S) + (unsigned)p0], k_hi = buf.bring[scan_base(b, S) + (unsigned)min(p0 + 255, N - 1)];
     if (threadIdx.x == 0) s_klo = k_lo;
     for (int t = threadIdx.x; t <= k_hi - k_lo + 1; t += 32) s_rs[t] = out.ring_start[k_lo + t];
   }
-  const float4* bucket = buf.bpt + (size_t)b * S;
+  const unsigned gb = scan_base(b, S);
+  const float4* bucket = buf.bpt + gb;
   const bool tiled = prm.curbPoints <= kHalo;
   if (tiled) {                                            // one bucket record per thread + a halo record for the first 64 threads
     const int pc = p0 + (int)threadIdx.x;
@@ -747,16 +751,16 @@ __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevPa
   int k = -1;
   unsigned dbits = 0;
   if (act) {
-    k = buf.bring[(size_t)b * S + p];
+    k = buf.bring[gb + (unsigned)p];
     const int base = s_rs[k - s_klo], n = s_rs[k - s_klo + 1] - base, m = p - base;
     const float4 me = tiled ? s_tile[threadIdx.x + kHalo] : bucket[p];
     const int idx = __float_as_int(me.w);
     float d, az;
     planar_az(me.x, me.y, &d, &az);                                     // lidar_segmentation.cpp:245-269
-    buf.az[(size_t)b * S + p] = az;
-    buf.d2[(size_t)b * S + p] = d;
+    buf.az[gb + (unsigned)p] = az;
+    buf.d2[gb + (unsigned)p] = d;
     dbits = fbits(d);
-    int lab = prm.star ? buf.mark[(size_t)b * S + idx] : 0;             // :241-242
+    int lab = prm.star ? buf.mark[gb + (unsigned)idx] : 0;             // :241-242
     // ring[q] must address bucket position base + q: through the shared tile, or straight from global memory (two code
     // paths so that the compiler keeps the address space of the loads)
     if (tiled) {
@@ -768,9 +772,9 @@ __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevPa
       if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;
       if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, n, m)) lab = 2;
     }
-    buf.blabel[(size_t)b * S + p] = (unsigned char)lab;
+    buf.blabel[gb + (unsigned)p] = (unsigned char)lab;
     if (lab == 2 && az >= 0.0f) {            // curb aggregates per (ring, integer-degree bin); NaN azimuths fall out
-      const size_t o = ((size_t)b * prm.channels + k) * kDegBins + deg_bin(az);
+      const unsigned o = ((unsigned)b * (unsigned)prm.channels + (unsigned)k) * kDegBins + (unsigned)deg_bin(az);
       atomicMin(&buf.cmin[o], fbits(az));
       atomicMax(&buf.cmax[o], fbits(az));
     }
@@ -882,7 +886,7 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   int lab = -1, k = 0, bin = 0;
   float a = 0.f;
-  const size_t g = (size_t)b * S + p;
+  const unsigned gb = scan_base(b, S), g = gb + (unsigned)p;
   if (p < N) {
     k = buf.bring[g];
     a = buf.az[g];
@@ -890,7 +894,7 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
     const int idx = buf.bidx[g];
     // everything the decision needs is loaded up front (independent loads, one round trip): the two threshold entries
     // and the bin's current first-non-road key
-    const size_t o = ((size_t)b * prm.channels + k) * kTStride;
+    const unsigned o = ((unsigned)b * (unsigned)prm.channels + (unsigned)k) * kTStride;
     const bool valid = a >= 0.0f;
     int j = 0, jc = 0;
     if (valid) T_indices(a, &j, &jc);
@@ -899,7 +903,7 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
     const unsigned long long cb = tab.cutbest[bin];
     if (lab != 2 && valid && covered_from(a, tf, tb)) lab = 1;       // covered_T of urf_logic.cuh with the loads hoisted
     buf.blabel[g] = (unsigned char)lab;
-    buf.label[(size_t)b * S + idx] = lab;
+    buf.label[gb + (unsigned)idx] = lab;
     if (valid && lab != 1) {                          // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
       const unsigned long long key = best_key(k, fbits(a), p);
       if (cb > key) atomicMin(&tab.cutbest[bin], key);
@@ -916,7 +920,7 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
     // one list slot per road point, handed out per warp from the running road count; a road point whose azimuth is NaN
     // belongs to no degree bin and is listed as a placeholder
     const int slot = base + __popc(br & ((1u << lane_id()) - 1u));
-    buf.roadlist[(size_t)b * S + slot] = a >= 0.0f ? make_uint4((unsigned)bin | ((unsigned)k << 16), fbits(a), fbits(buf.d2[g]), (unsigned)p)
+    buf.roadlist[gb + (unsigned)slot] = a >= 0.0f ? make_uint4((unsigned)bin | ((unsigned)k << 16), fbits(a), fbits(buf.d2[g]), (unsigned)p)
                                                    : make_uint4(0xffffffffu, 0u, 0u, 0u);
   }
 }
@@ -929,7 +933,7 @@ __global__ void __launch_bounds__(256) k_dmax(DevBuffers buf, int S) {
   ScanTab& tab = buf.tab[b];
   const int nroad = buf.out[b].n_road;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nroad; t += gridDim.x * blockDim.x) {
-    const uint4 e = buf.roadlist[(size_t)b * S + t];
+    const uint4 e = buf.roadlist[scan_base(b, S) + (unsigned)t];
     if (e.x == 0xffffffffu) continue;
     const int bin = e.x & 0xffff, k = e.x >> 16;
     if (marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w) && tab.dmax[bin] < e.z) atomicMax(&tab.dmax[bin], e.z);
@@ -941,7 +945,7 @@ __global__ void __launch_bounds__(256) k_best(DevBuffers buf, int S) {
   ScanTab& tab = buf.tab[b];
   const int nroad = buf.out[b].n_road;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nroad; t += gridDim.x * blockDim.x) {
-    const uint4 e = buf.roadlist[(size_t)b * S + t];
+    const uint4 e = buf.roadlist[scan_base(b, S) + (unsigned)t];
     if (e.x == 0xffffffffu) continue;
     const int bin = e.x & 0xffff, k = e.x >> 16;
     if (e.z != 0u && e.z == tab.dmax[bin] && marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w))
