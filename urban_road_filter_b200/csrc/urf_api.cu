@@ -84,7 +84,7 @@ __global__ void k_ring32(DevBuffers buf, int* dst, int S) {
 DevBuffers offset_view(const DevBuffers& a, int b0, int S, int T, int channels) {
   DevBuffers v = a;
   const size_t o = (size_t)b0 * S;
-  v.in += o; v.alpha_v += o; v.mark += o; v.ringid += o; v.sect += o; v.label += o; v.bpt += o; v.spt_rz += o; v.spt_i += o; v.srt_rz += o; v.srt_i += o;
+  v.in += o; v.alpha_v += o; v.mark += o; v.ringid += o; v.sect += o; v.label += o; v.bpt += o; v.spt += o; v.ssorted += o;
   v.az += o; v.d2 += o; v.blabel += o; v.bring += o; v.bidx += o; v.roadlist += o; v.order += o; v.sortbuf += 2 * o;
   v.Tf += (size_t)b0 * channels * kTStride; v.Tb += (size_t)b0 * channels * kTStride;
   v.lut += (size_t)b0 * (kElevBins + 1); v.firstidx += (size_t)b0 * (kElevBins + 1);
@@ -128,7 +128,7 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
     K("k_mark_exact", k_mark_exact<<<(B + 127) / 128, 128, 0, st>>>(buf, B));
   }
   K("k_scan_offsets", k_scan_offsets<<<B, 1024, 0, st>>>(buf, T));
-  K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, kScatterSmem, st>>>(buf, dp, S, T));
+  K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
   if (dp.star) {
     const int gbig = std::max(4, std::min(kSectKeys, 2048 / B)), gslow = std::max(2, std::min(kSectKeys, 512 / B));
     K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, S));
@@ -271,10 +271,8 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   TRY(dalloc(ctx, &b.sect, P));
   TRY(dalloc(ctx, &ctx->own_label, P));
   TRY(dalloc(ctx, &b.bpt, P));
-  TRY(dalloc(ctx, &b.spt_rz, P));
-  TRY(dalloc(ctx, &b.spt_i, P));
-  TRY(dalloc(ctx, &b.srt_rz, P));
-  TRY(dalloc(ctx, &b.srt_i, P));
+  TRY(dalloc(ctx, &b.spt, P));
+  TRY(dalloc(ctx, &b.ssorted, P));
   TRY(dalloc(ctx, &b.az, P));
   TRY(dalloc(ctx, &b.d2, P));
   TRY(dalloc(ctx, &b.blabel, P));
@@ -311,7 +309,6 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
     CKF(cudaMemcpyToSymbol(c_beam_yx, byx, sizeof(byx)));
     ctx->dp.Kfi = Kfi;
   }
-  CKF(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
   CKF(cudaFuncSetAttribute(k_star_sort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
   CKF(cudaFuncSetAttribute(k_sort_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingSmemKeys * sizeof(unsigned long long))));
   urf_default_params(&ctx->params);

@@ -80,10 +80,8 @@ struct DevBuffers {
   short* sect;           // [P]   star sector or -1
   int* label;            // [P]   output labels, input order
   float4* bpt;           // [P]   ring buckets (ring-major, input order inside a ring): x, y, z, input index bits
-  float2* spt_rz;        // [P]   sector buckets (unordered inside a sector): planar radius, z
-  int* spt_i;            // [P]   ... and the input index
-  float2* srt_rz;        // [P]   sector buckets sorted by (radius, input index)
-  int* srt_i;            // [P]
+  float4* spt;           // [P]   sector buckets (unordered inside a sector): r, z, input index bits, -
+  float4* ssorted;       // [P]   sector buckets sorted by r
   float* az;             // [P]   azimuth per bucket position
   float* d2;             // [P]   planar range per bucket position
   unsigned char* blabel; // [P]   label per bucket position

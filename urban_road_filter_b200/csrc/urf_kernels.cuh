@@ -367,27 +367,20 @@ __global__ void __launch_bounds__(1024) k_scan_offsets(DevBuffers buf, int T) {
 // push_back order of star_shaped_search.cpp:173).
 // Ring buckets are written coalesced: the warp first ranks its 512-point chunk by ring in shared memory, then walks the
 // chunk in ring order so that consecutive lanes write consecutive bucket slots.
-struct ScatterSmem {                                   // per warp (72 KB per CTA: dynamic shared memory)
-  unsigned goff[kRingKeys];                            // global bucket offset of this chunk, per ring
-  unsigned short lcnt[kRingKeys];                      // per-ring count, then exclusive local start
-  unsigned short perm[kChunk];                         // chunk-local point index in ring order
-  unsigned char pring[kChunk];                         // ring of that slot
-  float x[kChunk], y[kChunk], z[kChunk];               // the chunk's points (read again in ring order)
-};
-constexpr size_t kScatterSmem = sizeof(ScatterSmem) * kWarpsPerBlock;
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_scatter(DevBuffers buf, DevParams prm, int S, int T) {
-  extern __shared__ __align__(16) unsigned char s_scatter_raw[];
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf, DevParams prm, int S, int T) {
   const int b = blockIdx.y;
   const int n = buf.n[b];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int chunk = blockIdx.x * kWarpsPerBlock + warp;
+  __shared__ unsigned s_goff[kWarpsPerBlock][kRingKeys];          // global bucket offset of this chunk, per ring
+  __shared__ unsigned short s_lcnt[kWarpsPerBlock][kRingKeys];    // per-ring count, then exclusive local start
+  __shared__ unsigned short s_perm[kWarpsPerBlock][kChunk];       // chunk-local point index in ring order
+  __shared__ unsigned char s_pring[kWarpsPerBlock][kChunk];       // ring of that slot
   if (chunk * kChunk >= n) return;
-  ScatterSmem& sm = reinterpret_cast<ScatterSmem*>(s_scatter_raw)[warp];
-  unsigned* goff = sm.goff;
-  unsigned short* lcnt = sm.lcnt;
-  unsigned short* perm = sm.perm;
-  unsigned char* pring = sm.pring;
-  float *s_x = sm.x, *s_y = sm.y, *s_z = sm.z;
+  unsigned* goff = s_goff[warp];
+  unsigned short* lcnt = s_lcnt[warp];
+  unsigned short* perm = s_perm[warp];
+  unsigned char* pring = s_pring[warp];
   ScanTab& tab = buf.tab[b];
   const unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
   for (int t = lane; t < kRingKeys; t += 32) { goff[t] = row[t]; lcnt[t] = 0; }
@@ -412,8 +405,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_scatter(DevBuffers b
 #pragma unroll
     for (int u = 0; u < HALF; u++) {
       const int li = (h * HALF + u) * 32 + lane;
-      pp[u] = (ss[u] >= 0 || rr[u] >= 0) ? __ldg(&buf.in[g0 + li]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s_x[li] = pp[u].x; s_y[li] = pp[u].y; s_z[li] = pp[u].z;                          // read again in ring order below
+      pp[u] = ss[u] >= 0 ? __ldg(&buf.in[g0 + li]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < HALF; u++) {
@@ -434,9 +426,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_scatter(DevBuffers b
         int base = 0;
         if (lane == leader) base = atomicAdd(&tab.sect_cur[sec], __popc(peers));
         base = __shfl_sync(peers, base, leader);
-        const unsigned d = gb + (unsigned)(base + __popc(peers & lt));
-        buf.spt_rz[d] = make_float2(star_radius(pp[u].x, pp[u].y), pp[u].z);
-        buf.spt_i[d] = i;
+        buf.spt[gb + (unsigned)(base + __popc(peers & lt))] = make_float4(star_radius(pp[u].x, pp[u].y), pp[u].z, __int_as_float(i), 0.f);
       }
       __syncwarp();
     }
@@ -469,8 +459,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_scatter(DevBuffers b
   __syncwarp();
   for (int t = lane; t < total; t += 32) {
     const int li = perm[t], ring = pring[t];
+    const float4 p = __ldg(&buf.in[g0 + li]);
     const unsigned dst = gb + goff[ring] + (unsigned)(t - lcnt[ring]);
-    buf.bpt[dst] = make_float4(s_x[li], s_y[li], s_z[li], __int_as_float(chunk * kChunk + li));
+    buf.bpt[dst] = make_float4(p.x, p.y, p.z, __int_as_float(chunk * kChunk + li));
     buf.bring[dst] = (unsigned char)ring;
     buf.bidx[dst] = chunk * kChunk + li;
   }
@@ -490,8 +481,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k_scatter(DevBuffers b
 constexpr int kWarpCap = 1024, kCtaCap = 8192;
 
 template <int EPL, int WARPS>
-__device__ __forceinline__ bool bitonic_sector(const float2* __restrict__ src, const int* __restrict__ src_i,
-                                               float2* __restrict__ dst, int* __restrict__ dst_i, int n, int tid,
+__device__ __forceinline__ bool bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid,
                                                unsigned* s_xk, unsigned* s_xe) {
   constexpr int THREADS = WARPS * 32;                // sorts up to THREADS * EPL elements
   const int lane = tid & 31;
@@ -568,7 +558,6 @@ __device__ __forceinline__ bool bitonic_sector(const float2* __restrict__ src, c
     const unsigned prev = r > 0 ? key[r - 1] : prev0;
     if (e < n) {
       dst[e] = src[el[r]];
-      dst_i[e] = src_i[el[r]];
       if (e > 0 && prev == key[r]) tie = true;
     }
   }
@@ -582,12 +571,9 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, int S) {
   ScanTab& tab = buf.tab[b];
   const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
   if (n <= 0) return;
-  const unsigned o = scan_base(b, S) + (unsigned)base;
-  const float2* src = buf.spt_rz + o;
-  const int* src_i = buf.spt_i + o;
-  float2* dst = buf.srt_rz + o;
-  int* dst_i = buf.srt_i + o;
-  if (n == 1) { if (lane == 0) { dst[0] = src[0]; dst_i[0] = src_i[0]; } return; }
+  const float4* src = buf.spt + (size_t)b * S + base;
+  float4* dst = buf.ssorted + (size_t)b * S + base;
+  if (n == 1) { if (lane == 0) dst[0] = src[0]; return; }
   if (n > kWarpCap) {                                                   // hand over to the CTA sort / the fallback
     if (lane == 0) {
       if (n <= kCtaCap) tab.biglist[atomicAdd(&tab.nbig, 1)] = (unsigned short)s;
@@ -596,10 +582,10 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, int S) {
     return;
   }
   bool tie;
-  if (n <= 128) tie = bitonic_sector<4, 1>(src, src_i, dst, dst_i, n, lane, nullptr, nullptr);
-  else if (n <= 256) tie = bitonic_sector<8, 1>(src, src_i, dst, dst_i, n, lane, nullptr, nullptr);
-  else if (n <= 512) tie = bitonic_sector<16, 1>(src, src_i, dst, dst_i, n, lane, nullptr, nullptr);
-  else tie = bitonic_sector<32, 1>(src, src_i, dst, dst_i, n, lane, nullptr, nullptr);
+  if (n <= 128) tie = bitonic_sector<4, 1>(src, dst, n, lane, nullptr, nullptr);
+  else if (n <= 256) tie = bitonic_sector<8, 1>(src, dst, n, lane, nullptr, nullptr);
+  else if (n <= 512) tie = bitonic_sector<16, 1>(src, dst, n, lane, nullptr, nullptr);
+  else tie = bitonic_sector<32, 1>(src, dst, n, lane, nullptr, nullptr);
   if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;   // sets F_TIE_SECTOR there
 }
 
@@ -615,16 +601,13 @@ __global__ void __launch_bounds__(256) k_star_sort_cta(DevBuffers buf, int S) {
   for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
     const int s = tab.biglist[w];
     const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
-    const unsigned o = scan_base(b, S) + (unsigned)base;
-    const float2* src = buf.spt_rz + o;
-    const int* src_i = buf.spt_i + o;
-    float2* dst = buf.srt_rz + o;
-    int* dst_i = buf.srt_i + o;
+    const float4* src = buf.spt + (size_t)b * S + base;
+    float4* dst = buf.ssorted + (size_t)b * S + base;
     if (threadIdx.x == 0) s_tie = 0;
     bool tie;
-    if (n <= 2048) tie = bitonic_sector<8, 8>(src, src_i, dst, dst_i, n, threadIdx.x, s_xk, s_xe);
-    else if (n <= 4096) tie = bitonic_sector<16, 8>(src, src_i, dst, dst_i, n, threadIdx.x, s_xk, s_xe);
-    else tie = bitonic_sector<32, 8>(src, src_i, dst, dst_i, n, threadIdx.x, s_xk, s_xe);
+    if (n <= 2048) tie = bitonic_sector<8, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
+    else if (n <= 4096) tie = bitonic_sector<16, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
+    else tie = bitonic_sector<32, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
     __syncthreads();
     if (tie) s_tie = 1;
     __syncthreads();
@@ -645,15 +628,12 @@ __global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S) {
     const int s = tab.slowlist[w];
     const int base = tab.sect_start[s];
     const int n = tab.sect_start[s + 1] - base;
-    const unsigned o = scan_base(b, S) + (unsigned)base;
-    const float2* src = buf.spt_rz + o;
-    const int* src_i = buf.spt_i + o;
-    float2* dst = buf.srt_rz + o;
-    int* dst_i = buf.srt_i + o;
+    const float4* src = buf.spt + (size_t)b * S + base;
+    float4* dst = buf.ssorted + (size_t)b * S + base;
     const int npad = next_pow2(n);
     unsigned long long* keys = npad <= kStarSmemKeys ? s_keys : buf.sortbuf + 2 * ((size_t)b * S + base);
     for (int t = threadIdx.x; t < npad; t += blockDim.x)
-      keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)src_i[t]) : ~0ull;
+      keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
     __syncthreads();
     cta_bitonic(keys, npad);
     // keys hold (radius bits, input index) ascending: rebuild the records (z comes from the input record of that index)
@@ -662,8 +642,7 @@ __global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S) {
       const unsigned long long k = keys[t];
       if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
       const int idx = (int)(unsigned)k;
-      dst[t] = make_float2(bitsf((unsigned)(k >> 32)), buf.in[scan_base(b, S) + (unsigned)idx].z);
-      dst_i[t] = idx;
+      dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
     }
     if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
     __syncthreads();
@@ -685,7 +664,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
   const ScanTab& tab = buf.tab[b];
   int base = 0, n = 0;
   if (s < kSectKeys) { base = tab.sect_start[s]; n = tab.sect_start[s + 1] - base; }
-  const float2* all = buf.srt_rz + scan_base(b, S);
+  const float4* all = buf.ssorted + (size_t)b * S;
   StarState st;
   star_init(st, 0.f, 0.f);
   bool done = n <= 1;                                                   // star_shaped_search.cpp:112
@@ -696,7 +675,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
     // stage tile [t0, t0 + 32) of all 32 sector rows: 8 rows at a time so that the 16 loads of a group are in flight
     // together (one L2 round trip per group instead of one per row)
     for (int q0 = 0; q0 < 32; q0 += 8) {
-      float2 p[8], pp[8];
+      float4 p[8], pp[8];
       bool ok[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
@@ -730,7 +709,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
     __syncwarp();
     if (__all_sync(0xffffffffu, done)) break;
   }
-  if (hit >= 0) buf.mark[scan_base(b, S) + (unsigned)buf.srt_i[scan_base(b, S) + (unsigned)(base + hit)]] = 2;   // star_shaped_search.cpp:146
+  if (hit >= 0) buf.mark[scan_base(b, S) + (unsigned)__float_as_int(all[base + hit].z)] = 2;   // star_shaped_search.cpp:146
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
