@@ -46,29 +46,59 @@ def bench_params(shape_key: str):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own implementation (oracle/_ref = unmodified reference sources; else the oracle port)
-def _cpu_worker(args):
-    shape_key, seed, repeat, use_ref = args
+# CPU arm: the reference's own implementation (oracle/_ref = unmodified reference sources; else the oracle port).
+# One single-threaded process per host core (the reference is single-threaded by construction, src/main.cpp:54), each
+# with its own scan; the pool and the scans persist across steps so that a step only contains filtered() calls.
+_W = {}
+
+
+def _cpu_init(shape_key, seed0, use_ref, counter):
     sys.path.insert(0, ROOT)
     from oracle.pyoracle import PortOracle, RefOracle
-    pts = make_scan(shape_key, seed)
-    prm = bench_params(shape_key)
-    orc = RefOracle() if use_ref else PortOracle()
-    orc.time(pts, prm, 1)                      # untimed first call: page-faults the reference's big allocations
-    return orc.time(pts, prm, repeat), repeat
+    with counter.get_lock():
+        wid = counter.value
+        counter.value += 1
+    _W["pts"] = make_scan(shape_key, seed0 + wid)
+    _W["prm"] = bench_params(shape_key)
+    _W["orc"] = RefOracle() if use_ref else PortOracle()
+    _W["orc"].time(_W["pts"], _W["prm"], 1)          # untimed first call: page-faults the reference's big allocations
+
+
+def _cpu_step(repeat):
+    return _W["orc"].time(_W["pts"], _W["prm"], repeat), repeat
+
+
+class CpuReference:
+    def __init__(self, shape_key: str, workers: int, seed0: int = 10_000):
+        import multiprocessing as mp
+        from oracle.pyoracle import RefOracle
+        self.use_ref = RefOracle.available()
+        self.workers = workers
+        ctx = mp.get_context("fork" if not _cuda_initialised() else "spawn")
+        self.pool = ctx.Pool(workers, initializer=_cpu_init, initargs=(shape_key, seed0, self.use_ref, ctx.Value("i", 0)))
+        self.pool.map(_cpu_step, [0] * workers)          # make sure every worker is initialised
+
+    @property
+    def kind(self) -> str:
+        return "reference" if self.use_ref else "port"
+
+    def step(self, repeat: int = 1):
+        """Aggregate scans/s of all workers running `repeat` scans each at the same time, and the median ms per scan."""
+        res = self.pool.map(_cpu_step, [repeat] * self.workers, chunksize=1)
+        return sum(r / s for s, r in res), 1e3 * statistics.median(s / r for s, r in res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def cpu_reference_rate(shape_key: str, workers: int, repeat: int, seed0: int = 10_000):
-    """Aggregate scans/s of `workers` processes, each running the single-threaded reference on its own scan."""
-    import multiprocessing as mp
-    from oracle.pyoracle import RefOracle
-    use_ref = RefOracle.available()
-    ctx = mp.get_context("fork" if "torch" not in sys.modules or not _cuda_initialised() else "spawn")
-    with ctx.Pool(workers) as pool:
-        res = pool.map(_cpu_worker, [(shape_key, seed0 + w, repeat, use_ref) for w in range(workers)])
-    rate = sum(r / s for s, r in res)
-    per_scan_ms = 1e3 * statistics.median(s / r for s, r in res)
-    return rate, per_scan_ms, ("reference" if use_ref else "port")
+    ref = CpuReference(shape_key, workers, seed0)
+    try:
+        rate, per_scan_ms = ref.step(repeat)
+    finally:
+        ref.close()
+    return rate, per_scan_ms, ref.kind
 
 
 def _cuda_initialised() -> bool:
@@ -184,14 +214,14 @@ def run_reference_arm(args):
         return 0            # the reference arm is a host-CPU measurement: rank 0 alone runs and prints it
     cores = usable_cores(args.shape)
     n = SHAPES[args.shape].rings * SHAPES[args.shape].cols
+    ref = CpuReference(args.shape, cores, seed0=20_000)
+    kind = ref.kind
     for _ in range(args.warmup):
-        cpu_reference_rate(args.shape, cores, 1)
+        ref.step(1)
     t0 = time.perf_counter()
-    rates, kind = [], "reference"
-    for k in range(args.steps):
-        r, _, kind = cpu_reference_rate(args.shape, cores, 1, seed0=20_000 + 1000 * k)
-        rates.append(r)
+    rates = [ref.step(1)[0] for _ in range(args.steps)]
     wall = time.perf_counter() - t0
+    ref.close()
     value = statistics.median(rates)
     line = {
         "impl": "reference", "metric": "scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": args.gpus,

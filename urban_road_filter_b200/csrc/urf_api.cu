@@ -491,7 +491,7 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
   cudaStream_t st = ctx->stream;
   // Software pipeline over chunks of scans: H2D of chunk c+1 (s_in), kernels of chunk c (stream) and D2H of chunk c-1
   // (s_out) overlap; scans are independent, every chunk owns its slice of every buffer.
-  const int chunk = batch >= 16 ? (batch + 7) / 8 : batch;
+  const int chunk = batch >= 16 ? std::max(4, (batch + 15) / 16) : batch;     // short fill / drain of the pipeline
   const int nchunks = (batch + chunk - 1) / chunk;
   while ((int)ctx->ev_in.size() < nchunks) {
     cudaEvent_t a, c;
