@@ -975,6 +975,7 @@ __global__ void __launch_bounds__(384) k_verts(DevBuffers buf, int S) {
     out.vert[slot][3] = tab.cutbest[i] != ~0ull ? 1.0f : 0.0f;          // redPoints, :320,348
   }
   if (i == 0) out.n_vert = total;
+  if (i >= total && i < URF_MAX_VERTS) { out.vert[i][0] = 0.f; out.vert[i][1] = 0.f; out.vert[i][2] = 0.f; out.vert[i][3] = 0.f; }   // defined tail
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
