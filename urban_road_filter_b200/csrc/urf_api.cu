@@ -138,7 +138,7 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   }
   K("k_ring_detect", k_ring_detect<8><<<gpts, 256, 0, st>>>(buf, dp, S));   // 8 CTAs/SM (32 registers): measured 2 % faster than 6, 25 % faster than 4
   K("k_tab1", k_tab1<<<dim3((dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
-  K("k_reach", k_reach<<<dim3((2 * kDegBins * dp.channels + 255) / 256, B), 256, 0, st>>>(buf, dp));
+  K("k_reach", k_reach<<<dim3((2 * kDegBins + 7) / 8, B), 256, 0, st>>>(buf, dp));
   K("k_tab2", k_tab2<<<dim3((2 * dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
   K("k_label", k_label<<<gpts, 256, 0, st>>>(buf, dp, S));
   const dim3 groad(std::max(1, std::min((S + 255) / 256, 96)), B);        // grid-stride over the compact road list

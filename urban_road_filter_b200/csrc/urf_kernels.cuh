@@ -823,21 +823,27 @@ __global__ void __launch_bounds__(256) k_tab1(DevBuffers buf, DevParams prm) {
   }
 }
 
-// k_reach: one thread per (direction, window start i, ring k) cell: does ring k hold a curb point inside window i?
-// reach[dir][i] = the first such ring (blind_spots.cpp:107-171 / :216-280 stop at it).
+// k_reach: one warp per (direction, window start i): lanes test 32 rings at a time whether ring k holds a curb point
+// inside window i and stop at the first blocked ring — reach[dir][i] (blind_spots.cpp:107-171 / :216-280 stop there too).
 __global__ void __launch_bounds__(256) k_reach(DevBuffers buf, DevParams prm) {
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
   const int R = out.n_rings;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * kDegBins * R) return;
-  const int k = c % R, di = c / R, dir = di / kDegBins, i = di % kDegBins;
-  if (dir == 0 ? i > prm.fwd_last : i < prm.bwd_first) return;
-  if (tab.reach[dir][i] <= k) return;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id();
+  if (w >= 2 * kDegBins || R <= 0) return;
+  const int dir = w / kDegBins, i = w % kDegBins;
+  if (dir == 0 ? i > prm.fwd_last : i < prm.bwd_first) return;          // outside the loop range: never accepted anyway
   const size_t nb = (size_t)prm.channels * kDegBins;
   CurbView cv{buf.cmin + (size_t)b * nb, buf.cmax + (size_t)b * nb, buf.ne + (size_t)b * prm.channels * (kDegBins + 1)};
-  if (window_blocked(prm, cv, tab.A[k], dir, i, k)) atomicMin(&tab.reach[dir][i], k);
+  int reach = R;
+  for (int k0 = 0; k0 < R; k0 += 32) {
+    const int k = k0 + lane;
+    const bool blocked = k < R && window_blocked(prm, cv, tab.A[k], dir, i, k);
+    const unsigned bal = __ballot_sync(0xffffffffu, blocked);
+    if (bal) { reach = k0 + __ffs(bal) - 1; break; }
+  }
+  if (lane == 0) tab.reach[dir][i] = reach;
 }
 
 // k_tab2: one warp per (ring, direction) builds a row of a threshold table with a warp max/min scan over the 361
