@@ -63,6 +63,26 @@ int main(int argc, char** argv) {
     b += sweep1("atanf", 0, 0x100000000ull, stride, threads, urfm::atanf_glibc, (float (*)(float))atanf, &c);
     printf("atanf checked=%llu mismatches=%llu\n", (unsigned long long)c, (unsigned long long)b);
     rc |= b != 0;
+    c = b = 0;
+    {   // div_pi((double)f) against the IEEE double quotient, all 64 bits, every `stride`-th finite float
+      std::atomic<uint64_t> bad{0}, cnt{0};
+      std::vector<std::thread> th;
+      for (int t = 0; t < threads; t++) th.emplace_back([&, t]() {
+        uint64_t bb = 0, cc = 0;
+        for (uint64_t u = (uint64_t)t * stride; u < 0x100000000ull; u += stride * threads) {
+          const float f = fl((uint32_t)u);
+          if (!std::isfinite(f)) continue;
+          const double mine = urfm::div_pi((double)f), ref = (double)f / URF_PI_D;
+          if (memcmp(&mine, &ref, 8)) { if (bb < 3) fprintf(stderr, "div_pi(%a) = %a, IEEE %a\n", (double)f, mine, ref); bb++; }
+          cc++;
+        }
+        bad += bb; cnt += cc;
+      });
+      for (auto& x : th) x.join();
+      b += bad; c += cnt;
+    }
+    printf("div_pi checked=%llu mismatches=%llu\n", (unsigned long long)c, (unsigned long long)b);
+    rc |= b != 0;
   }
   {
     std::atomic<uint64_t> bad{0}, cnt{0};

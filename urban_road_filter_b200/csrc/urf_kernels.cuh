@@ -716,62 +716,101 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
 // k_ring_detect: one thread per ring-bucket position. Planar range + azimuth (lidar_segmentation.cpp:245-274), the
 // x-zero test for which this point is the middle point p2 (x_zero_method.cpp:30-67), the z-zero test centred on it
 // (z_zero_method.cpp:21-72), the curb aggregates blindSpots needs and maxDistance per ring. The CTA stages its 256
-// bucket positions plus a halo of curb_points on each side in shared memory (plain global reads when curb_points
-// exceeds kHalo).
+// bucket positions plus a halo of curb_points on each side in shared memory as three coordinate arrays (plain global
+// reads when curb_points exceeds kHalo). Both detectors are a cheap height gate followed by an expensive angle test
+// (four double square roots, a double divide, acosf); about one point in eight passes a gate, scattered over most warps,
+// so every thread evaluates only the gates and the CTA compacts the survivors into a work list that full warps then run
+// the angle tests over (x-zero items from thread 0 upwards, z-zero items from thread 255 downwards).
 constexpr int kHalo = 32;
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
   const int N = out.n_order;
-  __shared__ float4 s_tile[256 + 2 * kHalo];
+  __shared__ float s_x[256 + 2 * kHalo], s_y[256 + 2 * kHalo], s_z[256 + 2 * kHalo];
   __shared__ int s_rs[kRingKeys + 1];                     // ring_start of the rings this CTA touches, indexed by ring - k_lo
-  __shared__ int s_klo;
+  __shared__ int s_base[256];                             // ring_start of each thread's ring
+  __shared__ unsigned short s_item[512];                  // x-zero work items grow from 0 up, z-zero items from 511 down
+  __shared__ unsigned char s_hit[2][256];
+  __shared__ int s_klo, s_nx, s_nz;
   const int p0 = blockIdx.x * blockDim.x;
   if (p0 >= N) return;
-  if (threadIdx.x < 32) {                                 // rings are contiguous in bucket order: first .. last ring of the CTA
+  const int tid = threadIdx.x;
+  if (tid < 32) {                                         // rings are contiguous in bucket order: first .. last ring of the CTA
     const int k_lo = buf.bring[scan_base(b, S) + (unsigned)p0], k_hi = buf.bring[scan_base(b, S) + (unsigned)min(p0 + 255, N - 1)];
-    if (threadIdx.x == 0) s_klo = k_lo;
-    for (int t = threadIdx.x; t <= k_hi - k_lo + 1; t += 32) s_rs[t] = out.ring_start[k_lo + t];
+    if (tid == 0) { s_klo = k_lo; s_nx = 0; s_nz = 0; }
+    for (int t = tid; t <= k_hi - k_lo + 1; t += 32) s_rs[t] = out.ring_start[k_lo + t];
   }
   const unsigned gb = scan_base(b, S);
   const float4* bucket = buf.bpt + gb;
   const bool tiled = prm.curbPoints <= kHalo;
+  const int p = p0 + tid;
+  const bool act = p < N;
+  float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) me = bucket[p];
   if (tiled) {                                            // one bucket record per thread + a halo record for the first 64 threads
-    const int pc = p0 + (int)threadIdx.x;
-    if (pc < N) s_tile[kHalo + threadIdx.x] = bucket[pc];
-    if (threadIdx.x < 2 * kHalo) {
-      const int ph = threadIdx.x < kHalo ? p0 - kHalo + (int)threadIdx.x : p0 + 256 + (int)threadIdx.x - kHalo;
-      if (ph >= 0 && ph < N) s_tile[threadIdx.x < kHalo ? threadIdx.x : 256 + threadIdx.x] = bucket[ph];
+    s_x[kHalo + tid] = me.x; s_y[kHalo + tid] = me.y; s_z[kHalo + tid] = me.z;
+    if (tid < 2 * kHalo) {
+      const int ph = tid < kHalo ? p0 - kHalo + tid : p0 + 256 + tid - kHalo;
+      const int sh = tid < kHalo ? tid : 256 + tid;
+      if (ph >= 0 && ph < N) { const float4 h = bucket[ph]; s_x[sh] = h.x; s_y[sh] = h.y; s_z[sh] = h.z; }
     }
+    s_hit[0][tid] = 0; s_hit[1][tid] = 0;
   }
   __syncthreads();
-  const int p = p0 + threadIdx.x;
-  const bool act = p < N;
-  int k = -1;
+  int k = -1, lab = 0;
   unsigned dbits = 0;
+  float az = 0.f;
+  bool need_x = false, need_z = false;
   if (act) {
     k = buf.bring[gb + (unsigned)p];
     const int base = s_rs[k - s_klo], n = s_rs[k - s_klo + 1] - base, m = p - base;
-    const float4 me = tiled ? s_tile[threadIdx.x + kHalo] : bucket[p];
     const int idx = __float_as_int(me.w);
-    float d, az;
+    float d;
     planar_az(me.x, me.y, &d, &az);                                     // lidar_segmentation.cpp:245-269
     buf.az[gb + (unsigned)p] = az;
     buf.d2[gb + (unsigned)p] = d;
     dbits = fbits(d);
-    int lab = prm.star ? buf.mark[gb + (unsigned)idx] : 0;             // :241-242
-    // ring[q] must address bucket position base + q: through the shared tile, or straight from global memory (two code
-    // paths so that the compiler keeps the address space of the loads)
+    lab = prm.star ? buf.mark[gb + (unsigned)idx] : 0;                  // :241-242
     if (tiled) {
-      const float4* ring = s_tile + (base - (p0 - kHalo));
-      if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;   // x_zero_method.cpp:66
-      if (prm.z_zero && lab != 2 && (prm.curbPoints == 5 ? zzero_mark_t<5>(prm, ring, n, m) : zzero_mark_t<0>(prm, ring, n, m))) lab = 2;   // z_zero_method.cpp:71
-    } else {
+      s_base[tid] = base;
+      const int off = base - (p0 - kHalo);                              // ring-local index q lives at tile slot off + q
+      const RingSoA ring{s_x + off, s_y + off, s_z + off};
+      need_x = prm.x_zero && lab != 2 && xzero_pre(prm, ring, n, m);
+      need_z = prm.z_zero && lab != 2 && (prm.curbPoints == 5 ? zzero_pre_t<5>(prm, ring, n, m) : zzero_pre_t<0>(prm, ring, n, m));
+    } else {                                                            // huge curb_points: straight from global memory
       const float4* ring = bucket + base;
-      if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;
-      if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, n, m)) lab = 2;
+      if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;   // x_zero_method.cpp:66
+      if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, n, m)) lab = 2;             // z_zero_method.cpp:71
     }
+  }
+  if (tiled) {
+    const unsigned bx = __ballot_sync(0xffffffffu, need_x), bz = __ballot_sync(0xffffffffu, need_z);
+    const unsigned lt = (1u << lane_id()) - 1u;
+    int ox = 0, oz = 0;
+    if (lane_id() == 0) {
+      if (bx) ox = atomicAdd(&s_nx, __popc(bx));
+      if (bz) oz = atomicAdd(&s_nz, __popc(bz));
+    }
+    ox = __shfl_sync(0xffffffffu, ox, 0); oz = __shfl_sync(0xffffffffu, oz, 0);
+    if (need_x) s_item[ox + __popc(bx & lt)] = (unsigned short)tid;
+    if (need_z) s_item[511 - (oz + __popc(bz & lt))] = (unsigned short)tid;
+    __syncthreads();
+    const int nx = s_nx, nz = s_nz;
+    for (int it = tid; it < nx; it += 256) {                            // x-zero angle tests, x_zero_method.cpp:35-61
+      const int t = s_item[it], base = s_base[t], off = base - (p0 - kHalo);
+      const RingSoA ring{s_x + off, s_y + off, s_z + off};
+      if (xzero_post(prm, ring, p0 + t - base, buf.newY)) s_hit[0][t] = 1;
+    }
+    for (int it = 255 - tid; it < nz; it += 256) {                      // z-zero angle tests, z_zero_method.cpp:23-66
+      const int t = s_item[511 - it], base = s_base[t], off = base - (p0 - kHalo);
+      const RingSoA ring{s_x + off, s_y + off, s_z + off};
+      if (prm.curbPoints == 5 ? zzero_post_t<5>(prm, ring, p0 + t - base) : zzero_post_t<0>(prm, ring, p0 + t - base)) s_hit[1][t] = 1;
+    }
+    __syncthreads();
+    if (act && (s_hit[0][tid] | s_hit[1][tid])) lab = 2;               // x_zero_method.cpp:66, z_zero_method.cpp:71
+  }
+  if (act) {
     buf.blabel[gb + (unsigned)p] = (unsigned char)lab;
     if (lab == 2 && az >= 0.0f) {            // curb aggregates per (ring, integer-degree bin); NaN azimuths fall out
       const unsigned o = ((unsigned)b * (unsigned)prm.channels + (unsigned)k) * kDegBins + (unsigned)deg_bin(az);

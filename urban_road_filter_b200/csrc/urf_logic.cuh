@@ -27,8 +27,9 @@ URF_HD unsigned fbits(float f) { return (unsigned)URF_F2I(f); }
 URF_HD float bitsf(unsigned u) { return URF_I2F((int32_t)u); }
 URF_HD double dsq(float a) { return URF_DMUL((double)a, (double)a); }      // pow(float, 2): exact in double
 
-// tail of every `acos(..) * 180 / M_PI` of the reference: float multiply, then double divide
-URF_HD double deg_d(float rad) { return URF_DDIV((double)URF_FMUL(rad, 180.0f), URF_PI_D); }
+// tail of every `acos(..) * 180 / M_PI` of the reference: float multiply, then double divide (urfm::div_pi: the same
+// correctly rounded quotient from two FMAs)
+URF_HD double deg_d(float rad) { return urfm::div_pi((double)URF_FMUL(rad, 180.0f)); }
 
 URF_HD float clamp_unit(float b) {   // lidar_segmentation.cpp:154-157 (NaN passes through)
   if (b < -1.0f) return -1.0f;
@@ -126,54 +127,81 @@ URF_HD bool registration_violation(const float* angle, const int* regidx, const 
   return l2 < channels;                    // uncovered and room left: it would have registered
 }
 
-// x-zero test with local index m as the middle point p2 = j + cp/2 (x_zero_method.cpp:30-67). ring[q] = (x, y, z, -).
-URF_HD bool xzero_mark(const DevParams& prm, const float4* ring, int n, int m, const float* newY) {
+// A ring's points in ring order, as the two detectors read them: array-of-float4 (global memory, host model) or three
+// separate coordinate arrays (the shared-memory tile of k_ring_detect). q = local index inside the ring.
+struct RingAoS {
+  const float4* p;
+  URF_HDM float x(int q) const { return p[q].x; }
+  URF_HDM float y(int q) const { return p[q].y; }
+  URF_HDM float z(int q) const { return p[q].z; }
+};
+struct RingSoA {
+  const float *px, *py, *pz;
+  URF_HDM float x(int q) const { return px[q]; }
+  URF_HDM float y(int q) const { return py[q]; }
+  URF_HDM float z(int q) const { return pz[q]; }
+};
+
+// x-zero test with local index m as the middle point p2 = j + cp/2 (x_zero_method.cpp:30-67), split in two: the index
+// range + height gate (cheap, float only; false for most points) and the triangle-angle test behind it. The kernel runs
+// the second half only for the points that pass the first (compacted per CTA); xzero_mark is both, for the host model.
+template <class RV>
+URF_HD bool xzero_pre(const DevParams& prm, const RV& ring, int n, int m) {
   const int cp = prm.curbPoints;
   const int j = m - cp / 2;
   if (!(j >= cp && j <= (n - 1) - cp)) return false;
-  const int p3 = j + cp;
-  const float4 a = ring[j], c = ring[p3];
-  const float z = ring[m].z;
-  const bool h = (fabsf(URF_FSUB(a.z, z)) >= prm.curbHeight || fabsf(URF_FSUB(c.z, z)) >= prm.curbHeight) &&
-                 (double)fabsf(URF_FSUB(a.z, c.z)) >= 0.05;                                                  // :62-64
-  if (!h) return false;
-  const float dd = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(c.x, a.x)), dsq(URF_FSUB(c.y, a.y)))));            // :35-37
+  const float az = ring.z(j), cz = ring.z(j + cp), z = ring.z(m);
+  return (fabsf(URF_FSUB(az, z)) >= prm.curbHeight || fabsf(URF_FSUB(cz, z)) >= prm.curbHeight) &&
+         (double)fabsf(URF_FSUB(az, cz)) >= 0.05;                                                             // :62-64
+}
+template <class RV>
+URF_HD bool xzero_post(const DevParams& prm, const RV& ring, int m, const float* newY) {
+  const int cp = prm.curbPoints;
+  const int j = m - cp / 2, p3 = j + cp;
+  const float az = ring.z(j), cz = ring.z(p3), z = ring.z(m);
+  const float dd = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(ring.x(p3), ring.x(j))), dsq(URF_FSUB(ring.y(p3), ring.y(j))))));   // :35-37
   if (!((double)dd < 5.0)) return false;                                                                      // :40
   const float yj = newY[j], y2 = newY[m], y3 = newY[p3];
-  const float x1 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y2, yj)), dsq(URF_FSUB(z, a.z)))));               // :42-44
-  const float x2 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y3, y2)), dsq(URF_FSUB(c.z, z)))));               // :45-47
-  const float x3 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y3, yj)), dsq(URF_FSUB(c.z, a.z)))));             // :48-50
+  const float x1 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y2, yj)), dsq(URF_FSUB(z, az)))));                // :42-44
+  const float x2 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y3, y2)), dsq(URF_FSUB(cz, z)))));                // :45-47
+  const float x3 = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(y3, yj)), dsq(URF_FSUB(cz, az)))));               // :48-50
   const double num = URF_DSUB(URF_DSUB(dsq(x3), dsq(x1)), dsq(x2));
   const float den = URF_FMUL(URF_FMUL(-2.0f, x1), x2);
   const float bk = clamp_unit(URF_D2F(URF_DDIV(num, (double)den)));                                           // :52-56
   const float al = URF_D2F(deg_d(urfm::acosf_glibc(bk)));                                                     // :58
   return al <= prm.angleFilter1;                                                                              // :61
 }
+URF_HD bool xzero_mark(const DevParams& prm, const float4* ring, int n, int m, const float* newY) {
+  const RingAoS rv{ring};
+  return xzero_pre(prm, rv, n, m) && xzero_post(prm, rv, m, newY);
+}
 
-// z-zero test centred on local index m (z_zero_method.cpp:21-72). CP > 0: curb_points known at compile time (loops
-// unroll); CP == 0: taken from the parameters. Same arithmetic either way.
-template <int CP>
-URF_HD bool zzero_mark_t(const DevParams& prm, const float4* ring, int n, int m) {
+// z-zero test centred on local index m (z_zero_method.cpp:21-72), split the same way. CP > 0: curb_points known at
+// compile time (loops unroll); CP == 0: taken from the parameters. Same arithmetic either way.
+template <int CP, class RV>
+URF_HD bool zzero_pre_t(const DevParams& prm, const RV& ring, int n, int m) {
   const int cp = CP > 0 ? CP : prm.curbPoints;
   if (!(m >= cp && m <= (n - 1) - cp)) return false;
-  const float4 me = ring[m];
-  const float az0 = fabsf(me.z);
+  const float az0 = fabsf(ring.z(m));
   float max1 = az0, max2 = az0;
 #pragma unroll
-  for (int u = 1; u <= cp; u++) { const float v = fabsf(ring[m - u].z); if (v > max1) max1 = v; }            // :38-40 (k = j-1 .. j-cp)
+  for (int u = 1; u <= cp; u++) { const float v = fabsf(ring.z(m - u)); if (v > max1) max1 = v; }            // :38-40 (k = j-1 .. j-cp)
 #pragma unroll
-  for (int u = 1; u <= cp; u++) { const float v = fabsf(ring[m + u].z); if (v > max2) max2 = v; }            // :47-49 (k = j+1 .. j+cp)
-  const bool h = (URF_FSUB(max1, az0) >= prm.curbHeight || URF_FSUB(max2, az0) >= prm.curbHeight) &&
-                 (double)fabsf(URF_FSUB(max1, max2)) >= 0.05;                                                 // :67-69
-  if (!h) return false;
-  const float4 lo = ring[m - cp], hi = ring[m + cp];
-  const float dd = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(hi.x, lo.x)), dsq(URF_FSUB(hi.y, lo.y)))));        // :23-25
+  for (int u = 1; u <= cp; u++) { const float v = fabsf(ring.z(m + u)); if (v > max2) max2 = v; }            // :47-49 (k = j+1 .. j+cp)
+  return (URF_FSUB(max1, az0) >= prm.curbHeight || URF_FSUB(max2, az0) >= prm.curbHeight) &&
+         (double)fabsf(URF_FSUB(max1, max2)) >= 0.05;                                                         // :67-69
+}
+template <int CP, class RV>
+URF_HD bool zzero_post_t(const DevParams& prm, const RV& ring, int m) {
+  const int cp = CP > 0 ? CP : prm.curbPoints;
+  const float dd = URF_D2F(URF_DSQRT(URF_DADD(dsq(URF_FSUB(ring.x(m + cp), ring.x(m - cp))), dsq(URF_FSUB(ring.y(m + cp), ring.y(m - cp))))));   // :23-25
   if (!((double)dd < 5.0)) return false;                                                                      // :28
+  const float mx = ring.x(m), my = ring.y(m);
   float va1 = 0.f, va2 = 0.f, vb1 = 0.f, vb2 = 0.f;
 #pragma unroll
-  for (int u = 1; u <= cp; u++) { const float4 o = ring[m - u]; va1 = URF_FADD(va1, URF_FSUB(o.x, me.x)); va2 = URF_FADD(va2, URF_FSUB(o.y, me.y)); }   // :35-37, same order
+  for (int u = 1; u <= cp; u++) { va1 = URF_FADD(va1, URF_FSUB(ring.x(m - u), mx)); va2 = URF_FADD(va2, URF_FSUB(ring.y(m - u), my)); }   // :35-37, same order
 #pragma unroll
-  for (int u = 1; u <= cp; u++) { const float4 o = ring[m + u]; vb1 = URF_FADD(vb1, URF_FSUB(o.x, me.x)); vb2 = URF_FADD(vb2, URF_FSUB(o.y, me.y)); }   // :44-46
+  for (int u = 1; u <= cp; u++) { vb1 = URF_FADD(vb1, URF_FSUB(ring.x(m + u), mx)); vb2 = URF_FADD(vb2, URF_FSUB(ring.y(m + u), my)); }   // :44-46
   const float sc = URF_FDIV(1.0f, (float)cp);
   va1 = URF_FMUL(sc, va1); va2 = URF_FMUL(sc, va2); vb1 = URF_FMUL(sc, vb1); vb2 = URF_FMUL(sc, vb2);        // :52-55
   const float dot = URF_FADD(URF_FMUL(va1, vb1), URF_FMUL(va2, vb2));
@@ -182,7 +210,11 @@ URF_HD bool zzero_mark_t(const DevParams& prm, const float4* ring, int n, int m)
   const float al = URF_D2F(deg_d(urfm::acosf_glibc(bk)));                                                     // :63
   return al <= prm.angleFilter2;                                                                              // :66
 }
-
+template <int CP>
+URF_HD bool zzero_mark_t(const DevParams& prm, const float4* ring, int n, int m) {
+  const RingAoS rv{ring};
+  return zzero_pre_t<CP>(prm, rv, n, m) && zzero_post_t<CP>(prm, rv, m);
+}
 URF_HD bool zzero_mark(const DevParams& prm, const float4* ring, int n, int m) { return zzero_mark_t<0>(prm, ring, n, m); }
 
 // Edge search along one radius-sorted sector (star_shaped_search.cpp:112-150) as a step function: state after point

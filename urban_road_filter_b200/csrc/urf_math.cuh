@@ -33,6 +33,7 @@
 #define URF_DMUL(a, b) __dmul_rn((a), (b))
 #define URF_DDIV(a, b) __ddiv_rn((a), (b))
 #define URF_DSQRT(a) __dsqrt_rn((a))
+#define URF_DFMA(a, b, c) __fma_rn((a), (b), (c))
 #define URF_F2I(x) __float_as_int((x))
 #define URF_I2F(x) __int_as_float((x))
 #define URF_FABS(x) fabsf((x))
@@ -49,6 +50,7 @@
 #define URF_DMUL(a, b) ((double)(a) * (double)(b))
 #define URF_DDIV(a, b) ((double)(a) / (double)(b))
 #define URF_DSQRT(a) sqrt((a))
+#define URF_DFMA(a, b, c) fma((double)(a), (double)(b), (double)(c))   /* correctly rounded with or without hardware FMA */
 static inline int32_t urf_f2i_(float x) { int32_t i; memcpy(&i, &x, 4); return i; }
 static inline float urf_i2f_(int32_t i) { float x; memcpy(&x, &i, 4); return x; }
 #define URF_F2I(x) urf_f2i_((x))
@@ -59,6 +61,17 @@ static inline float urf_i2f_(int32_t i) { float x; memcpy(&x, &i, 4); return x; 
 #define URF_PI_D 3.14159265358979323846 /* M_PI */
 
 namespace urfm {
+
+// v / M_PI in double, correctly rounded, without the divide: q = RN(v * RN(1/pi)), one Markstein correction step with the
+// exact remainder. Equal to the IEEE quotient for EVERY double that is a finite float (all 2^32 patterns are swept by
+// tests/kat/math_sweep.cpp); the path only ever divides float radians * 180.0f (converted to double) by M_PI.
+URF_HD double div_pi(double v) {
+  if (v == 0.0) return v;                                   // keeps the sign of zero
+  const double inv = 0.31830988618379069122;                // RN(1 / M_PI) = 0x1.45f306dc9c883p-2
+  const double q = URF_DMUL(v, inv);
+  const double r = URF_DFMA(-URF_PI_D, q, v);
+  return URF_DFMA(r, inv, q);
+}
 
 // ---- asinf: glibc 2.39 sysdeps/ieee754/flt-32/e_asinf.c (Moshier single-precision polynomial) -------------------
 URF_HD float asinf_glibc(float x) {
