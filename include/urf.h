@@ -144,6 +144,34 @@ int urf_process(urf_ctx* ctx, const float* xyzi, int n, urf_result* out);
 int urf_process_cloud2(urf_ctx* ctx, const void* data, int n_points, int point_step, int off_x, int off_y, int off_z,
                        urf_result* out);
 
+/* One pcl::PointXYZI record as the reference stores it in its output clouds (32 bytes, PCL_ADD_POINT4D + intensity). */
+typedef struct urf_point_xyzi {
+  float x, y, z, w;              /* w = data[3] = 1.0f, as PCL's constructor leaves it */
+  float intensity, pad[3];
+} urf_point_xyzi;
+
+/* The four output clouds of one scan, packed on the device in the reference's emission order:
+ *   road          = cloud_filtered_Road          lidar_segmentation.cpp:354-361 (label 1; ring-major, ascending azimuth)
+ *   curb          = cloud_filtered_High          lidar_segmentation.cpp:362-366 (label 2; same order)
+ *   roi           = cloud_filtered_Box           lidar_segmentation.cpp:114-120 (every ROI point, input order)
+ *   road_probably = cloud_filtered_ProbablyRoad  lidar_segmentation.cpp:605-608 (ring 10, ascending azimuth)
+ * Each pointer is a caller-owned HOST buffer with room for n_points records, or NULL to skip that cloud; n_* are set
+ * by the call (all 0 when status == URF_TOO_FEW_POINTS). */
+typedef struct urf_clouds {
+  urf_point_xyzi* road;
+  urf_point_xyzi* curb;
+  urf_point_xyzi* roi;
+  urf_point_xyzi* road_probably;
+  int32_t n_road, n_curb, n_roi, n_road_probably;
+} urf_clouds;
+
+/* urf_process_cloud2 with the output side on the device too: instead of (or besides) labels and the emission order, the
+ * call returns the four clouds the reference publishes, ready to be wrapped in PointCloud2 messages; only the records
+ * that exist cross PCIe. off_intensity = byte offset of the FLOAT32 intensity field, or -1 (intensity 0). out->label /
+ * ring / order may be NULL. The first packed call allocates 96 bytes of device memory per point of capacity. */
+int urf_process_cloud2_packed(urf_ctx* ctx, const void* data, int n_points, int point_step, int off_x, int off_y, int off_z,
+                              int off_intensity, urf_result* out, urf_clouds* clouds);
+
 /* `batch` independent scans (distinct clouds, same params), HOST buffers. xyzi[b] has n[b] points; outs[b] as above. */
 int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int batch, urf_result* outs);
 

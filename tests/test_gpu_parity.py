@@ -294,3 +294,68 @@ def test_gpu_pointcloud2_unpack_on_device(det, port, step, ox, oy, oz):
     r = det.filtered_cloud2(raw, n, step, ox, oy, oz)
     o = port.run(pts, prm)
     assert stage_diffs(o, r, n) == []
+
+
+def _cloud2_records(pts, step, ox, oy, oz, oi, seed=0):
+    n = pts.shape[0]
+    rec = np.random.default_rng(seed).integers(0, 256, (n, step), dtype=np.uint8)     # garbage in the other fields
+    for k, off in enumerate((ox, oy, oz, oi)):
+        if off >= 0:
+            rec[:, off: off + 4] = pts[:, k: k + 1].copy().view(np.uint8)
+    return rec.reshape(-1)
+
+
+def _expect_records(pts, ids, with_intensity=True):
+    e = np.zeros((len(ids), 8), np.float32)
+    e[:, 0:3] = pts[ids, 0:3]
+    e[:, 3] = 1.0
+    if with_intensity:
+        e[:, 4] = pts[ids, 3]
+    return e
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_gpu_packed_clouds_match_reference_goldens(det, name):
+    """urf_process_cloud2_packed: the four clouds packed on the device are, record for record and in
+    order, the clouds the UNMODIFIED reference published for the same input (fixtures of tests/golden)."""
+    g = Golden(name)
+    pts = g.cloud
+    n = pts.shape[0]
+    if n > det.max_points:
+        pytest.skip("larger than the module's detector")
+    det.set_params(g.params())
+    raw = _cloud2_records(pts, 48, 0, 4, 8, 16, seed=n)                 # Ouster-like 48-byte records, intensity at 16
+    r, cl = det.filtered_cloud2_packed(raw, n, 48, 0, 4, 8, 16, want_labels=True)
+    if not g.published:
+        assert r.status == 1 and all(len(v) == 0 for v in cl.values())
+        return
+    assert r.status == 0
+    np.testing.assert_array_equal(r.label, g.label)
+    for key, ids in (("road", g.road_ids), ("curb", g.curb_ids), ("road_probably", g.prob_ids), ("roi", np.flatnonzero(g.label >= 0))):
+        exp = _expect_records(pts, np.asarray(ids, np.int64))
+        assert cl[key].shape == exp.shape, f"{key}: {cl[key].shape[0]} records, reference published {exp.shape[0]}"
+        assert cl[key].tobytes() == exp.tobytes(), f"{key}: packed cloud differs from the reference's"
+
+
+@pytest.mark.parametrize("shape,step,offs", [("C1", 22, (0, 4, 8, 12)), ("C2", 32, (0, 4, 8, 16)), ("C2", 64, (40, 12, 28, -1))])
+def test_gpu_packed_clouds_match_oracle(det, port, shape, step, offs):
+    """Packed clouds against the oracle's labels + emission order on larger scans, default and full ROI, with records
+    that are not 4-byte aligned and without an intensity field."""
+    pts = make_scan(shape, 21)
+    n = pts.shape[0]
+    for prm in (make_params(), make_params(**FULL_ROI)):
+        det.set_params(prm)
+        raw = _cloud2_records(pts, step, *offs, seed=step)
+        r, cl = det.filtered_cloud2_packed(raw, n, step, *offs)
+        o = port.run(pts, prm)
+        assert r.status == o.status == 0
+        lab = np.asarray(o.label)
+        order = np.asarray(o.order[: o.n_order])
+        rs = np.asarray(o.ring_start)
+        wi = offs[3] >= 0
+        exp = {"road": order[lab[order] == 1], "curb": order[lab[order] == 2], "roi": np.flatnonzero(lab >= 0),
+               "road_probably": order[rs[10]: rs[11]] if len(rs) > 11 else order[:0]}
+        for key, ids in exp.items():
+            e = _expect_records(pts, ids, wi)
+            assert cl[key].shape == e.shape and cl[key].tobytes() == e.tobytes(), key
+        assert r.label is None and (r.n_road, r.n_curb) == (len(exp["road"]), len(exp["curb"]))

@@ -14,7 +14,7 @@ from .ctypes_abi import (URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_TOO_FEW_PO
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liburf_b200.so")
 
-EXPORTS = ["urf_process_cloud2", "urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
+EXPORTS = ["urf_process_cloud2", "urf_process_cloud2_packed", "urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
            "urf_set_params", "urf_get_params", "urf_process", "urf_process_batch", "urf_process_batch_device",
            "urf_enqueue_batch_device", "urf_finish_batch_device", "urf_stream", "urf_last_device_ms",
            "urf_last_launch_count", "urf_build_markers"]
@@ -52,6 +52,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.urf_process.argtypes = [vp, vp, ip, C.POINTER(UrfResult)]
     lib.urf_process_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(ip), ip, C.POINTER(UrfResult)]
     lib.urf_process_cloud2.argtypes = [vp, vp, ip, ip, ip, ip, ip, C.POINTER(UrfResult)]
+    lib.urf_process_cloud2_packed.argtypes = [vp, vp, ip, ip, ip, ip, ip, ip, C.POINTER(UrfResult), C.POINTER(UrfClouds)]
     lib.urf_process_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp, C.POINTER(UrfResult)]
     lib.urf_enqueue_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp]
     lib.urf_finish_batch_device.argtypes = [vp, C.POINTER(UrfResult)]
@@ -205,6 +206,37 @@ class Detector:
         r.ring_start = rs[: r.n_rings + 1].copy()
         r.vert = np.ctypeslib.as_array(res.vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()
         return r
+
+    def filtered_cloud2_packed(self, data, n_points: int, point_step: int, off_x: int, off_y: int, off_z: int,
+                               off_intensity: int = -1, want_labels: bool = False):
+        """One scan from raw PointCloud2 bytes; returns (ScanResult, clouds) where clouds maps "road" / "curb" / "roi" /
+        "road_probably" to float32 arrays [count, 8] of 32-byte pcl::PointXYZI records packed on the device in the
+        reference's emission order (include/urf.h urf_clouds). Labels / order are only fetched with want_labels."""
+        raw = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        m = max(n_points, 1)
+        bufs = {k: np.empty((m, 8), np.float32) for k in ("road", "curb", "roi", "road_probably")}
+        cl = UrfClouds()
+        for k, a in bufs.items():
+            setattr(cl, k, a.ctypes.data)
+        rs = np.zeros(URF_MAX_CHANNELS + 1, np.int32)
+        res = UrfResult()
+        res.ring_start = rs.ctypes.data_as(C.POINTER(C.c_int32))
+        lab = order = None
+        if want_labels:
+            lab, order = np.full(m, -1, np.int32), np.zeros(m, np.int32)
+            res.label = lab.ctypes.data_as(C.POINTER(C.c_int32)); res.order = order.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(self.lib.urf_process_cloud2_packed(self._ctx, raw.ctypes.data, n_points, point_step, off_x, off_y, off_z,
+                                                       off_intensity, C.byref(res), C.byref(cl)), "urf_process_cloud2_packed")
+        r = ScanResult()
+        for f in ("status", "n_in", "n_roi", "n_rings", "n_order", "n_road", "n_curb", "n_vert", "flags"):
+            setattr(r, f, int(getattr(res, f)))
+        r.label = lab[:n_points] if want_labels else None
+        r.order = order[: r.n_order].copy() if want_labels else None
+        r.ring = None
+        r.ring_start = rs[: r.n_rings + 1].copy()
+        r.vert = np.ctypeslib.as_array(res.vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()
+        counts = dict(road=cl.n_road, curb=cl.n_curb, roi=cl.n_roi, road_probably=cl.n_road_probably)
+        return r, {k: bufs[k][: counts[k]] for k in bufs}
 
     def filtered(self, cloud, **kw) -> ScanResult:
         """One Detector::filtered() call."""

@@ -37,6 +37,10 @@ struct urf_ctx {
   float4* own_in = nullptr;
   unsigned char* raw = nullptr;        // PointCloud2 staging: max_points * URF_MAX_POINT_STEP bytes (urf_process_cloud2)
   int* own_label = nullptr;
+  float4* pack = nullptr;              // packed output clouds (urf_process_cloud2_packed): 3 * max_points 32-byte records, allocated on first use
+  int* packcnt = nullptr;              // [3][tiles] per-tile counts / offsets
+  int* packtot = nullptr;              // [4] cloud sizes
+  int* h_packtot = nullptr;            // pinned copy
   urf_params params{};
   DevParams dp{};
   int* h_n = nullptr;          // pinned
@@ -327,6 +331,7 @@ void urf_destroy(urf_ctx* ctx) {
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->h_n) cudaFreeHost(ctx->h_n);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
+  if (ctx->h_packtot) cudaFreeHost(ctx->h_packtot);
   if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
   for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
@@ -532,25 +537,47 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
   return URF_OK;
 }
 
-int urf_process_cloud2(urf_ctx* ctx, const void* data, int n, int point_step, int off_x, int off_y, int off_z, urf_result* out) {
+namespace {
+// Shared body of urf_process_cloud2 / urf_process_cloud2_packed: H2D of the raw records, unpack, pipeline, optional pack.
+int process_cloud2(urf_ctx* ctx, const void* data, int n, int point_step, int off_x, int off_y, int off_z, int off_i,
+                   urf_result* out, urf_clouds* clouds) {
   if (!ctx || !out || n < 0 || (n > 0 && !data)) return URF_ERR_INVALID;
   if (point_step < 12 || point_step > URF_MAX_POINT_STEP) return URF_ERR_INVALID;
   for (int o : {off_x, off_y, off_z}) if (o < 0 || o + 4 > point_step) return URF_ERR_INVALID;
+  if (off_i >= 0 && off_i + 4 > point_step) return URF_ERR_INVALID;
   if (n > ctx->max_points) return URF_ERR_CAPACITY;
   CK(cudaSetDevice(ctx->device));
+  const int tiles = (std::max(ctx->max_points, 1) + kPackTile - 1) / kPackTile;
+  if (clouds && !ctx->pack) {                                // first packed call: 96 bytes per point of capacity
+    int rc = dalloc(ctx, &ctx->pack, (size_t)6 * ctx->max_points);
+    if (rc == URF_OK) rc = dalloc(ctx, &ctx->packcnt, (size_t)3 * tiles);
+    if (rc == URF_OK) rc = dalloc(ctx, &ctx->packtot, 4);
+    if (rc != URF_OK) { ctx->pack = nullptr; return rc; }
+    CK(cudaMallocHost((void**)&ctx->h_packtot, sizeof(int) * 4));
+  }
   const int S = ((std::max(n, 1) + 255) / 256) * 256;
   cudaStream_t st = ctx->stream;
   ctx->h_n[0] = n;
   CK(cudaMemcpyAsync(ctx->buf.n, ctx->h_n, sizeof(int), cudaMemcpyHostToDevice, st));
   if (n > 0) {
     CK(cudaMemcpyAsync(ctx->raw, data, (size_t)n * point_step, cudaMemcpyHostToDevice, st));
-    k_unpack_cloud2<<<(n + 255) / 256, 256, 0, st>>>(ctx->raw, ctx->own_in, n, point_step, off_x, off_y, off_z);
+    k_unpack_cloud2<<<(n + 255) / 256, 256, 0, st>>>(ctx->raw, ctx->own_in, n, point_step, off_x, off_y, off_z, off_i);
   }
-  const bool want_order = out->order != nullptr;
+  const bool want_order = out->order != nullptr || clouds != nullptr;
   int rc = launch_pipeline_graphed(ctx, 1, S, want_order);
   if (rc != URF_OK) return rc;
   int* ring32 = reinterpret_cast<int*>(ctx->buf.sortbuf);
   if (out->ring) k_ring32<<<dim3((S + 255) / 256, 1), 256, 0, st>>>(ctx->buf, ring32, S);
+  float4 *d_rc = nullptr, *d_roi = nullptr, *d_prob = nullptr;
+  if (clouds) {
+    const int nt = (std::max(n, 1) + kPackTile - 1) / kPackTile;
+    d_rc = ctx->pack; d_roi = ctx->pack + 2 * (size_t)ctx->max_points; d_prob = ctx->pack + 4 * (size_t)ctx->max_points;
+    k_pack_count<<<nt, 256, 0, st>>>(ctx->buf, ctx->packcnt, nt);
+    k_pack_scan<<<1, 1024, 0, st>>>(ctx->buf, ctx->packcnt, nt, ctx->packtot);
+    k_pack_write<<<nt, 256, 0, st>>>(ctx->buf, ctx->packcnt, nt, ctx->packtot, d_rc, d_roi, d_prob);
+    ctx->launches += 3;
+    CK(cudaMemcpyAsync(ctx->h_packtot, ctx->packtot, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  }
   CK(cudaMemcpyAsync(ctx->h_out, ctx->buf.out, sizeof(ScanOut), cudaMemcpyDeviceToHost, st));
   if (n > 0) {
     if (out->label) CK(cudaMemcpyAsync(out->label, ctx->own_label, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -558,10 +585,31 @@ int urf_process_cloud2(urf_ctx* ctx, const void* data, int n, int point_step, in
     if (out->order) CK(cudaMemcpyAsync(out->order, ctx->buf.order, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
+  if (clouds) {                                              // sizes are known now: copy exactly the records that exist
+    const int* t = ctx->h_packtot;
+    clouds->n_road = t[0]; clouds->n_curb = t[1]; clouds->n_roi = t[2]; clouds->n_road_probably = t[3];
+    const size_t rec = sizeof(urf_point_xyzi);
+    if (clouds->road && t[0] > 0) CK(cudaMemcpyAsync(clouds->road, d_rc, rec * t[0], cudaMemcpyDeviceToHost, st));
+    if (clouds->curb && t[1] > 0) CK(cudaMemcpyAsync(clouds->curb, d_rc + 2 * (size_t)t[0], rec * t[1], cudaMemcpyDeviceToHost, st));
+    if (clouds->roi && t[2] > 0) CK(cudaMemcpyAsync(clouds->roi, d_roi, rec * t[2], cudaMemcpyDeviceToHost, st));
+    if (clouds->road_probably && t[3] > 0) CK(cudaMemcpyAsync(clouds->road_probably, d_prob, rec * t[3], cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   ctx->last_B = 1; ctx->last_S = S;
   fill_result(ctx->h_out[0], out);
   if (out->status == URF_TOO_FEW_POINTS && out->ring) for (int i = 0; i < n; i++) out->ring[i] = -1;
   return URF_OK;
+}
+}  // namespace
+
+int urf_process_cloud2(urf_ctx* ctx, const void* data, int n, int point_step, int off_x, int off_y, int off_z, urf_result* out) {
+  return process_cloud2(ctx, data, n, point_step, off_x, off_y, off_z, -1, out, nullptr);
+}
+
+int urf_process_cloud2_packed(urf_ctx* ctx, const void* data, int n, int point_step, int off_x, int off_y, int off_z,
+                              int off_intensity, urf_result* out, urf_clouds* clouds) {
+  if (!clouds) return URF_ERR_INVALID;
+  return process_cloud2(ctx, data, n, point_step, off_x, off_y, off_z, off_intensity, out, clouds);
 }
 
 int urf_process(urf_ctx* ctx, const float* xyzi, int n, urf_result* out) {

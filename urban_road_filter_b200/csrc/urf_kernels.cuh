@@ -1050,19 +1050,127 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
   if (tie) atomicOr(&out.flags, F_TIE_AZIMUTH);
 }
 
-// k_unpack_cloud2: PointCloud2 record -> (x, y, z, 0) float4. Byte-wise loads when a field is not
-// 4-byte aligned (Velodyne's 22-byte records).
+// k_unpack_cloud2: PointCloud2 record -> (x, y, z, intensity) float4. Byte-wise loads when a field is
+// not 4-byte aligned (Velodyne's 22-byte records). off_i < 0: no intensity field, 0 is stored.
 __device__ __forceinline__ float load_f32_unaligned(const unsigned char* p) {
   if ((reinterpret_cast<size_t>(p) & 3) == 0) return *reinterpret_cast<const float*>(p);
   const unsigned v = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
   return __uint_as_float(v);
 }
 __global__ void __launch_bounds__(256) k_unpack_cloud2(const unsigned char* __restrict__ raw, float4* __restrict__ dst, int n,
-                                                        int point_step, int off_x, int off_y, int off_z) {
+                                                        int point_step, int off_x, int off_y, int off_z, int off_i) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned char* rec = raw + (size_t)i * point_step;
-  dst[i] = make_float4(load_f32_unaligned(rec + off_x), load_f32_unaligned(rec + off_y), load_f32_unaligned(rec + off_z), 0.f);
+  dst[i] = make_float4(load_f32_unaligned(rec + off_x), load_f32_unaligned(rec + off_y), load_f32_unaligned(rec + off_z),
+                       off_i >= 0 ? load_f32_unaligned(rec + off_i) : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Output clouds packed on the device (scan 0 of the buffers): what lidar_segmentation.cpp:354-367 and
+// :605-608 push into cloud_filtered_Road / _High / _ProbablyRoad and what :120 leaves in cloud_filtered_Box, as 32-byte
+// pcl::PointXYZI records (x, y, z, 1.0f | intensity, 0, 0, 0) in the reference's emission order:
+//   road = points of `order` (ring-major, ascending azimuth) with label 1, curb = label 2 (stored behind road in the same
+//   buffer), roi = label >= 0 in input order, road_probably = ring 10 of `order`.
+// Three kernels: per-tile counts -> exclusive scan over tiles -> stable per-tile compaction.
+constexpr int kPackTile = 1024;
+__device__ __forceinline__ void pack_flags(const DevBuffers& buf, const ScanOut& out, int e, bool* road, bool* curb, bool* roi, int* idx) {
+  *road = *curb = *roi = false; *idx = 0;
+  if (out.n_roi < 30) return;                                            // nothing is published, lidar_segmentation.cpp:124-126
+  if (e < out.n_order) { *idx = buf.order[e]; const int lab = buf.label[*idx]; *road = lab == 1; *curb = lab == 2; }
+  if (e < out.n_in) *roi = buf.label[e] >= 0;
+}
+// exclusive rank of `flag` among the CTA's 256 threads (thread order) and the CTA total; all threads must call
+__device__ __forceinline__ int cta_rank(bool flag, int* s_w /* [8] */, int* total) {
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();                                                       // s_w free again
+  if (lane_id() == 0) s_w[w] = __popc(bal);
+  __syncthreads();
+  int before = 0, all = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { const int c = s_w[j]; all += c; if (j < w) before += c; }
+  *total = all;
+  return before + __popc(bal & ((1u << lane_id()) - 1u));
+}
+__global__ void __launch_bounds__(256) k_pack_count(DevBuffers buf, int* __restrict__ cnt, int tiles) {
+  __shared__ int s_c[3];
+  const ScanOut& out = buf.out[0];
+  if (threadIdx.x < 3) s_c[threadIdx.x] = 0;
+  __syncthreads();
+  int c0 = 0, c1 = 0, c2 = 0;
+  for (int j = 0; j < kPackTile / 256; j++) {
+    bool road, curb, roi; int idx;
+    pack_flags(buf, out, blockIdx.x * kPackTile + j * 256 + threadIdx.x, &road, &curb, &roi, &idx);
+    c0 += road; c1 += curb; c2 += roi;
+  }
+  c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
+  if (lane_id() == 0) { atomicAdd(&s_c[0], c0); atomicAdd(&s_c[1], c1); atomicAdd(&s_c[2], c2); }
+  __syncthreads();
+  if (threadIdx.x < 3) cnt[threadIdx.x * tiles + blockIdx.x] = s_c[threadIdx.x];
+}
+// one CTA: exclusive scan of the three per-tile count rows in place; tot[0..3] = road, curb, roi, road_probably counts
+__global__ void __launch_bounds__(1024) k_pack_scan(DevBuffers buf, int* __restrict__ cnt, int tiles, int* __restrict__ tot) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  for (int row = 0; row < 3; row++) {
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < tiles; t0 += 1024) {
+      const int t = t0 + threadIdx.x;
+      const int v = t < tiles ? cnt[row * tiles + t] : 0;
+      int x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane_id() >= d) x += y; }
+      if (lane_id() == 31) s_w[threadIdx.x >> 5] = x;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        int wv = s_w[threadIdx.x];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wv, d); if (lane_id() >= d) wv += y; }
+        s_w[threadIdx.x] = wv;
+      }
+      __syncthreads();
+      const int carry = s_carry, wbase = (threadIdx.x >> 5) ? s_w[(threadIdx.x >> 5) - 1] : 0;
+      if (t < tiles) cnt[row * tiles + t] = carry + wbase + x - v;
+      __syncthreads();
+      if (threadIdx.x == 0) s_carry = carry + s_w[31];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) tot[row] = s_carry;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const ScanOut& out = buf.out[0];
+    tot[3] = out.n_roi < 30 ? 0 : out.ring_start[11] - out.ring_start[10];     // lidar_segmentation.cpp:605-608
+  }
+}
+__device__ __forceinline__ void pack_record(float4* __restrict__ dst, int pos, const float4 p) {
+  dst[2 * (size_t)pos] = make_float4(p.x, p.y, p.z, 1.0f);               // PCL_ADD_POINT4D: data[3] = 1.0f
+  dst[2 * (size_t)pos + 1] = make_float4(p.w, 0.f, 0.f, 0.f);            // intensity + padding
+}
+__global__ void __launch_bounds__(256) k_pack_write(DevBuffers buf, const int* __restrict__ cnt, int tiles, const int* __restrict__ tot,
+                                                     float4* __restrict__ road_curb, float4* __restrict__ roi_dst, float4* __restrict__ prob) {
+  __shared__ int s_w[8];
+  const ScanOut& out = buf.out[0];
+  int road_pos = cnt[blockIdx.x], curb_pos = tot[0] + cnt[tiles + blockIdx.x], roi_pos = cnt[2 * tiles + blockIdx.x];
+  const int rs10 = out.ring_start[10], rs11 = out.n_roi < 30 ? rs10 : out.ring_start[11];
+  for (int j = 0; j < kPackTile / 256; j++) {
+    const int e = blockIdx.x * kPackTile + j * 256 + threadIdx.x;
+    bool road, curb, roi; int idx;
+    pack_flags(buf, out, e, &road, &curb, &roi, &idx);
+    int total;
+    const int r0 = cta_rank(road, s_w, &total);
+    if (road) pack_record(road_curb, road_pos + r0, buf.in[idx]);
+    road_pos += total;
+    const int r1 = cta_rank(curb, s_w, &total);
+    if (curb) pack_record(road_curb, curb_pos + r1, buf.in[idx]);
+    curb_pos += total;
+    const int r2 = cta_rank(roi, s_w, &total);
+    if (roi) pack_record(roi_dst, roi_pos + r2, buf.in[e]);
+    roi_pos += total;
+    if (e >= rs10 && e < rs11) pack_record(prob, e - rs10, buf.in[idx]);
+  }
 }
 
 // Device-side evaluation of the emulated libm (test hook: urf_test_math).

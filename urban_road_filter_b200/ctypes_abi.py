@@ -68,6 +68,17 @@ class UrfStrip(C.Structure):
                 ("count", C.c_int32)]
 
 
+class UrfPointXYZI(C.Structure):
+    """pcl::PointXYZI as the reference stores it (32 bytes)."""
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("w", C.c_float),
+                ("intensity", C.c_float), ("pad", C.c_float * 3)]
+
+
+class UrfClouds(C.Structure):
+    _fields_ = [("road", C.c_void_p), ("curb", C.c_void_p), ("roi", C.c_void_p), ("road_probably", C.c_void_p),
+                ("n_road", C.c_int32), ("n_curb", C.c_int32), ("n_roi", C.c_int32), ("n_road_probably", C.c_int32)]
+
+
 # cfg/LidarFilters.cfg:10-84 defaults
 DEFAULTS = dict(
     fixed_frame=b"left_os1/os1_lidar", topic_name=b"/left_os1/os1_cloud_node/points",
