@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .ctypes_abi import (URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_TOO_FEW_POINTS, UrfParams, UrfResult, UrfStrip,
+from .ctypes_abi import (URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_TOO_FEW_POINTS, UrfClouds, UrfParams, UrfResult, UrfStrip,
                          make_params)
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liburf_b200.so")
