@@ -388,47 +388,56 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   const unsigned lt = (1u << lane) - 1u;
   unsigned packed[kChunk / 32];                 // (ring + 1) << 16 | rank inside the chunk's ring group
   const unsigned gb = scan_base(b, S), g0 = gb + (unsigned)chunk * kChunk;
-  // two halves of 8 iterations: the loads of a half (ring, sector, and the point itself where a sector record has to be
-  // written) are issued together before the dependent ranking work
-  constexpr int HALF = kChunk / 64;
+  // four groups of 4 iterations. Inside a group everything with a long latency is issued before anything depends on it:
+  // ring/sector loads, then the point loads (where a sector record has to be written), then the sector cursor atomics
+  // (one per set of equal sectors, slots handed out in lane order); the shared-memory ring ranking runs while the atomics
+  // are in flight, and the sector records are stored last.
+  constexpr int GRP = 4;
 #pragma unroll
-  for (int h = 0; h < 2; h++) {
-    short rr[HALF], ss[HALF];
-    float4 pp[HALF];
+  for (int h = 0; h < kChunk / 32 / GRP; h++) {
+    short rr[GRP], ss[GRP];
+    float4 pp[GRP];
+    int sbase[GRP];
+    unsigned speers[GRP];
 #pragma unroll
-    for (int u = 0; u < HALF; u++) {
-      const int li = (h * HALF + u) * 32 + lane;
+    for (int u = 0; u < GRP; u++) {
+      const int li = (h * GRP + u) * 32 + lane;
       const bool in = chunk * kChunk + li < n;
       rr[u] = in ? buf.ringid[g0 + li] : (short)-1;
       ss[u] = in ? buf.sect[g0 + li] : (short)-1;
     }
 #pragma unroll
-    for (int u = 0; u < HALF; u++) {
-      const int li = (h * HALF + u) * 32 + lane;
+    for (int u = 0; u < GRP; u++) {
+      const int li = (h * GRP + u) * 32 + lane;
       pp[u] = ss[u] >= 0 ? __ldg(&buf.in[g0 + li]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < HALF; u++) {
-      const int it = h * HALF + u;
-      const int li = it * 32 + lane;
-      const int i = chunk * kChunk + li;
-      const int ring = rr[u], sec = ss[u];
-      unsigned peers = __match_any_sync(0xffffffffu, ring);
+    for (int u = 0; u < GRP; u++) {
+      const int sec = ss[u];
+      const unsigned peers = __match_any_sync(0xffffffffu, sec);
+      speers[u] = peers;
+      sbase[u] = 0;
+      if (sec >= 0 && lane == __ffs(peers) - 1) sbase[u] = atomicAdd(&tab.sect_cur[sec], __popc(peers));
+    }
+#pragma unroll
+    for (int u = 0; u < GRP; u++) {
+      const int it = h * GRP + u;
+      const int ring = rr[u];
+      const unsigned peers = __match_any_sync(0xffffffffu, ring);
       unsigned pk = 0;
       if (ring >= 0) pk = ((unsigned)(ring + 1) << 16) | (lcnt[ring] + __popc(peers & lt));
       __syncwarp();
       if (ring >= 0 && lane == __ffs(peers) - 1) lcnt[ring] += (unsigned short)__popc(peers);
       packed[it] = pk;
-      // sector: one atomic per group of equal sectors, slots handed out in lane order
-      peers = __match_any_sync(0xffffffffu, sec);
-      if (sec >= 0) {
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&tab.sect_cur[sec], __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        buf.spt[gb + (unsigned)(base + __popc(peers & lt))] = make_float4(star_radius(pp[u].x, pp[u].y), pp[u].z, __int_as_float(i), 0.f);
-      }
       __syncwarp();
+    }
+#pragma unroll
+    for (int u = 0; u < GRP; u++) {
+      const int i = chunk * kChunk + (h * GRP + u) * 32 + lane;
+      const unsigned peers = speers[u];
+      const int base = __shfl_sync(0xffffffffu, sbase[u], __ffs(peers) - 1);
+      if (ss[u] >= 0)
+        buf.spt[gb + (unsigned)(base + __popc(peers & lt))] = make_float4(star_radius(pp[u].x, pp[u].y), pp[u].z, __int_as_float(i), 0.f);
     }
   }
   // exclusive scan of the chunk's ring counts -> local starts
@@ -457,13 +466,28 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
     total += __popc(__ballot_sync(0xffffffffu, pk != 0));
   }
   __syncwarp();
-  for (int t = lane; t < total; t += 32) {
-    const int li = perm[t], ring = pring[t];
-    const float4 p = __ldg(&buf.in[g0 + li]);
-    const unsigned dst = gb + goff[ring] + (unsigned)(t - lcnt[ring]);
-    buf.bpt[dst] = make_float4(p.x, p.y, p.z, __int_as_float(chunk * kChunk + li));
-    buf.bring[dst] = (unsigned char)ring;
-    buf.bidx[dst] = chunk * kChunk + li;
+  // walk the chunk in ring order, four warp-rows at a time so that four point gathers are in flight per lane
+  for (int t0 = 0; t0 < total; t0 += 128) {
+    float4 p[4];
+    int li[4], ring[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int t = t0 + j * 32 + lane;
+      li[j] = t < total ? perm[t] : 0;
+      ring[j] = t < total ? pring[t] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) p[j] = __ldg(&buf.in[g0 + li[j]]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int t = t0 + j * 32 + lane;
+      if (t < total) {
+        const unsigned dst = gb + goff[ring[j]] + (unsigned)(t - lcnt[ring[j]]);
+        buf.bpt[dst] = make_float4(p[j].x, p[j].y, p[j].z, __int_as_float(chunk * kChunk + li[j]));
+        buf.bring[dst] = (unsigned char)ring[j];
+        buf.bidx[dst] = chunk * kChunk + li[j];
+      }
+    }
   }
 }
 
