@@ -372,18 +372,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   const int n = buf.n[b];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int chunk = blockIdx.x * kWarpsPerBlock + warp;
-  __shared__ unsigned s_goff[kWarpsPerBlock][kRingKeys];          // global bucket offset of this chunk, per ring
+  __shared__ unsigned s_delta[kWarpsPerBlock][kChunk];            // bucket slot of ring-ordered slot t, minus t
   __shared__ unsigned short s_lcnt[kWarpsPerBlock][kRingKeys];    // per-ring count, then exclusive local start
   __shared__ unsigned short s_perm[kWarpsPerBlock][kChunk];       // chunk-local point index in ring order
   __shared__ unsigned char s_pring[kWarpsPerBlock][kChunk];       // ring of that slot
   if (chunk * kChunk >= n) return;
-  unsigned* goff = s_goff[warp];
+  unsigned* delta = s_delta[warp];
   unsigned short* lcnt = s_lcnt[warp];
   unsigned short* perm = s_perm[warp];
   unsigned char* pring = s_pring[warp];
   ScanTab& tab = buf.tab[b];
   const unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
-  for (int t = lane; t < kRingKeys; t += 32) { goff[t] = row[t]; lcnt[t] = 0; }
+  for (int t = lane; t < kRingKeys; t += 32) lcnt[t] = 0;
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
   unsigned packed[kChunk / 32];                 // (ring + 1) << 16 | rank inside the chunk's ring group
@@ -459,9 +459,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
     const unsigned pk = packed[it];
     if (pk) {
       const int ring = (int)(pk >> 16) - 1;
-      const int slot = lcnt[ring] + (pk & 0xffffu);
+      const unsigned lstart = lcnt[ring];
+      const int slot = lstart + (pk & 0xffffu);
       perm[slot] = (unsigned short)(it * 32 + lane);
       pring[slot] = (unsigned char)ring;
+      delta[slot] = __ldg(&row[ring]) - lstart;        // global offset of the chunk's ring group - its local start
     }
     total += __popc(__ballot_sync(0xffffffffu, pk != 0));
   }
@@ -470,11 +472,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   for (int t0 = 0; t0 < total; t0 += 128) {
     float4 p[4];
     int li[4], ring[4];
+    unsigned dl[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int t = t0 + j * 32 + lane;
       li[j] = t < total ? perm[t] : 0;
       ring[j] = t < total ? pring[t] : 0;
+      dl[j] = t < total ? delta[t] : 0;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) p[j] = __ldg(&buf.in[g0 + li[j]]);
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
     for (int j = 0; j < 4; j++) {
       const int t = t0 + j * 32 + lane;
       if (t < total) {
-        const unsigned dst = gb + goff[ring[j]] + (unsigned)(t - lcnt[ring[j]]);
+        const unsigned dst = gb + dl[j] + (unsigned)t;
         buf.bpt[dst] = make_float4(p[j].x, p[j].y, p[j].z, __int_as_float(chunk * kChunk + li[j]));
         buf.bring[dst] = (unsigned char)ring[j];
         buf.bidx[dst] = chunk * kChunk + li[j];
