@@ -75,20 +75,22 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
 // Also records, per fine elevation bin, the first input index that falls into it (speculation input for k_register).
 __global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
-  const int n = buf.n[b];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned g = scan_base(b, S) + (unsigned)i;
+  // i < S: inside the scan's slot whatever n is, so the load need not wait for n
+  const float4 p = i < S ? __ldg(&buf.in[g]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n = buf.n[b];
   int keep = 0, sec = -1;
   if (i < n) {
-    const unsigned g = scan_base(b, S) + (unsigned)i;
-    const float4 p = __ldg(&buf.in[g]);
     keep = roi_keep(prm, p.x, p.y, p.z);
     float a = -1.0f;
     if (keep) {
       a = elev_alpha(p.x, p.y, p.z);
       unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1) + elev_bin(a);
-      if (*fi > (unsigned)i) atomicMin(fi, (unsigned)i);      // plain (possibly stale) read: a stale value is only larger
+      const unsigned seen = *(volatile unsigned*)fi;          // plain (possibly stale) read, issued before the sector math that hides it
       if (a == 0.0f) atomicOr(&buf.out[b].flags, F_ZERO_ALPHA);
       if (prm.star) sec = star_sector(prm, p.x, p.y, c_beam_d, c_beam_o, c_beam_yx);   // star_shaped_search.cpp:164-173
+      if (seen > (unsigned)i) atomicMin(fi, (unsigned)i);     // a stale value is only larger
     }
     buf.alpha_v[g] = a;
     buf.mark[g] = 0;
@@ -754,6 +756,8 @@ template <int MINB>
 __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
+  // inside the scan's slot whatever n_order is, so the load need not wait for it
+  const float4 me0 = (int)(blockIdx.x * blockDim.x + threadIdx.x) < S ? buf.bpt[scan_base(b, S) + blockIdx.x * blockDim.x + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
   const int N = out.n_order;
   __shared__ float s_x[256 + 2 * kHalo], s_y[256 + 2 * kHalo], s_z[256 + 2 * kHalo];
   __shared__ int s_rs[kRingKeys + 1];                     // ring_start of the rings this CTA touches, indexed by ring - k_lo
@@ -774,8 +778,7 @@ __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevPa
   const bool tiled = prm.curbPoints <= kHalo;
   const int p = p0 + tid;
   const bool act = p < N;
-  float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (act) me = bucket[p];
+  const float4 me = act ? me0 : make_float4(0.f, 0.f, 0.f, 0.f);
   if (tiled) {                                            // one bucket record per thread + a halo record for the first 64 threads
     s_x[kHalo + tid] = me.x; s_y[kHalo + tid] = me.y; s_z[kHalo + tid] = me.z;
     if (tid < 2 * kHalo) {
@@ -954,17 +957,20 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
   const int b = blockIdx.y;
   ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned gb = scan_base(b, S), g = gb + (unsigned)p;
+  // p < S: the four loads stay inside the scan's slot whatever n_order is, so they are issued together with its load
+  const bool in_slot = p < S;
+  const int k0 = in_slot ? buf.bring[g] : 0, lab0 = in_slot ? buf.blabel[g] : 0, idx = in_slot ? buf.bidx[g] : 0;
+  const float a0 = in_slot ? buf.az[g] : 0.f;
   const int N = out.n_order;
   if ((int)(blockIdx.x * blockDim.x) >= N) return;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   int lab = -1, k = 0, bin = 0;
   float a = 0.f;
-  const unsigned gb = scan_base(b, S), g = gb + (unsigned)p;
   if (p < N) {
-    k = buf.bring[g];
-    a = buf.az[g];
-    lab = buf.blabel[g];
-    const int idx = buf.bidx[g];
+    k = k0;
+    a = a0;
+    lab = lab0;
     // everything the decision needs is loaded up front (independent loads, one round trip): the two threshold entries
     // and the bin's current first-non-road key
     const unsigned o = ((unsigned)b * (unsigned)prm.channels + (unsigned)k) * kTStride;
