@@ -359,3 +359,32 @@ def test_gpu_packed_clouds_match_oracle(det, port, shape, step, offs):
             e = _expect_records(pts, ids, wi)
             assert cl[key].shape == e.shape and cl[key].tobytes() == e.tobytes(), key
         assert r.label is None and (r.n_road, r.n_curb) == (len(exp["road"]), len(exp["curb"]))
+
+
+@pytest.mark.parametrize("variant", ["scan", "flat", "half_flat"])
+@pytest.mark.parametrize("shape", ["C2", "C4"])
+def test_gpu_near_first_star_sort(det, port, shape, variant):
+    """k_star_sort_warp sorts only the points below a sampled pivot radius and k_star_scan redoes (tab.refine) the sectors
+    whose edge search runs off that prefix. A flat world has no edge at all (every sector is refined), a half-flat one
+    mixes both paths; each must give the oracle's result, and the same result as whole-sector sorting (option 4 = 0)."""
+    sh = SHAPES[shape]
+    pts = make_scan(shape, 31)
+    if variant == "flat":
+        pts[:, 2] = -1.8
+    elif variant == "half_flat":
+        pts[pts[:, 0] < 0, 2] = -1.8
+    n = pts.shape[0]
+    prm = make_params(channels=sh.channels, interval=sh.interval, **FULL_ROI)
+    det.set_params(prm)
+    o = port.run(pts, prm, debug=True)
+    if variant == "flat":
+        assert int((np.asarray(o.star_mark) == 2).sum()) == 0
+    res = {}
+    for mode in (1, 0):
+        det.set_option(4, mode)
+        r = det.filtered(pts)
+        assert stage_diffs(o, GpuDebug(det, r, n), n) == [], f"star_prefix={mode}"
+        res[mode] = r
+    det.set_option(4, 1)
+    np.testing.assert_array_equal(res[0].label, res[1].label)
+    np.testing.assert_array_equal(res[0].vert, res[1].vert)

@@ -135,10 +135,16 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
   if (dp.star) {
     const int gbig = std::max(4, std::min(kSectKeys, 2048 / B)), gslow = std::max(2, std::min(kSectKeys, 512 / B));
-    K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, S));
+    const dim3 gscan((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B);
+    K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, dp, S));
     K("k_star_sort_cta", k_star_sort_cta<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
-    K("k_star_sort", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S));
-    K("k_star_scan", k_star_scan<<<dim3((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B), kScanWarps * 32, 0, st>>>(buf, dp, S));
+    K("k_star_sort", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S, 0));
+    K("k_star_scan", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S, 0));
+    if (dp.star_prefix) {          // sectors whose edge search ran off the near-first prefix: full sort, second search pass
+      K("k_star_sort_refine", k_star_sort_refine<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, S));
+      K("k_star_sort_2", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S, 1));
+      K("k_star_scan_2", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S, 1));
+    }
   }
   K("k_ring_detect", k_ring_detect<8><<<gpts, 256, 0, st>>>(buf, dp, S));   // 8 CTAs/SM (32 registers): measured 2 % faster than 6, 25 % faster than 4
   K("k_tab1", k_tab1<<<dim3((dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
@@ -318,6 +324,8 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   urf_default_params(&ctx->params);
   const char* fe = std::getenv("URF_FORCE_EXACT_REGISTRATION");
   narrow_params(&ctx->params, &ctx->dp, ctx->dp.Kfi, fe && fe[0] == '1', 0);
+  const char* sp = std::getenv("URF_STAR_PREFIX");          // near-first star sort, on unless URF_STAR_PREFIX=0 (A/B measurements)
+  ctx->dp.star_prefix = !(sp && sp[0] == '0');
 #undef TRY
 #undef CKF
   *out = ctx;
@@ -363,11 +371,13 @@ int urf_get_params(const urf_ctx* ctx, urf_params* p) {
 }
 
 // test/diagnostic options: 0 = force exact ring registration (0/1); 1 = per-kernel CUDA-event timing (slots, 0 = off);
-// 2 = number of compute streams a device-resident batch is spread over (1..4); 3 = CUDA graph for small batches (0/1)
+// 2 = number of compute streams a device-resident batch is spread over (1..4); 3 = CUDA graph for small batches (0/1);
+// 4 = near-first star sort (0/1, default 1)
 int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (!ctx) return URF_ERR_INVALID;
   ctx->version++;
-  if (option == 0) { ctx->dp.force_exact = value != 0; return URF_OK; }
+  if (option == 0) { ctx->dp.force_exact = value != 0; ctx->version++; return URF_OK; }
+  if (option == 4) { ctx->dp.star_prefix = value != 0; ctx->version++; return URF_OK; }
   if (option == 3) { ctx->use_graph = value != 0; return URF_OK; }
   if (option == 2) { ctx->groups = value < 1 ? 1 : (value > urf_ctx::kGroups ? urf_ctx::kGroups : value); return URF_OK; }
   if (option == 1) {                   // value = number of event slots (0 = off)

@@ -43,6 +43,7 @@ struct DevParams {
   int bwd_special;   // the i with (float)i == beamZone (:245), or -1
   int force_exact;   // test hook: always use the exact registration path
   int want_order;    // produce emission order (per-ring azimuth sort)
+  int star_prefix;   // near-first star sort on (default); 0 = always sort whole sectors (test hook)
 };
 
 // Small per-scan outputs copied back to the host after every call.
@@ -69,6 +70,10 @@ struct ScanTab {
   unsigned long long cutbest[kDegBins];              // min (ring, azimuth bits, bucket pos) over the bin's non-road points
   unsigned dmax[kDegBins];         // float bits of the farthest candidate road point
   unsigned long long best[kDegBins];                 // (ring, azimuth bits, bucket pos) of the first candidate reaching dmax
+  // near-first star sort (k_star_sort_warp): only the points below a sampled pivot radius are sorted at first
+  int sorted_len[kSectKeys];       // length of the radius-sorted prefix of the sector in `ssorted` (== size when fully sorted)
+  int nrefine, nslow2;             // sectors whose edge search ran off the sorted prefix / ties found while redoing them
+  unsigned short refine[kSectKeys], slowlist2[kSectKeys];
 };
 
 // All device buffers of a context. P = max_batch * max_points; T = ceil(max_points / kChunk).

@@ -61,7 +61,7 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
   for (int i = tid; i < kRingKeys; i += nth) { t.maxdist[i] = 0u; t.angle[i] = 0.f; t.regidx[i] = 0x7fffffff; t.regorder[i] = 0x7fffffff; }
   for (int i = tid; i < kDegBins; i += nth) { t.cutbest[i] = ~0ull; t.dmax[i] = 0u; t.best[i] = ~0ull; }
   for (int i = tid; i < kSectKeys; i += nth) t.sect_cnt[i] = 0;
-  if (tid == 0) { t.nbig = 0; t.nslow = 0; }
+  if (tid == 0) { t.nbig = 0; t.nslow = 0; t.nrefine = 0; t.nslow2 = 0; }
   unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1);
   for (int i = tid; i <= kElevBins; i += nth) fi[i] = 0xffffffffu;
   const size_t nb = (size_t)prm.channels * kDegBins;
@@ -510,17 +510,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
 // points, is redone by the 64-bit bitonic fallback k_star_sort.
 constexpr int kWarpCap = 1024, kCtaCap = 8192;
 
-template <int EPL, int WARPS>
+// LIST (single-warp only): the n elements to sort are given as (radius bits, slot in src) pairs in s_xk / s_xe instead of
+// being all of src[0 .. n) — the near-first prefix of k_star_sort_warp.
+template <int EPL, int WARPS, bool LIST = false>
 __device__ __forceinline__ bool bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid,
                                                unsigned* s_xk, unsigned* s_xe) {
   constexpr int THREADS = WARPS * 32;                // sorts up to THREADS * EPL elements
+  static_assert(!LIST || WARPS == 1, "list input shares the exchange buffers");
   const int lane = tid & 31;
   unsigned key[EPL], el[EPL];
 #pragma unroll
   for (int r = 0; r < EPL; r++) {
     const int e = tid * EPL + r;
     key[r] = 0xffffffffu; el[r] = 0u;
-    if (e < n) { key[r] = fbits(src[e].x); el[r] = (unsigned)e; }
+    if (e < n) {
+      if (LIST) { key[r] = s_xk[e]; el[r] = s_xe[e]; }
+      else { key[r] = fbits(src[e].x); el[r] = (unsigned)e; }
+    }
   }
   // intra-thread compare-exchange network for strides EPL/2 .. 1 of merge phase k (compile-time register indices)
   auto intra = [&](int k_over_epl, auto kc) {
@@ -594,12 +600,31 @@ __device__ __forceinline__ bool bitonic_sector(const float4* __restrict__ src, f
   return tie;
 }
 
+// whole sector of up to kWarpCap points by one warp; true = radius tie
+__device__ __forceinline__ bool sort_sector_warp(const float4* __restrict__ src, float4* __restrict__ dst, int n, int lane) {
+  if (n <= 128) return bitonic_sector<4, 1>(src, dst, n, lane, nullptr, nullptr);
+  if (n <= 256) return bitonic_sector<8, 1>(src, dst, n, lane, nullptr, nullptr);
+  if (n <= 512) return bitonic_sector<16, 1>(src, dst, n, lane, nullptr, nullptr);
+  return bitonic_sector<32, 1>(src, dst, n, lane, nullptr, nullptr);
+}
+
 // One 32-thread CTA per sector: sector index and size derive from blockIdx, so the compiler knows the control flow
 // around the shuffles is warp-uniform (no convergence barriers around every SHFL).
-__global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, int S) {
+//
+// Near-first sort. The edge search (k_star_scan) walks a sector outwards and stops at its first edge point, so the far
+// part of a sector is usually never looked at. Sectors above kPrefixMin points are therefore split at a pivot radius (the
+// 18th smallest of 32 evenly spaced samples): points below the pivot are compacted into shared memory and sorted (about
+// half the sector -> a network of half the width, ~40 % of the compare-exchanges), the rest is stored behind them
+// unsorted. tab.sorted_len tells k_star_scan how far it may walk; a sector whose walk reaches the end of the sorted prefix
+// without an edge is put on tab.refine and redone in full (k_star_sort_refine + a second k_star_scan pass). Exact either
+// way: every point of the prefix is closer than every point behind it.
+constexpr int kPrefixMin = 128;
+__global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, DevParams prm, int S) {
+  __shared__ unsigned s_pk[kWarpCap], s_pe[kWarpCap];
   const int b = blockIdx.y, s = blockIdx.x, lane = threadIdx.x;
   ScanTab& tab = buf.tab[b];
   const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+  if (lane == 0) tab.sorted_len[s] = n;
   if (n <= 0) return;
   const float4* src = buf.spt + (size_t)b * S + base;
   float4* dst = buf.ssorted + (size_t)b * S + base;
@@ -612,11 +637,54 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, int S) {
     return;
   }
   bool tie;
-  if (n <= 128) tie = bitonic_sector<4, 1>(src, dst, n, lane, nullptr, nullptr);
-  else if (n <= 256) tie = bitonic_sector<8, 1>(src, dst, n, lane, nullptr, nullptr);
-  else if (n <= 512) tie = bitonic_sector<16, 1>(src, dst, n, lane, nullptr, nullptr);
-  else tie = bitonic_sector<32, 1>(src, dst, n, lane, nullptr, nullptr);
+  int m = 0;
+  if (prm.star_prefix && n > kPrefixMin) {
+    // pivot: rank the 32 samples against each other (ranks are a permutation; ties broken by lane)
+    const unsigned mine = fbits(src[(int)(((unsigned)lane * (unsigned)n) >> 5)].x);
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) { const unsigned o = __shfl_sync(0xffffffffu, mine, j); rank += (o < mine) || (o == mine && j < lane); }
+    const unsigned pivot = __shfl_sync(0xffffffffu, mine, __ffs(__ballot_sync(0xffffffffu, rank == 17)) - 1);
+    const unsigned lt = (1u << lane) - 1u;
+    int tail = 0;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      const bool in = e < n;
+      float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in) rec = src[e];
+      const unsigned k = fbits(rec.x);
+      const bool sel = in && k < pivot;
+      const unsigned bs = __ballot_sync(0xffffffffu, sel), bn = __ballot_sync(0xffffffffu, in && !sel);
+      if (sel) { const int pos = m + __popc(bs & lt); s_pk[pos] = k; s_pe[pos] = (unsigned)e; }
+      else if (in) dst[n - 1 - (tail + __popc(bn & lt))] = rec;
+      m += __popc(bs); tail += __popc(bn);
+    }
+    __syncwarp();
+  }
+  if (m >= 32 && 4 * m <= 3 * n) {                                      // worth it: sort the near part only
+    if (m <= 128) tie = bitonic_sector<4, 1, true>(src, dst, m, lane, s_pk, s_pe);
+    else if (m <= 256) tie = bitonic_sector<8, 1, true>(src, dst, m, lane, s_pk, s_pe);
+    else if (m <= 512) tie = bitonic_sector<16, 1, true>(src, dst, m, lane, s_pk, s_pe);
+    else tie = bitonic_sector<32, 1, true>(src, dst, m, lane, s_pk, s_pe);
+    if (lane == 0) tab.sorted_len[s] = m;
+  } else {
+    tie = sort_sector_warp(src, dst, n, lane);
+  }
   if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;   // sets F_TIE_SECTOR there
+}
+
+// Sectors whose edge search ran off their sorted prefix (tab.refine): sort them completely.
+__global__ void __launch_bounds__(32) k_star_sort_refine(DevBuffers buf, int S) {
+  const int b = blockIdx.y, lane = threadIdx.x;
+  ScanTab& tab = buf.tab[b];
+  if ((int)blockIdx.x >= tab.nrefine) return;
+  const int s = tab.refine[blockIdx.x];
+  const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+  const float4* src = buf.spt + (size_t)b * S + base;
+  float4* dst = buf.ssorted + (size_t)b * S + base;
+  const bool tie = sort_sector_warp(src, dst, n, lane);
+  if (lane == 0) tab.sorted_len[s] = n;
+  if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist2[atomicAdd(&tab.nslow2, 1)] = (unsigned short)s;
 }
 
 constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap;
@@ -649,13 +717,15 @@ __global__ void __launch_bounds__(256) k_star_sort_cta(DevBuffers buf, int S) {
 // Fallback: CTA-wide bitonic sort on (radius bits, input index) keys (shared memory up to 4096 keys, global scratch
 // beyond) for sectors larger than kCtaCap or holding long runs of identical radii.
 constexpr int kStarSmemKeys = 4096;
-__global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S) {
+__global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S, int second) {
   const int b = blockIdx.y;
-  const ScanTab& tab = buf.tab[b];
+  ScanTab& tab = buf.tab[b];
   __shared__ unsigned long long s_keys[kStarSmemKeys];
-  const int nslow = tab.nslow;
+  const int nslow = second ? tab.nslow2 : tab.nslow;
+  const unsigned short* list = second ? tab.slowlist2 : tab.slowlist;
   for (int w = blockIdx.x; w < nslow; w += gridDim.x) {
-    const int s = tab.slowlist[w];
+    const int s = list[w];
+    if (threadIdx.x == 0) tab.sorted_len[s] = tab.sect_start[s + 1] - tab.sect_start[s];   // the whole sector gets sorted
     const int base = tab.sect_start[s];
     const int n = tab.sect_start[s + 1] - base;
     const float4* src = buf.spt + (size_t)b * S + base;
@@ -685,15 +755,24 @@ __global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S) {
 // 1 / i — including the IEEE divisions) into shared memory; the serial walk is then a dozen dependent float operations
 // per point.
 constexpr int kScanWarps = 2;
-__global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, DevParams prm, int S) {
+__global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, DevParams prm, int S, int second) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = lane_id();
-  const int s = (blockIdx.x * kScanWarps + warp) * 32 + lane;
   __shared__ float s_slp[kScanWarps][32][33];
   __shared__ float s_dxk[kScanWarps][32][33];
   __shared__ float s_inv[kScanWarps][32][33];
-  const ScanTab& tab = buf.tab[b];
-  int base = 0, n = 0;
-  if (s < kSectKeys) { base = tab.sect_start[s]; n = tab.sect_start[s + 1] - base; }
+  ScanTab& tab = buf.tab[b];
+  // first pass: lane = sector. Second pass: lane = entry of the refine list (sectors now sorted in full).
+  int s = (blockIdx.x * kScanWarps + warp) * 32 + lane;
+  if (second) {
+    const int nref = tab.nrefine;
+    if ((int)(blockIdx.x * kScanWarps * 32) >= nref) return;
+    s = s < nref ? tab.refine[s] : kSectKeys;
+  }
+  int base = 0, n = 0, whole = 0;
+  if (s < kSectKeys) {
+    base = tab.sect_start[s]; whole = tab.sect_start[s + 1] - base;
+    n = min(whole, tab.sorted_len[s]);               // walk the sorted prefix only
+  }
   const float4* all = buf.ssorted + (size_t)b * S;
   StarState st;
   star_init(st, 0.f, 0.f);
@@ -740,6 +819,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
     if (__all_sync(0xffffffffu, done)) break;
   }
   if (hit >= 0) buf.mark[scan_base(b, S) + (unsigned)__float_as_int(all[base + hit].z)] = 2;   // star_shaped_search.cpp:146
+  else if (n < whole) tab.refine[atomicAdd(&tab.nrefine, 1)] = (unsigned short)s;             // ran off the sorted prefix: redo in full
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
