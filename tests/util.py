@@ -99,9 +99,11 @@ def compare_strips(mine, ref, what):
 
 
 def feq(a: np.ndarray, b: np.ndarray) -> bool:
-    """bitwise float equality (NaN == NaN)"""
+    """bitwise float equality, any NaN == any NaN (x86 and the GPU produce different NaN bit patterns for 0/0)"""
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
+    a = np.where(np.isnan(a), np.float32(np.nan), a)
+    b = np.where(np.isnan(b), np.float32(np.nan), b)
     return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 

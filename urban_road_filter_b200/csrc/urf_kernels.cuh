@@ -75,22 +75,20 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
 // Also records, per fine elevation bin, the first input index that falls into it (speculation input for k_register).
 __global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned g = scan_base(b, S) + (unsigned)i;
-  // i < S: inside the scan's slot whatever n is, so the load need not wait for n
-  const float4 p = i < S ? __ldg(&buf.in[g]) : make_float4(0.f, 0.f, 0.f, 0.f);
   const int n = buf.n[b];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int keep = 0, sec = -1;
   if (i < n) {
+    const unsigned g = scan_base(b, S) + (unsigned)i;
+    const float4 p = __ldg(&buf.in[g]);
     keep = roi_keep(prm, p.x, p.y, p.z);
     float a = -1.0f;
     if (keep) {
       a = elev_alpha(p.x, p.y, p.z);
       unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1) + elev_bin(a);
-      const unsigned seen = *(volatile unsigned*)fi;          // plain (possibly stale) read, issued before the sector math that hides it
+      if (*fi > (unsigned)i) atomicMin(fi, (unsigned)i);      // plain (possibly stale) read: a stale value is only larger
       if (a == 0.0f) atomicOr(&buf.out[b].flags, F_ZERO_ALPHA);
       if (prm.star) sec = star_sector(prm, p.x, p.y, c_beam_d, c_beam_o, c_beam_yx);   // star_shaped_search.cpp:164-173
-      if (seen > (unsigned)i) atomicMin(fi, (unsigned)i);     // a stale value is only larger
     }
     buf.alpha_v[g] = a;
     buf.mark[g] = 0;
@@ -608,14 +606,43 @@ __device__ __forceinline__ bool sort_sector_warp(const float4* __restrict__ src,
   return bitonic_sector<32, 1>(src, dst, n, lane, nullptr, nullptr);
 }
 
+// Near-first selection (see k_star_sort_warp): all radius loads of the sector are issued together, the pivot is the 18th
+// smallest of 32 evenly spaced samples, and the (radius bits, slot) pairs below the pivot are appended to the shared
+// lists in any order. Returns their number.
+template <int EPL>
+__device__ __forceinline__ int select_near(const float4* __restrict__ src, int n, int lane, unsigned* s_pk, unsigned* s_pe) {
+  const unsigned mine = fbits(src[(int)(((unsigned)lane * (unsigned)n) >> 5)].x);
+  unsigned key[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; r++) {
+    const int e = r * 32 + lane;
+    key[r] = e < n ? fbits(src[e].x) : 0xffffffffu;
+  }
+  int rank = 0;                                        // ranks of the samples are a permutation (ties broken by lane)
+#pragma unroll
+  for (int j = 0; j < 32; j++) { const unsigned o = __shfl_sync(0xffffffffu, mine, j); rank += (o < mine) || (o == mine && j < lane); }
+  const unsigned pivot = __shfl_sync(0xffffffffu, mine, __ffs(__ballot_sync(0xffffffffu, rank == 17)) - 1);
+  const unsigned lt = (1u << lane) - 1u;
+  int m = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; r++) {
+    const bool sel = key[r] < pivot;                   // padding keys are 0xffffffff: never selected
+    const unsigned bs = __ballot_sync(0xffffffffu, sel);
+    if (sel) { const int pos = m + __popc(bs & lt); s_pk[pos] = key[r]; s_pe[pos] = (unsigned)(r * 32 + lane); }
+    m += __popc(bs);
+  }
+  __syncwarp();
+  return m;
+}
+
 // One 32-thread CTA per sector: sector index and size derive from blockIdx, so the compiler knows the control flow
 // around the shuffles is warp-uniform (no convergence barriers around every SHFL).
 //
 // Near-first sort. The edge search (k_star_scan) walks a sector outwards and stops at its first edge point, so the far
 // part of a sector is usually never looked at. Sectors above kPrefixMin points are therefore split at a pivot radius (the
 // 18th smallest of 32 evenly spaced samples): points below the pivot are compacted into shared memory and sorted (about
-// half the sector -> a network of half the width, ~40 % of the compare-exchanges), the rest is stored behind them
-// unsorted. tab.sorted_len tells k_star_scan how far it may walk; a sector whose walk reaches the end of the sorted prefix
+// half the sector -> a network of half the width, ~40 % of the compare-exchanges); the rest is not written at all.
+// tab.sorted_len tells k_star_scan how far it may walk; a sector whose walk reaches the end of the sorted prefix
 // without an edge is put on tab.refine and redone in full (k_star_sort_refine + a second k_star_scan pass). Exact either
 // way: every point of the prefix is closer than every point behind it.
 constexpr int kPrefixMin = 128;
@@ -639,27 +666,9 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, DevParams
   bool tie;
   int m = 0;
   if (prm.star_prefix && n > kPrefixMin) {
-    // pivot: rank the 32 samples against each other (ranks are a permutation; ties broken by lane)
-    const unsigned mine = fbits(src[(int)(((unsigned)lane * (unsigned)n) >> 5)].x);
-    int rank = 0;
-#pragma unroll
-    for (int j = 0; j < 32; j++) { const unsigned o = __shfl_sync(0xffffffffu, mine, j); rank += (o < mine) || (o == mine && j < lane); }
-    const unsigned pivot = __shfl_sync(0xffffffffu, mine, __ffs(__ballot_sync(0xffffffffu, rank == 17)) - 1);
-    const unsigned lt = (1u << lane) - 1u;
-    int tail = 0;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-      const int e = e0 + lane;
-      const bool in = e < n;
-      float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (in) rec = src[e];
-      const unsigned k = fbits(rec.x);
-      const bool sel = in && k < pivot;
-      const unsigned bs = __ballot_sync(0xffffffffu, sel), bn = __ballot_sync(0xffffffffu, in && !sel);
-      if (sel) { const int pos = m + __popc(bs & lt); s_pk[pos] = k; s_pe[pos] = (unsigned)e; }
-      else if (in) dst[n - 1 - (tail + __popc(bn & lt))] = rec;
-      m += __popc(bs); tail += __popc(bn);
-    }
-    __syncwarp();
+    if (n <= 256) m = select_near<8>(src, n, lane, s_pk, s_pe);
+    else if (n <= 512) m = select_near<16>(src, n, lane, s_pk, s_pe);
+    else m = select_near<32>(src, n, lane, s_pk, s_pe);
   }
   if (m >= 32 && 4 * m <= 3 * n) {                                      // worth it: sort the near part only
     if (m <= 128) tie = bitonic_sector<4, 1, true>(src, dst, m, lane, s_pk, s_pe);
