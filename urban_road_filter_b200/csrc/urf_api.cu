@@ -139,11 +139,11 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
     K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, dp, S));
     K("k_star_sort_cta", k_star_sort_cta<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
     K("k_star_sort", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S, 0));
-    K("k_star_scan", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S, 0));
-    if (dp.star_prefix) {          // sectors whose edge search ran off the near-first prefix: full sort, second search pass
-      K("k_star_sort_refine", k_star_sort_refine<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, S));
+    K("k_star_scan", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S));
+    if (dp.star_prefix) {          // sectors whose edge search ran off the near-first prefix: full sort, search resumed
+      K("k_star_sort_refine", k_star_sort_refine<<<dim3(std::max(8, std::min(kSectKeys, 4096 / B)), B), 32, 0, st>>>(buf, S));
       K("k_star_sort_2", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S, 1));
-      K("k_star_scan_2", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S, 1));
+      K("k_star_scan_resume", k_star_scan_resume<<<dim3((kSectKeys + 63) / 64, B), 64, 0, st>>>(buf, dp, S));
     }
   }
   K("k_ring_detect", k_ring_detect<8><<<gpts, 256, 0, st>>>(buf, dp, S));   // 8 CTAs/SM (32 registers): measured 2 % faster than 6, 25 % faster than 4

@@ -74,6 +74,7 @@ struct ScanTab {
   int sorted_len[kSectKeys];       // length of the radius-sorted prefix of the sector in `ssorted` (== size when fully sorted)
   int nrefine, nslow2;             // sectors whose edge search ran off the sorted prefix / ties found while redoing them
   unsigned short refine[kSectKeys], slowlist2[kSectKeys];
+  float resume[kSectKeys][4];      // per refine entry: running mean, deviation, NaN count of the walk over the prefix, its length
 };
 
 // All device buffers of a context. P = max_batch * max_points; T = ceil(max_points / kChunk).

@@ -686,14 +686,17 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, DevParams
 __global__ void __launch_bounds__(32) k_star_sort_refine(DevBuffers buf, int S) {
   const int b = blockIdx.y, lane = threadIdx.x;
   ScanTab& tab = buf.tab[b];
-  if ((int)blockIdx.x >= tab.nrefine) return;
-  const int s = tab.refine[blockIdx.x];
-  const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
-  const float4* src = buf.spt + (size_t)b * S + base;
-  float4* dst = buf.ssorted + (size_t)b * S + base;
-  const bool tie = sort_sector_warp(src, dst, n, lane);
-  if (lane == 0) tab.sorted_len[s] = n;
-  if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist2[atomicAdd(&tab.nslow2, 1)] = (unsigned short)s;
+  const int nref = tab.nrefine;
+  for (int w = blockIdx.x; w < nref; w += gridDim.x) {
+    const int s = tab.refine[w];
+    const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+    const float4* src = buf.spt + (size_t)b * S + base;
+    float4* dst = buf.ssorted + (size_t)b * S + base;
+    const bool tie = sort_sector_warp(src, dst, n, lane);
+    if (lane == 0) tab.sorted_len[s] = n;
+    if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist2[atomicAdd(&tab.nslow2, 1)] = (unsigned short)s;
+    __syncwarp();
+  }
 }
 
 constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap;
@@ -764,19 +767,13 @@ __global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S, int se
 // 1 / i — including the IEEE divisions) into shared memory; the serial walk is then a dozen dependent float operations
 // per point.
 constexpr int kScanWarps = 2;
-__global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, DevParams prm, int S, int second) {
+__global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = lane_id();
   __shared__ float s_slp[kScanWarps][32][33];
   __shared__ float s_dxk[kScanWarps][32][33];
   __shared__ float s_inv[kScanWarps][32][33];
   ScanTab& tab = buf.tab[b];
-  // first pass: lane = sector. Second pass: lane = entry of the refine list (sectors now sorted in full).
-  int s = (blockIdx.x * kScanWarps + warp) * 32 + lane;
-  if (second) {
-    const int nref = tab.nrefine;
-    if ((int)(blockIdx.x * kScanWarps * 32) >= nref) return;
-    s = s < nref ? tab.refine[s] : kSectKeys;
-  }
+  const int s = (blockIdx.x * kScanWarps + warp) * 32 + lane;
   int base = 0, n = 0, whole = 0;
   if (s < kSectKeys) {
     base = tab.sect_start[s]; whole = tab.sect_start[s + 1] - base;
@@ -828,7 +825,40 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
     if (__all_sync(0xffffffffu, done)) break;
   }
   if (hit >= 0) buf.mark[scan_base(b, S) + (unsigned)__float_as_int(all[base + hit].z)] = 2;   // star_shaped_search.cpp:146
-  else if (n < whole) tab.refine[atomicAdd(&tab.nrefine, 1)] = (unsigned short)s;             // ran off the sorted prefix: redo in full
+  else if (n < whole) {                               // ran off the sorted prefix: sort in full, k_star_scan_resume continues from here
+    const int w = atomicAdd(&tab.nrefine, 1);
+    tab.refine[w] = (unsigned short)s;
+    tab.resume[w][0] = st.avg; tab.resume[w][1] = st.dev; tab.resume[w][2] = st.nan; tab.resume[w][3] = __int_as_float(n);
+  }
+}
+
+// Second pass of the edge search for the sectors on tab.refine, now sorted in full: the first n points of the full order
+// are the prefix already walked (all of them are closer than the rest), so the walk resumes at point n with the saved
+// running mean / deviation. One lane per sector, four records in flight.
+__global__ void __launch_bounds__(64) k_star_scan_resume(DevBuffers buf, DevParams prm, int S) {
+  const int b = blockIdx.y;
+  ScanTab& tab = buf.tab[b];
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= tab.nrefine) return;
+  const int s = tab.refine[w];
+  const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+  const float4* pts = buf.ssorted + (size_t)b * S + base;
+  StarState st;
+  st.avg = tab.resume[w][0]; st.dev = tab.resume[w][1]; st.nan = tab.resume[w][2];
+  int i = __float_as_int(tab.resume[w][3]);            // >= 32: a prefix is never shorter
+  const float4 last = pts[i - 1];
+  st.bx = last.x; st.by = last.y;
+  int hit = -1;
+  while (i < n && hit < 0) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) p[u] = pts[min(i + u, n - 1)];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (hit < 0 && i + u < n && star_step(prm, st, i + u, p[u].x, p[u].y)) hit = i + u;
+    i += 4;
+  }
+  if (hit >= 0) buf.mark[scan_base(b, S) + (unsigned)__float_as_int(pts[hit].z)] = 2;           // star_shaped_search.cpp:146
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
