@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from urban_road_filter_b200 import UrfParams, UrfResult, UrfStrip, make_params
+from urban_road_filter_b200.ctypes_abi import UrfClouds, UrfPointXYZI
 from urban_road_filter_b200 import api
 from util import ROOT
 
@@ -32,8 +33,9 @@ def test_struct_layouts_match_the_header():
 #include <stddef.h>
 #include "urf.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(urf_params), sizeof(urf_result), sizeof(urf_strip),
-         offsetof(urf_params, channels), offsetof(urf_params, interval), offsetof(urf_result, label), offsetof(urf_result, vert));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(urf_params), sizeof(urf_result), sizeof(urf_strip),
+         offsetof(urf_params, channels), offsetof(urf_params, interval), offsetof(urf_result, label), offsetof(urf_result, vert),
+         sizeof(urf_point_xyzi), offsetof(urf_point_xyzi, intensity), sizeof(urf_clouds), offsetof(urf_clouds, n_road));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -41,7 +43,9 @@ int main(void) {
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")], check=True)
         vals = [int(v) for v in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()]
     assert vals == [C.sizeof(UrfParams), C.sizeof(UrfResult), C.sizeof(UrfStrip), UrfParams.channels.offset,
-                    UrfParams.interval.offset, UrfResult.label.offset, UrfResult.vert.offset]
+                    UrfParams.interval.offset, UrfResult.label.offset, UrfResult.vert.offset,
+                    C.sizeof(UrfPointXYZI), UrfPointXYZI.intensity.offset, C.sizeof(UrfClouds), UrfClouds.n_road.offset]
+    assert C.sizeof(UrfPointXYZI) == 32          # pcl::PointXYZI (PCL_ADD_POINT4D + intensity, 16-byte aligned)
 
 
 def test_defaults_match_cfg():

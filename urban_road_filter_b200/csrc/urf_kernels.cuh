@@ -7,9 +7,11 @@
 //
 // Pipeline (DESIGN.md has the picture):
 //   k_reset -> k_points -> k_register -> k_assign -> [k_register_exact -> k_assign(redo) -> k_mark_exact]
-//   -> k_scan_offsets -> k_scatter -> k_star_sort_warp / k_star_sort_cta / k_star_sort(fallback) -> k_star_scan
+//   -> k_scan_offsets -> k_scatter -> k_star_sort_warp (near-first) / k_star_sort_cta / k_star_sort(fallback) -> k_star_scan
+//   -> [k_star_sort_refine -> k_star_sort(fallback, second list) -> k_star_scan_resume: sectors without an edge in their prefix]
 //   -> k_ring_detect -> k_tab1 -> k_reach -> k_tab2 -> k_label -> k_dmax -> k_best -> k_verts
 //   [-> k_sort_rings when the emission order is requested]
+//   PointCloud2 entry points: k_unpack_cloud2 in front, k_pack_count -> k_pack_scan -> k_pack_write behind
 #pragma once
 #include <type_traits>
 
