@@ -200,6 +200,54 @@ int urf_last_launch_count(const urf_ctx* ctx);
 int urf_build_markers(const urf_params* p, const float (*vert)[4], int n_vert, int* ghostcount,
                       urf_strip* strips, int max_strips, double* points_xyz, int max_points, int* n_points_out);
 
+/* Pinned (page-locked) host memory for callers that stage scans themselves: urf_process* copies from such buffers
+ * asynchronously at full PCIe rate. NULL without a CUDA device. */
+void* urf_pinned_alloc(size_t bytes);
+void urf_pinned_free(void* p);
+
+/*
+ * Streaming ingest. The reference node subscribes with queue size 1 (lidar_segmentation.cpp:53): while
+ * Detector::filtered() runs, newer scans replace each other and all but the last are dropped. urf_queue keeps that
+ * contract available (URF_QUEUE_DROP_OLDEST) but makes it rare: producers (one per LiDAR topic / driver thread) copy
+ * their scan into one of `slots` pinned staging buffers and return at once; one worker thread owns the ctx and runs
+ * every scan that is pending — up to `max_batch` of them per urf_process_batch call, whose chunked three-stream pipeline
+ * overlaps the H2D copy of one chunk with the kernels of the previous one — and consumers take the results in
+ * submission order. The ctx must have been created with max_batch >= the queue's max_batch and must not be used by
+ * anyone else until urf_queue_destroy returns.
+ */
+typedef struct urf_queue urf_queue;
+enum { URF_QUEUE_BLOCK = 0, URF_QUEUE_DROP_OLDEST = 1 };
+enum { URF_ERR_TIMEOUT = -6, URF_ERR_CLOSED = -7 };
+typedef struct urf_queue_stats {
+  uint64_t submitted, processed, dropped, delivered, batches;
+  int32_t  largest_batch, pending, reserved;
+} urf_queue_stats;
+
+int urf_queue_create(urf_queue** out, urf_ctx* ctx, int max_points, int slots, int max_batch, int policy);
+/* Copy scan (n points of x, y, z, intensity) into a free slot. `tag` comes back with the result (sequence number,
+ * sensor id, stamp). No free slot: URF_QUEUE_BLOCK waits up to timeout_ms (< 0: forever) and returns URF_ERR_TIMEOUT;
+ * URF_QUEUE_DROP_OLDEST discards the oldest scan whose processing has not started (it is never delivered) — if every
+ * slot is already being processed or waiting to be collected it waits like BLOCK. Results are ordered by the moment a
+ * submit call finished copying (with one producer: submission order). */
+int urf_queue_submit(urf_queue* q, const float* xyzi, int n, uint64_t tag, int timeout_ms);
+/* Next result in submission order (dropped scans are skipped). out->label (n ints) may be NULL; ring / order /
+ * ring_start are not produced by the queue. URF_ERR_TIMEOUT when nothing finished within timeout_ms (< 0: wait),
+ * URF_ERR_CLOSED once the queue is closed and drained. A scan whose processing failed returns that error code. */
+int urf_queue_next(urf_queue* q, uint64_t* tag, urf_result* out, int timeout_ms);
+int urf_queue_get_stats(urf_queue* q, urf_queue_stats* st);
+/* Stop accepting scans: blocked and later urf_queue_submit calls return URF_ERR_CLOSED; the worker still finishes what
+ * is pending and urf_queue_next keeps delivering until the queue is drained, then returns URF_ERR_CLOSED. */
+void urf_queue_close(urf_queue* q);
+/* urf_queue_close, then waits for the worker and frees everything (undelivered results are discarded). No other thread
+ * may be inside a urf_queue_* call on this queue any more: close first, let producers and consumers return, then destroy. */
+void urf_queue_destroy(urf_queue* q);
+
+/* Test hook: the same queue around a caller-supplied batch function with urf_process_batch's signature (`user` is passed
+ * as its ctx argument) and malloc'ed instead of pinned staging — the queue mechanics can then be exercised without a GPU. */
+typedef int (*urf_queue_process_fn)(void* user, const float* const* xyzi, const int* n, int batch, urf_result* outs);
+int urf_queue_create_with(urf_queue** out, urf_queue_process_fn fn, void* user, int max_points, int slots, int max_batch,
+                          int policy);
+
 const char* urf_strerror(int code);
 const char* urf_last_cuda_error(const urf_ctx* ctx);
 int urf_version(void);

@@ -9,12 +9,15 @@ import os
 
 import numpy as np
 
-from .ctypes_abi import (URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_TOO_FEW_POINTS, UrfClouds, UrfParams, UrfResult, UrfStrip,
+from .ctypes_abi import (QUEUE_PROCESS_FN, URF_ERR_CLOSED, URF_ERR_TIMEOUT, URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_QUEUE_BLOCK,
+                         URF_QUEUE_DROP_OLDEST, URF_TOO_FEW_POINTS, UrfClouds, UrfParams, UrfQueueStats, UrfResult, UrfStrip,
                          make_params)
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liburf_b200.so")
 
-EXPORTS = ["urf_process_cloud2", "urf_process_cloud2_packed", "urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
+EXPORTS = ["urf_process_cloud2", "urf_process_cloud2_packed", "urf_pinned_alloc", "urf_pinned_free", "urf_queue_create",
+           "urf_queue_create_with", "urf_queue_submit", "urf_queue_next", "urf_queue_get_stats", "urf_queue_close", "urf_queue_destroy",
+           "urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
            "urf_set_params", "urf_get_params", "urf_process", "urf_process_batch", "urf_process_batch_device",
            "urf_enqueue_batch_device", "urf_finish_batch_device", "urf_stream", "urf_last_device_ms",
            "urf_last_launch_count", "urf_build_markers"]
@@ -63,6 +66,19 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.urf_last_launch_count.argtypes = [vp]
     lib.urf_build_markers.argtypes = [C.POINTER(UrfParams), vp, ip, C.POINTER(ip), C.POINTER(UrfStrip), ip, vp, ip,
                                       C.POINTER(ip)]
+    lib.urf_pinned_alloc.restype = vp
+    lib.urf_pinned_alloc.argtypes = [C.c_size_t]
+    lib.urf_pinned_free.restype = None
+    lib.urf_pinned_free.argtypes = [vp]
+    lib.urf_queue_create.argtypes = [C.POINTER(vp), vp, ip, ip, ip, ip]
+    lib.urf_queue_create_with.argtypes = [C.POINTER(vp), QUEUE_PROCESS_FN, vp, ip, ip, ip, ip]
+    lib.urf_queue_submit.argtypes = [vp, vp, ip, C.c_uint64, ip]
+    lib.urf_queue_next.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(UrfResult), ip]
+    lib.urf_queue_get_stats.argtypes = [vp, C.POINTER(UrfQueueStats)]
+    lib.urf_queue_close.restype = None
+    lib.urf_queue_close.argtypes = [vp]
+    lib.urf_queue_destroy.restype = None
+    lib.urf_queue_destroy.argtypes = [vp]
     lib.urf_test_math.argtypes = [ip, ip, vp, vp, vp, ip]
     lib.urf_debug_fetch.argtypes = [vp, ip, ip, vp, C.c_size_t]
     lib.urf_debug_sizeof_tab.restype = C.c_size_t
@@ -269,3 +285,66 @@ class Detector:
         a = np.zeros(max(count, 1), dtype)
         self._check(self.lib.urf_debug_fetch(self._ctx, scan, what, a.ctypes.data, a.nbytes if count else 0), "urf_debug_fetch")
         return a[:count]
+
+
+class ScanQueue:
+    """Streaming ingest (include/urf.h urf_queue): producers `submit` scans from any thread, one worker
+    thread batches whatever is pending through the detector, `next` returns results in submission order. With
+    `process_fn` (a Python callable with urf_process_batch's arguments) the queue runs without a GPU — tests only."""
+
+    def __init__(self, detector: "Detector | None", max_points: int, slots: int = 8, max_batch: int = 4,
+                 policy: int = URF_QUEUE_BLOCK, process_fn=None):
+        self.lib = load_library()
+        self._q = C.c_void_p()
+        self.max_points = max_points
+        self._cb = None
+        if process_fn is not None:
+            self._cb = QUEUE_PROCESS_FN(process_fn)
+            rc = self.lib.urf_queue_create_with(C.byref(self._q), self._cb, None, max_points, slots, max_batch, policy)
+        else:
+            assert detector is not None and detector.max_batch >= max_batch and detector.max_points >= max_points
+            self._det = detector          # keeps the ctx alive; nobody else may use it while the queue exists
+            rc = self.lib.urf_queue_create(C.byref(self._q), detector._ctx, max_points, slots, max_batch, policy)
+        if rc != URF_OK:
+            raise UrfError(rc, "urf_queue_create")
+
+    def submit(self, cloud: np.ndarray, tag: int = 0, timeout_ms: int = -1) -> int:
+        """Returns URF_OK, URF_ERR_TIMEOUT or URF_ERR_CLOSED; raises on anything else."""
+        pts = np.ascontiguousarray(cloud, np.float32)
+        rc = self.lib.urf_queue_submit(self._q, pts.ctypes.data, pts.shape[0], tag, timeout_ms)
+        if rc not in (URF_OK, URF_ERR_TIMEOUT, URF_ERR_CLOSED):
+            raise UrfError(rc, "urf_queue_submit")
+        return rc
+
+    def next(self, timeout_ms: int = -1):
+        """(tag, ScanResult) of the oldest finished scan, or None on timeout / when the closed queue is drained."""
+        lab = np.full(self.max_points, -1, np.int32)
+        res = UrfResult()
+        res.label = lab.ctypes.data_as(C.POINTER(C.c_int32))
+        tag = C.c_uint64()
+        rc = self.lib.urf_queue_next(self._q, C.byref(tag), C.byref(res), timeout_ms)
+        if rc in (URF_ERR_TIMEOUT, URF_ERR_CLOSED):
+            return None
+        if rc != URF_OK:
+            raise UrfError(rc, "urf_queue_next")
+        r = ScanResult()
+        for f in ("status", "n_in", "n_roi", "n_rings", "n_order", "n_road", "n_curb", "n_vert", "flags"):
+            setattr(r, f, int(getattr(res, f)))
+        r.label = lab[: r.n_in].copy()
+        r.ring = r.order = r.ring_start = None
+        r.vert = np.ctypeslib.as_array(res.vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()
+        return int(tag.value), r
+
+    def stats(self) -> dict:
+        st = UrfQueueStats()
+        self.lib.urf_queue_get_stats(self._q, C.byref(st))
+        return {k: int(getattr(st, k)) for k, _ in UrfQueueStats._fields_ if k != "reserved"}
+
+    def close(self):
+        if self._q:
+            self.lib.urf_queue_close(self._q)
+
+    def destroy(self):
+        if self._q:
+            self.lib.urf_queue_destroy(self._q)
+            self._q = C.c_void_p()

@@ -13,7 +13,7 @@ LIB = os.path.join(PKG, "liburf_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC"]
 SOURCES = ["urf_api.cu"]
-HOST_SOURCES = ["urf_markers.cpp"]
+HOST_SOURCES = ["urf_markers.cpp", "urf_queue.cpp"]
 HEADERS = ["urf_kernels.cuh", "urf_logic.cuh", "urf_device.cuh", "urf_math.cuh", "urf_host.hpp"]
 
 
@@ -47,7 +47,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
     for s in HOST_SOURCES:
         o = os.path.join(bdir, s + ".o")
-        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-c", os.path.join(CSRC, s), "-o", o], check=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-pthread", "-c", os.path.join(CSRC, s), "-o", o], check=True)
         objs.append(o)
     subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs], check=True)
     return LIB
@@ -73,6 +73,11 @@ def build_kat() -> None:
     if _stale(tgt, [os.path.join(kat, "model_check.cpp")] + hdrs):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
                         "-o", tgt, os.path.join(kat, "model_check.cpp")], check=True)
+    # ThreadSanitizer build of the streaming queue around a stand-in batch function (no CUDA involved)
+    tgt = os.path.join(bdir, "queue_stress")
+    qsrc = [os.path.join(kat, "queue_stress.cpp"), os.path.join(CSRC, "urf_queue.cpp")]
+    if _stale(tgt, qsrc + [os.path.join(ROOT, "include", "urf.h")]):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-o", tgt, *qsrc], check=True)
 
 
 def build_glue() -> str:

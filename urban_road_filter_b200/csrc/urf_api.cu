@@ -224,6 +224,8 @@ const char* urf_strerror(int code) {
     case URF_ERR_CUDA: return "CUDA error";
     case URF_ERR_NOMEM: return "out of device or pinned memory";
     case URF_ERR_CAPACITY: return "scan or batch larger than the context was created for";
+    case URF_ERR_TIMEOUT: return "timed out";
+    case URF_ERR_CLOSED: return "queue closed";
     default: return "unknown error";
   }
 }
@@ -353,6 +355,13 @@ void urf_destroy(urf_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
+
+void* urf_pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void urf_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 int urf_set_params(urf_ctx* ctx, const urf_params* p) {
   if (!ctx || !p) return URF_ERR_INVALID;

@@ -1,0 +1,250 @@
+// urf_queue.cpp — streaming ingest in front of urf_process_batch (include/urf.h). Host code only.
+//
+// Replaces the reference's depth-1 subscriber (`nh->subscribe(params::topicName, 1, &Detector::filtered, this)`,
+// lidar_segmentation.cpp:53): scans that arrive while a scan is being processed are staged instead of dropped, and the
+// worker hands everything that is pending to one batched call.
+//
+// Slot life cycle (all transitions under one mutex):
+//   FREE -> FILLING (producer copies the scan, lock released) -> PENDING -> RUNNING (worker) -> DONE -> FREE (consumer)
+//   PENDING -> FREE when URF_QUEUE_DROP_OLDEST needs room (the scan is counted as dropped, never delivered).
+// Results are delivered in submission order: every accepted scan gets a sequence number when it becomes PENDING and the
+// consumer waits for the smallest live one.
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/urf.h"
+
+namespace {
+enum SlotState { FREE = 0, FILLING, PENDING, RUNNING, DONE };
+struct Slot {
+  SlotState state = FREE;
+  uint64_t seq = 0, tag = 0;
+  int n = 0, rc = URF_OK;
+  float* in = nullptr;       // max_points * 4 floats (pinned for the real queue)
+  int32_t* label = nullptr;  // max_points
+  urf_result res{};
+};
+}  // namespace
+
+struct urf_queue {
+  urf_queue_process_fn fn = nullptr;
+  void* user = nullptr;
+  bool pinned = false;
+  int max_points = 0, max_batch = 1, policy = URF_QUEUE_BLOCK;
+  std::vector<Slot> slots;
+  std::mutex mu;
+  std::condition_variable cv_free, cv_pending, cv_done;
+  uint64_t next_seq = 1;       // sequence number of the next accepted scan
+  bool closed = false;
+  urf_queue_stats st{};
+  std::thread worker;
+};
+
+namespace {
+
+int real_process(void* user, const float* const* xyzi, const int* n, int batch, urf_result* outs) {
+  return urf_process_batch(static_cast<urf_ctx*>(user), xyzi, n, batch, outs);
+}
+
+template <class Pred>
+bool wait_for(std::condition_variable& cv, std::unique_lock<std::mutex>& lk, int timeout_ms, Pred pred) {
+  if (timeout_ms < 0) { cv.wait(lk, pred); return true; }
+  return cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred);
+}
+
+void worker_loop(urf_queue* q) {
+  std::vector<int> idx;
+  std::vector<const float*> ptrs;
+  std::vector<int> ns;
+  std::vector<urf_result> outs;
+  for (;;) {
+    idx.clear();
+    {
+      std::unique_lock<std::mutex> lk(q->mu);
+      q->cv_pending.wait(lk, [&] {
+        if (q->closed) return true;
+        for (const Slot& s : q->slots) if (s.state == PENDING) return true;
+        return false;
+      });
+      // everything pending, oldest first, up to max_batch
+      for (;;) {
+        int best = -1;
+        for (int i = 0; i < (int)q->slots.size(); i++) {
+          const Slot& s = q->slots[i];
+          if (s.state == PENDING && (best < 0 || s.seq < q->slots[best].seq)) best = i;
+        }
+        if (best < 0 || (int)idx.size() >= q->max_batch) break;
+        q->slots[best].state = RUNNING;
+        idx.push_back(best);
+      }
+      if (idx.empty()) { if (q->closed) return; continue; }
+      q->st.batches++;
+      if ((int)idx.size() > q->st.largest_batch) q->st.largest_batch = (int)idx.size();
+    }
+    const int B = (int)idx.size();
+    ptrs.resize(B); ns.resize(B); outs.assign(B, urf_result{});
+    for (int j = 0; j < B; j++) {
+      Slot& s = q->slots[idx[j]];
+      ptrs[j] = s.in; ns[j] = s.n;
+      outs[j].label = s.label;
+    }
+    const int rc = q->fn(q->user, ptrs.data(), ns.data(), B, outs.data());
+    {
+      std::lock_guard<std::mutex> lk(q->mu);
+      for (int j = 0; j < B; j++) {
+        Slot& s = q->slots[idx[j]];
+        s.res = outs[j]; s.rc = rc; s.state = DONE;
+        q->st.processed++;
+      }
+    }
+    q->cv_done.notify_all();
+  }
+}
+
+int create_common(urf_queue** out, urf_queue_process_fn fn, void* user, bool pinned, int max_points, int slots, int max_batch, int policy) {
+  if (!out || !fn || max_points < 1 || slots < 1 || max_batch < 1 || (policy != URF_QUEUE_BLOCK && policy != URF_QUEUE_DROP_OLDEST))
+    return URF_ERR_INVALID;
+  urf_queue* q = new urf_queue;
+  q->fn = fn; q->user = user; q->pinned = pinned; q->max_points = max_points; q->max_batch = max_batch; q->policy = policy;
+  q->slots.resize(slots);
+  for (Slot& s : q->slots) {
+    const size_t in_bytes = sizeof(float) * 4 * (size_t)max_points, lab_bytes = sizeof(int32_t) * (size_t)max_points;
+    s.in = static_cast<float*>(pinned ? urf_pinned_alloc(in_bytes) : std::malloc(in_bytes));
+    s.label = static_cast<int32_t*>(pinned ? urf_pinned_alloc(lab_bytes) : std::malloc(lab_bytes));
+    if (!s.in || !s.label) {
+      for (Slot& t : q->slots) {
+        if (pinned) { urf_pinned_free(t.in); urf_pinned_free(t.label); } else { std::free(t.in); std::free(t.label); }
+      }
+      delete q;
+      return URF_ERR_NOMEM;
+    }
+  }
+  q->worker = std::thread(worker_loop, q);
+  *out = q;
+  return URF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int urf_queue_create(urf_queue** out, urf_ctx* ctx, int max_points, int slots, int max_batch, int policy) {
+  if (!ctx) return URF_ERR_INVALID;
+  return create_common(out, real_process, ctx, true, max_points, slots, max_batch, policy);
+}
+
+int urf_queue_create_with(urf_queue** out, urf_queue_process_fn fn, void* user, int max_points, int slots, int max_batch, int policy) {
+  return create_common(out, fn, user, false, max_points, slots, max_batch, policy);
+}
+
+int urf_queue_submit(urf_queue* q, const float* xyzi, int n, uint64_t tag, int timeout_ms) {
+  if (!q || n < 0 || (n > 0 && !xyzi)) return URF_ERR_INVALID;
+  if (n > q->max_points) return URF_ERR_CAPACITY;
+  int slot = -1;
+  {
+    std::unique_lock<std::mutex> lk(q->mu);
+    auto find = [&] {
+      if (q->closed) return true;
+      for (int i = 0; i < (int)q->slots.size(); i++) if (q->slots[i].state == FREE) { slot = i; return true; }
+      if (q->policy == URF_QUEUE_DROP_OLDEST) {           // lidar_segmentation.cpp:53: the subscriber keeps only the newest scan
+        int best = -1;
+        for (int i = 0; i < (int)q->slots.size(); i++) {
+          const Slot& s = q->slots[i];
+          if (s.state == PENDING && (best < 0 || s.seq < q->slots[best].seq)) best = i;
+        }
+        if (best >= 0) { q->st.dropped++; slot = best; return true; }
+      }
+      return false;
+    };
+    if (!wait_for(q->cv_free, lk, timeout_ms, find)) return URF_ERR_TIMEOUT;
+    if (q->closed) return URF_ERR_CLOSED;
+    q->slots[slot].state = FILLING;                       // a dropped scan's sequence number simply never reaches DONE
+  }
+  Slot& s = q->slots[slot];
+  if (n > 0) std::memcpy(s.in, xyzi, sizeof(float) * 4 * (size_t)n);
+  {
+    std::lock_guard<std::mutex> lk(q->mu);
+    if (q->closed) {                                      // closed while copying: the worker may already be gone
+      s.state = FREE;
+      return URF_ERR_CLOSED;
+    }
+    s.n = n; s.tag = tag; s.rc = URF_OK;
+    s.seq = q->next_seq++;
+    s.state = PENDING;
+    q->st.submitted++;
+  }
+  q->cv_pending.notify_one();
+  q->cv_done.notify_all();                                // a consumer waiting on a dropped sequence number re-evaluates
+  return URF_OK;
+}
+
+int urf_queue_next(urf_queue* q, uint64_t* tag, urf_result* out, int timeout_ms) {
+  if (!q || !out) return URF_ERR_INVALID;
+  std::unique_lock<std::mutex> lk(q->mu);
+  int slot = -1;
+  bool drained = false;
+  auto ready = [&] {
+    // the oldest live scan: smallest sequence number among PENDING / RUNNING / DONE slots
+    int best = -1;
+    bool filling = false;
+    for (int i = 0; i < (int)q->slots.size(); i++) {
+      const Slot& s = q->slots[i];
+      if (s.state == FILLING) filling = true;
+      if ((s.state == PENDING || s.state == RUNNING || s.state == DONE) && (best < 0 || s.seq < q->slots[best].seq)) best = i;
+    }
+    if (best >= 0 && q->slots[best].state == DONE) { slot = best; return true; }
+    if (best < 0 && !filling && q->closed) { drained = true; return true; }
+    return false;
+  };
+  if (!wait_for(q->cv_done, lk, timeout_ms, ready)) return URF_ERR_TIMEOUT;
+  if (drained) return URF_ERR_CLOSED;
+  Slot& s = q->slots[slot];
+  int32_t* user_label = out->label;
+  const int rc = s.rc;
+  *out = s.res;
+  out->label = user_label; out->ring = nullptr; out->order = nullptr; out->ring_start = nullptr;
+  if (user_label && rc == URF_OK && s.n > 0) std::memcpy(user_label, s.label, sizeof(int32_t) * (size_t)s.n);
+  if (tag) *tag = s.tag;
+  s.state = FREE;
+  q->st.delivered++;
+  lk.unlock();
+  q->cv_free.notify_one();
+  return rc;
+}
+
+int urf_queue_get_stats(urf_queue* q, urf_queue_stats* st) {
+  if (!q || !st) return URF_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(q->mu);
+  *st = q->st;
+  st->pending = 0;
+  for (const Slot& s : q->slots) if (s.state == PENDING || s.state == RUNNING || s.state == FILLING) st->pending++;
+  return URF_OK;
+}
+
+void urf_queue_close(urf_queue* q) {
+  if (!q) return;
+  {
+    std::lock_guard<std::mutex> lk(q->mu);
+    q->closed = true;
+  }
+  q->cv_pending.notify_all();
+  q->cv_free.notify_all();
+  q->cv_done.notify_all();
+}
+
+void urf_queue_destroy(urf_queue* q) {
+  if (!q) return;
+  urf_queue_close(q);
+  if (q->worker.joinable()) q->worker.join();             // the worker drains what is pending before it returns
+  for (Slot& s : q->slots) {
+    if (q->pinned) { urf_pinned_free(s.in); urf_pinned_free(s.label); } else { std::free(s.in); std::free(s.label); }
+  }
+  delete q;
+}
+
+}  // extern "C"

@@ -79,6 +79,17 @@ class UrfClouds(C.Structure):
                 ("n_road", C.c_int32), ("n_curb", C.c_int32), ("n_roi", C.c_int32), ("n_road_probably", C.c_int32)]
 
 
+class UrfQueueStats(C.Structure):
+    _fields_ = [("submitted", C.c_uint64), ("processed", C.c_uint64), ("dropped", C.c_uint64), ("delivered", C.c_uint64),
+                ("batches", C.c_uint64), ("largest_batch", C.c_int32), ("pending", C.c_int32), ("reserved", C.c_int32)]
+
+
+URF_QUEUE_BLOCK, URF_QUEUE_DROP_OLDEST = 0, 1
+URF_ERR_TIMEOUT, URF_ERR_CLOSED = -6, -7
+# int (*)(void* user, const float* const* xyzi, const int* n, int batch, urf_result* outs)
+QUEUE_PROCESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.POINTER(UrfResult))
+
+
 # cfg/LidarFilters.cfg:10-84 defaults
 DEFAULTS = dict(
     fixed_frame=b"left_os1/os1_lidar", topic_name=b"/left_os1/os1_cloud_node/points",
