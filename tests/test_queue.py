@@ -158,16 +158,20 @@ def test_queue_reports_a_failed_batch():
     fb = FakeBatch(fail_on_batch=0)
     fb.gate.clear()
     q = api.ScanQueue(None, max_points=32, slots=4, max_batch=2, process_fn=fb)
-    for k in range(3):
+    assert q.submit(scan(0), tag=0) == URF_OK
+    assert fb.started.acquire(timeout=5)                          # batch 0 = scan 0 alone, held at the gate; it will fail
+    for k in (1, 2):
         assert q.submit(scan(k), tag=k) == URF_OK
     fb.gate.set()
-    for _ in range(2):                                            # the two scans of the failed batch carry its error code
-        with pytest.raises(api.UrfError) as e:
-            q.next(5000)
-        assert e.value.code == -3
-    t, r = q.next(5000)
-    assert t == 2
-    np.testing.assert_array_equal(r.label, expect_labels(2))
+    with pytest.raises(api.UrfError) as e:                        # the scan of the failed batch carries its error code
+        q.next(5000)
+    assert e.value.code == -3
+    for k in (1, 2):                                              # the queue keeps going
+        t, r = q.next(5000)
+        assert t == k
+        np.testing.assert_array_equal(r.label, expect_labels(k))
+    st = q.stats()
+    assert (st["submitted"], st["processed"], st["delivered"]) == (3, 3, 3)
     q.destroy()
 
 
