@@ -73,6 +73,10 @@ def build_kat() -> None:
     if _stale(tgt, [os.path.join(kat, "model_check.cpp")] + hdrs):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
                         "-o", tgt, os.path.join(kat, "model_check.cpp")], check=True)
+    tgt = os.path.join(bdir, "star_prefix_check")
+    if _stale(tgt, [os.path.join(kat, "star_prefix_check.cpp")] + hdrs):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I/usr/local/cuda/include", "-o", tgt,
+                        os.path.join(kat, "star_prefix_check.cpp")], check=True)
     # ThreadSanitizer build of the streaming queue around a stand-in batch function (no CUDA involved)
     tgt = os.path.join(bdir, "queue_stress")
     qsrc = [os.path.join(kat, "queue_stress.cpp"), os.path.join(CSRC, "urf_queue.cpp")]
