@@ -251,6 +251,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--groups", type=int, default=0, help="compute streams per device-resident batch (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the host-buffer region")
+    ap.add_argument("--sub", type=int, default=-1, help="scans per sub-batch of a device-resident step (library option 5)")
+    ap.add_argument("--graph", type=int, default=-1, help="replay a device-resident step as one CUDA graph (library option 6)")
+    ap.add_argument("--reuse", type=int, default=-1, help="sub-batches of a stream share a workspace slot (library option 7)")
+    ap.add_argument("--sweep", default="", help="tuning: ';'-separated groups,sub,graph,reuse settings timed one after the other")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "urf" else args.warmup
 
@@ -288,6 +292,9 @@ def main():
     det = api.Detector(max_points=n, max_batch=B, device=local, params=prm)
     if args.groups:
         det.set_option(2, args.groups)
+    for opt, v in ((5, args.sub), (6, args.graph), (7, args.reuse)):
+        if v >= 0:
+            det.set_option(opt, v)
     lib, ctx = det.lib, det._ctx
     S = n
     x = torch.empty((B, S, 4), dtype=torch.float32, device="cuda")
@@ -311,6 +318,28 @@ def main():
     for _ in range(args.warmup):
         step_device()
     assert lib.urf_finish_batch_device(ctx, outs) == 0
+    if args.sweep:                       # tuning: scheduling settings of the device-resident step, same process, same data
+        ref_road = sum(o.n_road for o in outs)
+        for cfg in args.sweep.split(";"):
+            g, sub, graph, reuse = (int(v) for v in cfg.split(","))
+            det.set_option(2, g); det.set_option(5, sub); det.set_option(6, graph); det.set_option(7, reuse)
+            for _ in range(3):
+                step_device()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record(stream)
+            for _ in range(args.steps):
+                step_device()
+            b_.record(stream)
+            t_enq = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            assert lib.urf_finish_batch_device(ctx, outs) == 0
+            ok = sum(o.n_road for o in outs) == ref_road
+            print(json.dumps({"sweep": cfg, "ms_per_step": a.elapsed_time(b_) / args.steps, "enqueue_ms_per_step": 1e3 * t_enq / args.steps,
+                              "launches": det.last_launch_count(), "road_ok": ok}), flush=True)
+        det.close()
+        return 0
     # ---- timed region 1: inputs resident in HBM; K steps enqueued back to back, no host sync inside. The library spreads
     # ---- the batch over 4 compute streams (independent scans), joined on its main stream, where the events are recorded.
     ktimes: dict[str, float] = {}

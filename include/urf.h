@@ -186,6 +186,11 @@ int urf_process_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_point
  * enqueue with their own CUDA events on urf_stream(). */
 int urf_enqueue_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch,
                              int32_t* d_label);
+/* As urf_enqueue_batch_device, plus the emission order: d_order (DEVICE, int32, same layout as d_label, or NULL) receives
+ * for every scan b the input indices of its n_order ring-assigned points in the reference's emission order (ring-major,
+ * ascending azimuth, lidar_segmentation.cpp:289-291,354-367) — i.e. the per-ring azimuth sort runs as part of the call. */
+int urf_enqueue_batch_device_ex(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch,
+                                int32_t* d_label, int32_t* d_order);
 int urf_finish_batch_device(urf_ctx* ctx, urf_result* outs);
 void* urf_stream(urf_ctx* ctx);            /* cudaStream_t of the ctx */
 /* CUDA-event timing of everything enqueued by the last urf_enqueue/process call: total ms on the ctx stream. */
@@ -249,6 +254,7 @@ int urf_queue_create_with(urf_queue** out, urf_queue_process_fn fn, void* user, 
                           int policy);
 
 const char* urf_strerror(int code);
+/* Text of the last failed CUDA call of `ctx`; with ctx == NULL: why this thread's last urf_create failed. */
 const char* urf_last_cuda_error(const urf_ctx* ctx);
 int urf_version(void);
 

@@ -19,7 +19,7 @@ EXPORTS = ["urf_process_cloud2", "urf_process_cloud2_packed", "urf_pinned_alloc"
            "urf_queue_create_with", "urf_queue_submit", "urf_queue_next", "urf_queue_get_stats", "urf_queue_close", "urf_queue_destroy",
            "urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
            "urf_set_params", "urf_get_params", "urf_process", "urf_process_batch", "urf_process_batch_device",
-           "urf_enqueue_batch_device", "urf_finish_batch_device", "urf_stream", "urf_last_device_ms",
+           "urf_enqueue_batch_device", "urf_enqueue_batch_device_ex", "urf_finish_batch_device", "urf_stream", "urf_last_device_ms",
            "urf_last_launch_count", "urf_build_markers"]
 
 _lib = None
@@ -58,6 +58,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.urf_process_cloud2_packed.argtypes = [vp, vp, ip, ip, ip, ip, ip, ip, C.POINTER(UrfResult), C.POINTER(UrfClouds)]
     lib.urf_process_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp, C.POINTER(UrfResult)]
     lib.urf_enqueue_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp]
+    lib.urf_enqueue_batch_device_ex.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp, vp]
     lib.urf_finish_batch_device.argtypes = [vp, C.POINTER(UrfResult)]
     lib.urf_stream.restype = vp
     lib.urf_stream.argtypes = [vp]

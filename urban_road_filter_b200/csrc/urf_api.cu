@@ -21,10 +21,17 @@ struct urf_ctx {
   int Tmax = 0;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t s_in = nullptr, s_out = nullptr;   // H2D / D2H copy streams of the pipelined host-buffer path
-  static constexpr int kGroups = 8;               // sub-batches of a device-resident call run on separate streams: scans are
+  static constexpr int kGroups = 16;               // sub-batches of a device-resident call run on separate streams: scans are
   cudaStream_t s_grp[kGroups] = {};               // independent, so their (short, partly latency-bound) kernels overlap
   cudaEvent_t ev_fork = nullptr, ev_join[kGroups] = {};
   int groups = 4;
+  // device-resident batches as many small sub-batches: `sub` scans per sub-batch (0 = one sub-batch per stream), dealt
+  // round-robin to the `groups` streams, the whole fork/join captured once as a CUDA graph (bgraph) and replayed; with
+  // `slot_reuse` the sub-batches of a stream share one workspace slot (working set = groups * sub scans, L2-resident)
+  int sub = 0;
+  bool slot_reuse = false, batch_graph = false;
+  cudaGraphExec_t bexec = nullptr;
+  struct { int B = -1, S = -1, sub = -1, G = -1, order = -1; bool reuse = false; const void* in = nullptr; void* label = nullptr; void* orderp = nullptr; unsigned long long version = 0; int launches = 0; } bkey;
   // CUDA graph of the kernel sequence for small host-buffer batches (launch latency dominates there); re-captured when
   // the shape, the parameters or an option change
   bool use_graph = true;
@@ -44,6 +51,12 @@ struct urf_ctx {
   urf_params params{};
   DevParams dp{};
   int* h_n = nullptr;          // pinned
+  // asynchronous enqueues stage their point counts in a ring of pinned rows, each guarded by the event of its H2D copy,
+  // so back-to-back enqueues with different counts never overwrite a row whose copy has not run yet
+  static constexpr int kNRing = 8;
+  int* h_nring = nullptr;      // pinned, [kNRing][max_batch]
+  cudaEvent_t ev_nring[kNRing] = {};
+  int nring_pos = 0;
   ScanOut* h_out = nullptr;    // pinned
   int last_B = 0, last_S = 0;
   int launches = 0;
@@ -84,22 +97,27 @@ __global__ void k_ring32(DevBuffers buf, int* dst, int S) {
   if (i < buf.n[b]) dst[(size_t)b * S + i] = buf.ringid[(size_t)b * S + i];
 }
 
-// All per-scan arrays of `buf` advanced by b0 scans (S points of stride, T histogram rows per scan).
-DevBuffers offset_view(const DevBuffers& a, int b0, int S, int T, int channels) {
+// View of `buf` for a sub-batch: what belongs to a scan for good (input, labels, point count, results, emission order) is
+// advanced by b0 scans, the workspace arrays by w0 scans (S points of stride, T histogram rows per scan). w0 == b0 gives
+// every scan its own workspace; sub-batches that run one after the other on one stream may share a slot (w0 = slot * sub).
+DevBuffers slot_view(const DevBuffers& a, int b0, int w0, int S, int T, int channels) {
   DevBuffers v = a;
-  const size_t o = (size_t)b0 * S;
-  v.in += o; v.alpha_v += o; v.mark += o; v.ringid += o; v.sect += o; v.label += o; v.bpt += o; v.spt += o; v.ssorted += o;
-  v.az += o; v.d2 += o; v.blabel += o; v.bring += o; v.bidx += o; v.roadlist += o; v.order += o; v.sortbuf += 2 * o;
-  v.Tf += (size_t)b0 * channels * kTStride; v.Tb += (size_t)b0 * channels * kTStride;
-  v.lut += (size_t)b0 * (kElevBins + 1); v.firstidx += (size_t)b0 * (kElevBins + 1);
-  v.hist += (size_t)b0 * T * kRingKeys;
-  v.cmin += (size_t)b0 * channels * kDegBins; v.cmax += (size_t)b0 * channels * kDegBins;
-  v.ne += (size_t)b0 * channels * (kDegBins + 1);
-  v.n += b0; v.out += b0; v.tab += b0;
+  const size_t o = (size_t)b0 * S, w = (size_t)w0 * S;
+  v.in += o; v.label += o; v.order += o; v.n += b0; v.out += b0;
+  v.alpha_v += w; v.mark += w; v.ringid += w; v.sect += w; v.bpt += w; v.spt += w; v.ssorted += w;
+  v.az += w; v.d2 += w; v.blabel += w; v.bring += w; v.bidx += w; v.roadlist += w; v.sortbuf += 2 * w;
+  v.Tf += (size_t)w0 * channels * kTStride; v.Tb += (size_t)w0 * channels * kTStride;
+  v.lut += (size_t)w0 * (kElevBins + 1); v.firstidx += (size_t)w0 * (kElevBins + 1);
+  v.hist += (size_t)w0 * T * kRingKeys;
+  v.cmin += (size_t)w0 * channels * kDegBins; v.cmax += (size_t)w0 * channels * kDegBins;
+  v.ne += (size_t)w0 * channels * (kDegBins + 1);
+  v.tab += w0;
   return v;
 }
+DevBuffers offset_view(const DevBuffers& a, int b0, int S, int T, int channels) { return slot_view(a, b0, b0, S, T, channels); }
 
 constexpr int kMaxKernels = 32;
+thread_local std::string g_create_err;
 
 int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want_order, bool first = true, bool last = true,
                     cudaStream_t st_override = nullptr) {
@@ -230,7 +248,10 @@ const char* urf_strerror(int code) {
   }
 }
 
-const char* urf_last_cuda_error(const urf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* urf_last_cuda_error(const urf_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  return g_create_err.empty() ? "null context" : g_create_err.c_str();     // text of this thread's last failed urf_create
+}
 
 void urf_default_params(urf_params* p) {
   if (!p) return;
@@ -253,7 +274,8 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return URF_ERR_NO_DEVICE;
   urf_ctx* ctx = new urf_ctx();
-  auto fail = [&](int rc) { std::string e = ctx->err; urf_destroy(ctx); (void)e; return rc; };
+  // the context dies with the failure: its error text survives in a per-thread slot that urf_last_cuda_error(NULL) returns
+  auto fail = [&](int rc) { g_create_err = ctx->err.empty() ? std::string(urf_strerror(rc)) : ctx->err; urf_destroy(ctx); return rc; };
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess) return fail(URF_ERR_NO_DEVICE);
   ctx->max_points = ((max_points + kChunk - 1) / kChunk) * kChunk;
@@ -308,6 +330,8 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   b.in = ctx->own_in;
   b.label = ctx->own_label;
   CKF(cudaMallocHost((void**)&ctx->h_n, sizeof(int) * max_batch));
+  CKF(cudaMallocHost((void**)&ctx->h_nring, sizeof(int) * max_batch * urf_ctx::kNRing));
+  for (int r = 0; r < urf_ctx::kNRing; r++) CKF(cudaEventCreateWithFlags(&ctx->ev_nring[r], cudaEventDisableTiming));
   CKF(cudaMallocHost((void**)&ctx->h_out, sizeof(ScanOut) * max_batch));
   {
     std::vector<float> ny;
@@ -340,9 +364,12 @@ void urf_destroy(urf_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->h_n) cudaFreeHost(ctx->h_n);
+  if (ctx->h_nring) cudaFreeHost(ctx->h_nring);
+  for (cudaEvent_t e : ctx->ev_nring) if (e) cudaEventDestroy(e);
   if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->h_packtot) cudaFreeHost(ctx->h_packtot);
   if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
+  if (ctx->bexec) cudaGraphExecDestroy(ctx->bexec);
   for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_comp) cudaEventDestroy(e);
@@ -381,24 +408,39 @@ int urf_get_params(const urf_ctx* ctx, urf_params* p) {
 
 // test/diagnostic options: 0 = force exact ring registration (0/1); 1 = per-kernel CUDA-event timing (slots, 0 = off);
 // 2 = number of compute streams a device-resident batch is spread over (1..4); 3 = CUDA graph for small batches (0/1);
-// 4 = near-first star sort (0/1, default 1)
+// 4 = near-first star sort (0/1, default 1); 5 = scans per sub-batch of a device-resident batch (0 = batch / streams);
+// 6 = replay the fork/join of a device-resident batch as one CUDA graph (0/1); 7 = sub-batches of a stream share one
+// workspace slot (0/1)
 int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (!ctx) return URF_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
   ctx->version++;
   if (option == 0) { ctx->dp.force_exact = value != 0; ctx->version++; return URF_OK; }
   if (option == 4) { ctx->dp.star_prefix = value != 0; ctx->version++; return URF_OK; }
   if (option == 3) { ctx->use_graph = value != 0; return URF_OK; }
   if (option == 2) { ctx->groups = value < 1 ? 1 : (value > urf_ctx::kGroups ? urf_ctx::kGroups : value); return URF_OK; }
+  if (option == 5) { ctx->sub = value < 0 ? 0 : value; return URF_OK; }
+  if (option == 6) { ctx->batch_graph = value != 0; return URF_OK; }
+  if (option == 7) { ctx->slot_reuse = value != 0; return URF_OK; }
   if (option == 1) {                   // value = number of event slots (0 = off)
-    if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
-  for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+    CK(cudaStreamSynchronize(ctx->stream));               // events of the previous setting may still be pending
+    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; ctx->g_B = -1; }
+    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
     ctx->kev.clear();
     ctx->profile = value > 0;
     ctx->kslots = value > 0 ? value : 1;
     ctx->kslot = 0;
     if (ctx->profile) {
-      ctx->kev.resize((size_t)ctx->kslots * (kMaxKernels + 1));
-      for (cudaEvent_t& e : ctx->kev) CK(cudaEventCreate(&e));
+      ctx->kev.assign((size_t)ctx->kslots * (kMaxKernels + 1), nullptr);
+      for (cudaEvent_t& e : ctx->kev) {
+        const cudaError_t ce = cudaEventCreate(&e);
+        if (ce != cudaSuccess) {                           // leave the option off and leak nothing
+          for (cudaEvent_t f : ctx->kev) if (f) cudaEventDestroy(f);
+          ctx->kev.clear(); ctx->profile = false; ctx->kslots = 1;
+          ctx->err = std::string("cudaEventCreate: ") + cudaGetErrorString(ce);
+          return URF_ERR_CUDA;
+        }
+      }
       ctx->knames.assign(kMaxKernels, "");
       ctx->kcounts.assign(ctx->kslots, 0);
     }
@@ -435,42 +477,83 @@ int urf_profile_get(urf_ctx* ctx, int slot, int idx, const char** name, float* m
   return URF_OK;
 }
 
-int urf_enqueue_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch, int32_t* d_label) {
+int urf_enqueue_batch_device_ex(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch, int32_t* d_label,
+                                int32_t* d_order) {
   if (!ctx || !d_xyzi || !n || !d_label || batch < 1 || stride_points < 1) return URF_ERR_INVALID;
   if (batch > ctx->max_batch || (size_t)stride_points * batch > ctx->P || stride_points > ctx->max_points) return URF_ERR_CAPACITY;
   CK(cudaSetDevice(ctx->device));
-  for (int b = 0; b < batch; b++) {
-    if (n[b] < 0 || n[b] > stride_points) return URF_ERR_INVALID;
-    ctx->h_n[b] = n[b];
-  }
-  CK(cudaMemcpyAsync(ctx->buf.n, ctx->h_n, sizeof(int) * batch, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->buf.in = reinterpret_cast<float4*>(const_cast<float*>(d_xyzi));
-  ctx->buf.label = d_label;
+  for (int b = 0; b < batch; b++) if (n[b] < 0 || n[b] > stride_points) return URF_ERR_INVALID;
+  int* row = ctx->h_nring + (size_t)ctx->nring_pos * ctx->max_batch;
+  CK(cudaEventSynchronize(ctx->ev_nring[ctx->nring_pos]));    // the copy that last used this row (kNRing enqueues ago) is done
+  std::memcpy(row, n, sizeof(int) * batch);
+  CK(cudaMemcpyAsync(ctx->buf.n, row, sizeof(int) * batch, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_nring[ctx->nring_pos], ctx->stream));
+  ctx->nring_pos = (ctx->nring_pos + 1) % urf_ctx::kNRing;
+  const bool want_order = d_order != nullptr;
+  DevBuffers bufv = ctx->buf;                                 // the caller's buffers instead of the context's own
+  bufv.in = reinterpret_cast<float4*>(const_cast<float*>(d_xyzi));
+  bufv.label = d_label;
+  if (want_order) bufv.order = d_order;
   int rc = URF_OK;
-  const int G = (ctx->profile || batch < 2 * ctx->groups) ? 1 : ctx->groups;     // per-kernel event timing needs one stream
-  if (G == 1) rc = launch_pipeline(ctx, ctx->buf, batch, stride_points, false);
+  const int T = (stride_points + kChunk - 1) / kChunk;
+  int sub = ctx->sub > 0 ? std::min(ctx->sub, batch) : (batch + ctx->groups - 1) / ctx->groups;
+  const int nsub = (batch + sub - 1) / sub;
+  const int G = (ctx->profile || batch < 2 * ctx->groups) ? 1 : std::min(ctx->groups, nsub);   // per-kernel event timing needs one stream
+  if (G == 1) rc = launch_pipeline(ctx, bufv, batch, stride_points, want_order);
   else {
-    // fork: the ctx stream hands sub-batches to the group streams and joins them again, so callers still see ONE stream
-    const int T = (stride_points + kChunk - 1) / kChunk;
+    // fork: the ctx stream hands sub-batches to the group streams (round-robin) and joins them again, so callers still see
+    // ONE stream. Scans are independent: a stream works through its sub-batches one after the other.
+    const bool reuse = ctx->slot_reuse;
+    auto fork_join = [&]() -> int {
+      CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+      int launches = 0;
+      for (int g = 0; g < G; g++) CK(cudaStreamWaitEvent(ctx->s_grp[g], ctx->ev_fork, 0));
+      for (int j = 0; j < nsub; j++) {
+        const int g = j % G, b0 = j * sub, nb = std::min(sub, batch - b0);
+        const int r = launch_pipeline(ctx, slot_view(bufv, b0, reuse ? g * sub : b0, stride_points, T, ctx->dp.channels), nb, stride_points,
+                                      want_order, false, false, ctx->s_grp[g]);
+        if (r != URF_OK) return r;
+        launches += ctx->launches;
+      }
+      for (int g = 0; g < G; g++) {
+        CK(cudaEventRecord(ctx->ev_join[g], ctx->s_grp[g]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
+      }
+      ctx->launches = launches;
+      return URF_OK;
+    };
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    int launches = 0;
-    for (int g = 0; g < G && rc == URF_OK; g++) {
-      const int b0 = (int)((long long)batch * g / G), b1 = (int)((long long)batch * (g + 1) / G);
-      CK(cudaStreamWaitEvent(ctx->s_grp[g], ctx->ev_fork, 0));
-      rc = launch_pipeline(ctx, offset_view(ctx->buf, b0, stride_points, T, ctx->dp.channels), b1 - b0, stride_points, false, false, false,
-                           ctx->s_grp[g]);
-      launches += ctx->launches;
-      CK(cudaEventRecord(ctx->ev_join[g], ctx->s_grp[g]));
-      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
+    if (!ctx->batch_graph) rc = fork_join();
+    else {
+      auto& k = ctx->bkey;
+      if (!ctx->bexec || k.B != batch || k.S != stride_points || k.sub != sub || k.G != G || k.order != (int)want_order || k.reuse != reuse ||
+          k.in != (const void*)d_xyzi || k.label != (void*)d_label || k.orderp != (void*)d_order || k.version != ctx->version) {
+        if (ctx->bexec) { cudaGraphExecDestroy(ctx->bexec); ctx->bexec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        rc = fork_join();
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != URF_OK || e != cudaSuccess || !graph) {
+          if (graph) cudaGraphDestroy(graph);
+          if (rc == URF_OK) { ctx->err = std::string("batch graph capture: ") + cudaGetErrorString(e); rc = URF_ERR_CUDA; }
+        } else {
+          const cudaError_t ei = cudaGraphInstantiate(&ctx->bexec, graph, 0);
+          cudaGraphDestroy(graph);
+          if (ei != cudaSuccess) { ctx->bexec = nullptr; ctx->err = cudaGetErrorString(ei); rc = URF_ERR_CUDA; }
+          else { k.B = batch; k.S = stride_points; k.sub = sub; k.G = G; k.order = (int)want_order; k.reuse = reuse; k.in = d_xyzi; k.label = d_label; k.orderp = d_order;
+                 k.version = ctx->version; k.launches = ctx->launches; }
+        }
+      }
+      if (rc == URF_OK) { CK(cudaGraphLaunch(ctx->bexec, ctx->stream)); ctx->launches = ctx->bkey.launches; }
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->launches = launches;
   }
-  ctx->buf.in = ctx->own_in;
-  ctx->buf.label = ctx->own_label;
   ctx->last_B = batch; ctx->last_S = stride_points;
   return rc;
+}
+
+int urf_enqueue_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_points, const int* n, int batch, int32_t* d_label) {
+  return urf_enqueue_batch_device_ex(ctx, d_xyzi, stride_points, n, batch, d_label, nullptr);
 }
 
 int urf_finish_batch_device(urf_ctx* ctx, urf_result* outs) {
@@ -534,7 +617,10 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
     const DevBuffers view = offset_view(ctx->buf, b0, S, T, ctx->dp.channels);
     int rc = (nchunks == 1 && batch <= 8) ? launch_pipeline_graphed(ctx, nb, S, want_order)
                                           : launch_pipeline(ctx, view, nb, S, want_order, c == 0, c == nchunks - 1);
-    if (rc != URF_OK) return rc;
+    if (rc != URF_OK) {                                 // nothing of this call may still be writing into the caller's buffers
+      cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->s_out);
+      return rc;
+    }
     if (want_ring) k_ring32<<<dim3((S + 255) / 256, nb), 256, 0, st>>>(view, ring32 + (size_t)b0 * S * 4, S);
     CK(cudaEventRecord(ctx->ev_comp[c], st));
     CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[c], 0));

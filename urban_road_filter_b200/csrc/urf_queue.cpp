@@ -166,17 +166,26 @@ int urf_queue_submit(urf_queue* q, const float* xyzi, int n, uint64_t tag, int t
     q->slots[slot].state = FILLING;                       // a dropped scan's sequence number simply never reaches DONE
   }
   Slot& s = q->slots[slot];
+  bool closed_late = false;
   if (n > 0) std::memcpy(s.in, xyzi, sizeof(float) * 4 * (size_t)n);
   {
     std::lock_guard<std::mutex> lk(q->mu);
     if (q->closed) {                                      // closed while copying: the worker may already be gone
       s.state = FREE;
-      return URF_ERR_CLOSED;
+      closed_late = true;
+    } else {
+      s.n = n; s.tag = tag; s.rc = URF_OK;
+      s.seq = q->next_seq++;
+      s.state = PENDING;
+      q->st.submitted++;
     }
-    s.n = n; s.tag = tag; s.rc = URF_OK;
-    s.seq = q->next_seq++;
-    s.state = PENDING;
-    q->st.submitted++;
+  }
+  if (closed_late) {
+    // a consumer whose last look at the slots still saw this one FILLING must get to see the drained state: close()'s
+    // own notify may have come before that look
+    q->cv_done.notify_all();
+    q->cv_free.notify_one();
+    return URF_ERR_CLOSED;
   }
   q->cv_pending.notify_one();
   q->cv_done.notify_all();                                // a consumer waiting on a dropped sequence number re-evaluates
