@@ -40,9 +40,18 @@ ALGO_BYTES_PER_POINT = 20          # 16 B float4 read + 4 B in
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+_ABLATION = {}          # detector switches of BASELINE config 5 (--no-star / --no-xzero / --no-zzero), shared with the CPU workers
+
+
 def bench_params(shape_key: str):
     sh = SHAPES[shape_key]
-    return make_params(channels=sh.channels, interval=sh.interval, **FULL_ROI)
+    return make_params(channels=sh.channels, interval=sh.interval, **_ABLATION, **FULL_ROI)
+
+
+def detectors_text() -> str:
+    on = [name for name, key in (("star", "star_shaped_method"), ("x_zero", "x_zero_method"), ("z_zero", "z_zero_method"))
+          if _ABLATION.get(key, 1)]
+    return ("all three detectors" if len(on) == 3 else ("detectors: " + "+".join(on) if on else "no curb detector")) + " + blindSpots"
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -52,8 +61,9 @@ def bench_params(shape_key: str):
 _W = {}
 
 
-def _cpu_init(shape_key, seed0, use_ref, counter):
+def _cpu_init(shape_key, seed0, use_ref, counter, ablation=None):
     sys.path.insert(0, ROOT)
+    _ABLATION.update(ablation or {})
     from oracle.pyoracle import PortOracle, RefOracle
     with counter.get_lock():
         wid = counter.value
@@ -75,7 +85,7 @@ class CpuReference:
         self.use_ref = RefOracle.available()
         self.workers = workers
         ctx = mp.get_context("fork" if not _cuda_initialised() else "spawn")
-        self.pool = ctx.Pool(workers, initializer=_cpu_init, initargs=(shape_key, seed0, self.use_ref, ctx.Value("i", 0)))
+        self.pool = ctx.Pool(workers, initializer=_cpu_init, initargs=(shape_key, seed0, self.use_ref, ctx.Value("i", 0), dict(_ABLATION)))
         self.pool.map(_cpu_step, [0] * workers)          # make sure every worker is initialised
 
     @property
@@ -214,6 +224,7 @@ def run_reference_arm(args):
         return 0            # the reference arm is a host-CPU measurement: rank 0 alone runs and prints it
     cores = usable_cores(args.shape)
     n = SHAPES[args.shape].rings * SHAPES[args.shape].cols
+    single_rate, single_ms, _ = cpu_reference_rate(args.shape, 1, 2, seed0=30_000)
     ref = CpuReference(args.shape, cores, seed0=20_000)
     kind = ref.kind
     for _ in range(args.warmup):
@@ -227,11 +238,13 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": f"{SHAPES[args.shape].name} {n}-pt scans, all three detectors + blindSpots, full-ROI preset "
+        "config": {"workload": f"{SHAPES[args.shape].name} {n}-pt scans, {detectors_text()}, full-ROI preset "
                                f"({args.shape}); one step = {cores} scans, one per host core",
                    "points_per_scan": n, "mpoints_per_sec": value * n / 1e6},
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": kind,
-                         "sample": f"{cores} single-threaded processes x 1 scan per step, median of {args.steps} steps"},
+                         "sample": f"{cores} single-threaded processes x 1 scan per step, median of {args.steps} steps",
+                         "single_process": {"value": single_rate, "unit": "scans/s", "ms_per_scan": single_ms, "cores": 1,
+                                            "sample": "1 process x 2 scans after one untimed scan"}},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,7 +255,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="default: 200 (urf), 10 (reference)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="urf", choices=["urf", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="scans per step and per GPU")
@@ -255,8 +268,17 @@ def main():
     ap.add_argument("--graph", type=int, default=-1, help="replay a device-resident step as one CUDA graph (library option 6)")
     ap.add_argument("--reuse", type=int, default=-1, help="sub-batches of a stream share a workspace slot (library option 7)")
     ap.add_argument("--sweep", default="", help="tuning: ';'-separated groups,sub,graph,reuse settings timed one after the other")
+    ap.add_argument("--no-star", action="store_true", help="detector ablation (BASELINE config 5): star_shaped_method off")
+    ap.add_argument("--no-xzero", action="store_true", help="detector ablation: x_zero_method off")
+    ap.add_argument("--no-zzero", action="store_true", help="detector ablation: z_zero_method off")
+    ap.add_argument("--no-with-order", action="store_true", help="skip the second timed pass that also produces the emission order")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "urf" else args.warmup
+    if args.steps is None:
+        args.steps = 200 if args.impl == "urf" else 10
+    for flag, key in ((args.no_star, "star_shaped_method"), (args.no_xzero, "x_zero_method"), (args.no_zzero, "z_zero_method")):
+        if flag:
+            _ABLATION[key] = 0
 
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -269,8 +291,13 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = usable_cores(args.shape)
+        # (i) ONE process alone on the box: the stable anchor (the reference node is single-threaded, src/main.cpp:54);
+        # (ii) one process per core, which on some hosts is bound by page faults on the reference's channels x N x 48 B array
+        single_rate, single_ms, _ = cpu_reference_rate(args.shape, 1, 2)
         rate, per_scan_ms, kind = cpu_reference_rate(args.shape, cores, args.cpu_repeat)
         cpu_baseline = {"value": rate, "unit": "scans/s", "cores": cores, "kind": kind,
+                        "single_process": {"value": single_rate, "unit": "scans/s", "ms_per_scan": single_ms, "cores": 1,
+                                           "sample": "1 process x 2 scans after one untimed scan"},
                         "sample": f"{cores} single-threaded processes x {args.cpu_repeat} scans each (after one untimed scan), "
                                   f"median {per_scan_ms:.0f} ms per scan per core"}
 
@@ -356,6 +383,29 @@ def main():
     assert lib.urf_finish_batch_device(ctx, outs) == 0
     launches = det.last_launch_count() * args.steps
     n_road = sum(o.n_road for o in outs)
+    # ---- timed region 1w: the same K steps with the per-ring azimuth sort (lidar_segmentation.cpp:289-291) and the emission
+    # ---- order written to HBM: what the node needs to publish its clouds, on top of labels + vertices
+    with_order = None
+    if not args.no_with_order:
+        order = torch.empty((B, S), dtype=torch.int32, device="cuda")
+
+        def step_order():
+            rc = lib.urf_enqueue_batch_device_ex(ctx, x.data_ptr(), S, ns, B, labels.data_ptr(), order.data_ptr())
+            assert rc == 0, lib.urf_last_cuda_error(ctx)
+
+        for _ in range(3):
+            step_order()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        for _ in range(args.steps):
+            step_order()
+        w1.record(stream)
+        barrier()
+        with_order = {"dev_ms": w0.elapsed_time(w1)}
+        assert lib.urf_finish_batch_device(ctx, outs) == 0
+        assert sum(o.n_road for o in outs) == n_road
+        del order
     # ---- timed region 1b: the same steps once more on ONE stream with a CUDA event in front of every kernel (per-kernel
     # ---- durations are only meaningful without inter-stream overlap); feeds the roofline block, not `value`
     kprof = min(args.steps, 5)
@@ -400,6 +450,21 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    if with_order is not None:               # the same call with res[b].order set: the order comes back too (+4 B per point)
+        h_ord = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(B)]
+        for b in range(B):
+            res[b].order = C.cast(h_ord[b].data_ptr(), C.POINTER(C.c_int32))
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        with_order["e2e_ms"] = (time.perf_counter() - t0) * 1e3
+        barrier()
+        for b in range(B):
+            res[b].order = None
     t_w2 = time.time()
     clocks = sampler.stop(t_w0, t_w2) if sampler else None
     print(f"[rank {rank}] device {dev_ms / args.steps:.3f} ms/step, e2e {1e3 * e2e_s / args.steps:.3f} ms/step", file=sys.stderr)
@@ -407,6 +472,8 @@ def main():
 
     # max over ranks
     dev_ms, e2e_ms = allreduce_max([dev_ms, e2e_s * 1e3], device="cuda")
+    if with_order is not None:
+        with_order["dev_ms"], with_order["e2e_ms"] = allreduce_max([with_order["dev_ms"], with_order["e2e_ms"]], device="cuda")
     total_road = allreduce_sum([n_road], device="cuda")[0]
 
     if rank == 0:
@@ -424,7 +491,7 @@ def main():
             "metric": "scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
             "data": "synthetic",
-            "config": {"workload": f"{sh.name} {n}-pt scans, all three detectors + blindSpots, full-ROI preset (BASELINE config 2); "
+            "config": {"workload": f"{sh.name} {n}-pt scans, {detectors_text()}, full-ROI preset (BASELINE config {args.shape[1:]}); "
                                    f"one step = a batch of {B} distinct scans per GPU",
                        "batch_per_gpu": B, "points_per_scan": n, "mpoints_per_sec": value * n / 1e6,
                        "l2": f"inputs of one step are {B * n * 16 / 2**20:.0f} MiB per GPU (> 126 MB L2), no reuse between steps",
@@ -443,6 +510,10 @@ def main():
                          "kernel_ms_per_step": {k: v for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])}},
             "clocks": clocks,
         }
+        if with_order is not None:           # labels + vertices + emission order (k_sort_rings inside the timed region)
+            line["with_order"] = {"value": scans / (with_order["dev_ms"] / 1e3), "unit": "scans/s", "ms_per_step": with_order["dev_ms"] / K,
+                                  "e2e": {"value": scans / (with_order["e2e_ms"] / 1e3), "unit": "scans/s", "h2d_bytes_per_step": B * n * 16,
+                                          "d2h_bytes_per_step": 2 * B * n * 4 + B * C.sizeof(UrfResult)}}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)

@@ -175,6 +175,17 @@ int urf_process_cloud2_packed(urf_ctx* ctx, const void* data, int n_points, int 
 /* `batch` independent scans (distinct clouds, same params), HOST buffers. xyzi[b] has n[b] points; outs[b] as above. */
 int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int batch, urf_result* outs);
 
+/* Lean variants for callers that are bound by PCIe (opt-in additions; urf_process_batch above stays the drop-in for
+ * Detector::filtered): the label path never reads intensity and a label is one of four values, so
+ *   urf_process_batch_xyz   takes packed (x, y, z) FLOAT32 triples — 12 bytes per point cross PCIe instead of 16 — and
+ *   label8[b] (int8 HOST buffers of n[b] bytes, or label8 == NULL / label8[b] == NULL) receives the labels as one byte per
+ *   point (same URF_LABEL_* values) instead of four. outs[b].label / ring / order are still honoured when non-NULL.
+ *   urf_process_cloud2_batch is urf_process_cloud2 for `batch` scans of one sensor format: the raw PointCloud2 records of
+ *   every scan cross PCIe as they are and are unpacked on the device (off_intensity < 0: no intensity field). */
+int urf_process_batch_xyz(urf_ctx* ctx, const float* const* xyz, const int* n, int batch, urf_result* outs, int8_t* const* label8);
+int urf_process_cloud2_batch(urf_ctx* ctx, const void* const* data, const int* n_points, int batch, int point_step, int off_x,
+                             int off_y, int off_z, int off_intensity, urf_result* outs, int8_t* const* label8);
+
 /* Device-resident variant used to time the kernels without PCIe: d_xyzi is a DEVICE pointer to the scans stored back to
  * back (scan b starts at point offset b*stride_points, has n[b] points), d_label a DEVICE pointer with the same layout
  * (int32 per point) that receives the labels. Small per-scan metadata (counts, vertices) is still returned in outs[b]
@@ -247,11 +258,52 @@ void urf_queue_close(urf_queue* q);
  * may be inside a urf_queue_* call on this queue any more: close first, let producers and consumers return, then destroy. */
 void urf_queue_destroy(urf_queue* q);
 
+/* As urf_queue_submit, but the scan is NOT copied: `xyzi` is used in place by the worker's host-to-device copy and must stay
+ * valid and unchanged until the scan's result has been delivered by urf_queue_next (pinned memory — urf_pinned_alloc —
+ * gives asynchronous copies at full PCIe rate). Removes the producer-side memcpy, the host limiter of a single ingest thread. */
+int urf_queue_submit_ref(urf_queue* q, const float* xyzi, int n, uint64_t tag, int timeout_ms);
+
+/* A queue whose scans are raw sensor_msgs/PointCloud2 records of ONE sensor format (what the node's subscriber receives,
+ * lidar_segmentation.cpp:53,95): producers hand in the `data` bytes of a message with urf_queue_submit_cloud2, the worker
+ * runs everything pending through urf_process_cloud2_batch (records unpacked on the device). urf_queue_next as above. */
+int urf_queue_create_cloud2(urf_queue** out, urf_ctx* ctx, int max_points, int slots, int max_batch, int policy, int point_step,
+                            int off_x, int off_y, int off_z, int off_intensity);
+int urf_queue_submit_cloud2(urf_queue* q, const void* data, int n_points, uint64_t tag, int timeout_ms);
+
 /* Test hook: the same queue around a caller-supplied batch function with urf_process_batch's signature (`user` is passed
  * as its ctx argument) and malloc'ed instead of pinned staging — the queue mechanics can then be exercised without a GPU. */
 typedef int (*urf_queue_process_fn)(void* user, const float* const* xyzi, const int* n, int batch, urf_result* outs);
 int urf_queue_create_with(urf_queue** out, urf_queue_process_fn fn, void* user, int max_points, int slots, int max_batch,
                           int policy);
+
+/*
+ * Multi-GPU ingest (BASELINE config 4: one continuous scan stream sharded across the GPUs of a box). The reference is one
+ * subscriber in one process (lidar_segmentation.cpp:53); urf_mq is one submit / next interface over N devices: it creates
+ * a context and a urf_queue (above) per device, hands every scan to the device with the fewest scans in flight, and
+ * delivers the results in the order the submissions completed. Scans are independent, so no data moves between devices.
+ * Any number of producer threads; ONE consumer thread. urf_mq_submit_ref is the no-copy variant (see urf_queue_submit_ref).
+ * urf_mq_set_params applies to all devices and is only accepted while nothing is in flight (like the reference's
+ * paramsCallback between two scan callbacks).
+ */
+typedef struct urf_mq urf_mq;
+#define URF_MQ_MAX_DEVICES 16
+typedef struct urf_mq_stats {
+  int32_t  n_devices, pending;
+  uint64_t submitted[URF_MQ_MAX_DEVICES], delivered[URF_MQ_MAX_DEVICES], batches[URF_MQ_MAX_DEVICES];
+  int32_t  largest_batch[URF_MQ_MAX_DEVICES];
+} urf_mq_stats;
+int urf_mq_create(urf_mq** out, const int* devices, int n_devices, int max_points, int slots_per_device, int max_batch,
+                  const urf_params* params /* or NULL: cfg defaults */);
+int urf_mq_set_params(urf_mq* mq, const urf_params* p);
+int urf_mq_submit(urf_mq* mq, const float* xyzi, int n, uint64_t tag, int timeout_ms);
+int urf_mq_submit_ref(urf_mq* mq, const float* xyzi, int n, uint64_t tag, int timeout_ms);
+int urf_mq_next(urf_mq* mq, uint64_t* tag, urf_result* out, int timeout_ms);
+int urf_mq_get_stats(urf_mq* mq, urf_mq_stats* st);
+void urf_mq_close(urf_mq* mq);
+void urf_mq_destroy(urf_mq* mq);
+/* Test hook: N stand-in devices around a caller-supplied batch function (users[j] is passed to it for device j). */
+int urf_mq_create_with(urf_mq** out, urf_queue_process_fn fn, void* const* users, int n_devices, int max_points,
+                       int slots_per_device, int max_batch);
 
 const char* urf_strerror(int code);
 /* Text of the last failed CUDA call of `ctx`; with ctx == NULL: why this thread's last urf_create failed. */

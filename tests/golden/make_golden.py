@@ -44,6 +44,12 @@ CASES = [
     ("c2_full_ring_s1", dict(kind="scan", shape="C2", seed=1, order="ring"), False, dict(**FULL_ROI)),
     ("c3_full_s0", dict(kind="scan", shape="C3", seed=0, order="column"), False, dict(**FULL_ROI)),
     ("c4_full_s0", dict(kind="scan", shape="C4", seed=0, order="column"), False, dict(channels=128, interval=0.07, **FULL_ROI)),
+    # BASELINE config 5 (256 rings x 4096 columns = 1,048,576 points) and its detector ablation. The reference needs 12.9 GB
+    # for its channels x N array3D and about 80 s per call here (page faults + its O(n^2) ring sort): run with --only c5
+    ("c5_full_s0", dict(kind="scan", shape="C5", seed=0, order="column"), False, dict(channels=256, interval=0.07, **FULL_ROI)),
+    ("c5_full_staronly", dict(kind="scan", shape="C5", seed=0, order="column"), False, dict(channels=256, interval=0.07, x_zero_method=0, z_zero_method=0, **FULL_ROI)),
+    ("c5_full_xonly", dict(kind="scan", shape="C5", seed=0, order="column"), False, dict(channels=256, interval=0.07, star_shaped_method=0, z_zero_method=0, **FULL_ROI)),
+    ("c5_full_zonly", dict(kind="scan", shape="C5", seed=0, order="column"), False, dict(channels=256, interval=0.07, star_shaped_method=0, x_zero_method=0, **FULL_ROI)),
 ]
 
 
@@ -64,10 +70,13 @@ def strips_to_arrays(strips):
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""      # name prefix; default: everything but c5
     ref = RefOracle()
     env = dict(machine=platform.machine(), libc=" ".join(platform.libc_ver()), python=platform.python_version(),
                numpy=np.__version__)
     for name, recipe, store, over in CASES:
+        if (only and not name.startswith(only)) or (not only and name.startswith("c5")):
+            continue
         pts = cloud_from_recipe(recipe)
         sha = hashlib.sha256(pts.tobytes()).hexdigest()
         r0 = ref.run(pts, make_params(simple_poly_allow=0, poly_z_avg_allow=0, **over), ghostcount=0)

@@ -65,14 +65,20 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
   int flags = 0;
 
   // ---- k_points
-  std::vector<float> alpha(n, -1.0f);
+  std::vector<float> alpha(n, -1.0f), az(n, 0.f), d2(n, 0.f);      // az / d2: input order, ROI points only
   std::vector<unsigned> firstidx(kElevBins + 1, 0xffffffffu);
   int n_roi = 0;
   for (int i = 0; i < n; i++) {
     const float x = xyzi[4 * i], y = xyzi[4 * i + 1], z = xyzi[4 * i + 2];
     if (!roi_keep(prm, x, y, z)) continue;
     n_roi++;
-    const float a = elev_alpha(x, y, z);
+    float a;
+    point_angles(x, y, z, &a, &d2[i], &az[i]);
+    {                                      // the shared-squares form must agree with the two separate reference expressions
+      float d_ref, az_ref;
+      planar_az(x, y, &d_ref, &az_ref);
+      if (fbits(a) != fbits(elev_alpha(x, y, z)) || fbits(d_ref) != fbits(d2[i]) || fbits(az_ref) != fbits(az[i])) return -101;
+    }
     alpha[i] = a;
     const int bin = elev_bin(a);
     if (firstidx[bin] > (unsigned)i) firstidx[bin] = (unsigned)i;
@@ -138,8 +144,6 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     publish();
     assign_all(false);
   }
-  if (out->label) for (int i = 0; i < n; i++) if (alpha[i] >= 0.0f) out->label[i] = URF_LABEL_NONE;
-
   // ---- k_scan_offsets + k_scatter (stable partitions)
   std::vector<int> ring_start(kRingKeys + 1, 0), sect_start(kSectKeys + 1, 0);
   for (int i = 0; i < n; i++) { if (ringid[i] >= 0) ring_start[ringid[i] + 1]++; if (sect[i] >= 0) sect_start[sect[i] + 1]++; }
@@ -176,44 +180,48 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     }
   }
 
-  // ---- k_ring_detect
-  std::vector<float> az(std::max(N, 1)), d2(std::max(N, 1));
-  std::vector<unsigned char> blabel(std::max(N, 1), 0);
+  // ---- k_star_scan's curb_hit + k_ring_detect
   const size_t nb = (size_t)prm.channels * kDegBins;
   std::vector<unsigned> cmin(nb, 0x7f800000u), cmax(nb, 0u);
   std::vector<unsigned short> ne((size_t)prm.channels * (kDegBins + 1), 0);
-  for (int k = 0; k < kRingKeys; k++) tab.maxdist[k] = 0u;
+  auto curb_hit = [&](int idx, int k) {
+    mark[idx] = 2;
+    if (k < 0) k = ringid[idx];
+    if (k < 0) return;
+    const float a = az[idx];
+    if (a >= 0.0f) {
+      const size_t o = (size_t)k * kDegBins + deg_bin(a);
+      if (fbits(a) < cmin[o]) cmin[o] = fbits(a);
+      if (fbits(a) > cmax[o]) cmax[o] = fbits(a);
+    }
+  };
+  std::vector<unsigned char> star_mark(mark);           // the star search alone (debug output)
+  for (int i = 0; i < n; i++) if (star_mark[i] == 2) curb_hit(i, -1);
+  for (int k = 0; k < kRingKeys; k++) { tab.maxs[k] = 0ull; tab.maxdist[k] = 0u; }
   for (int k = 0; k < R; k++) {
     const int base = ring_start[k], m = ring_start[k + 1] - base;
     const float4* ring = bpt.data() + base;
+    unsigned maxd_ref = 0u;
     for (int t = 0; t < m; t++) {
-      float d, a;
-      planar_az(ring[t].x, ring[t].y, &d, &a);
-      az[base + t] = a; d2[base + t] = d;
-      if (fbits(d) > tab.maxdist[k]) tab.maxdist[k] = fbits(d);
       const int idx = URF_F2I(ring[t].w);
-      int lab = prm.star ? mark[idx] : 0;
-      if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, m, t, newY.data())) lab = 2;
-      if (prm.z_zero && lab != 2 && (prm.curbPoints == 5 ? zzero_mark_t<5>(prm, ring, m, t) : zzero_mark_t<0>(prm, ring, m, t))) lab = 2;
-      blabel[base + t] = (unsigned char)lab;
-      if (lab == 2 && a >= 0.0f) {
-        const size_t o = (size_t)k * kDegBins + deg_bin(a);
-        if (fbits(a) < cmin[o]) cmin[o] = fbits(a);
-        if (fbits(a) > cmax[o]) cmax[o] = fbits(a);
-      }
+      tab.maxs[k] = std::max(tab.maxs[k], planar_sum_bits(ring[t].x, ring[t].y));
+      maxd_ref = std::max(maxd_ref, fbits(d2[idx]));
+      const bool hit = (prm.x_zero && xzero_mark(prm, ring, m, t, newY.data())) ||
+                       (prm.z_zero && (prm.curbPoints == 5 ? zzero_mark_t<5>(prm, ring, m, t) : zzero_mark_t<0>(prm, ring, m, t)));
+      if (hit) curb_hit(idx, k);
     }
+    tab.maxdist[k] = fbits(maxdist_from_bits(tab.maxs[k]));        // k_tab1
+    if (tab.maxdist[k] != maxd_ref) return -102;                   // max of the sums first, one square root after: same value
   }
   if (dbg) {
     for (int i = 0; i < n; i++) {
       if (alpha[i] < 0.0f) continue;
       if (dbg->alpha_v) dbg->alpha_v[i] = alpha[i];
-      if (dbg->star_mark) dbg->star_mark[i] = (int8_t)mark[i];
-    }
-    for (int p = 0; p < N; p++) {
-      const int idx = URF_F2I(bpt[p].w);
-      if (dbg->az) dbg->az[idx] = az[p];
-      if (dbg->d2) dbg->d2[idx] = d2[p];
-      if (dbg->det_label) dbg->det_label[idx] = (int8_t)blabel[p];
+      if (dbg->star_mark) dbg->star_mark[i] = (int8_t)star_mark[i];
+      if (ringid[i] < 0) continue;
+      if (dbg->az) dbg->az[i] = az[i];
+      if (dbg->d2) dbg->d2[i] = d2[i];
+      if (dbg->det_label) dbg->det_label[i] = (int8_t)mark[i];
     }
     for (int k = 0; k < R; k++) {
       if (dbg->ring_angle) dbg->ring_angle[k] = tab.angle[k];
@@ -258,42 +266,41 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
         }
   }
 
-  // ---- k_label, k_dmax, k_best, k_verts
-  for (int i = 0; i < kDegBins; i++) { tab.cutbest[i] = ~0ull; tab.dmax[i] = 0u; tab.best[i] = ~0ull; }
-  std::vector<int> pring(std::max(N, 1));
-  for (int k = 0; k < R; k++) for (int p = ring_start[k]; p < ring_start[k + 1]; p++) pring[p] = k;
+  // ---- k_label (input order), k_dmax, k_best, k_verts
+  std::vector<unsigned> dmax(kDegBins, 0u);                     // k_markers keeps these two in the cluster's shared memory
+  std::vector<unsigned long long> best(kDegBins, ~0ull);
+  for (int i = 0; i < kDegBins; i++) tab.cutbest[i] = ~0ull;
   int formulation_mismatch = 0;
   std::vector<int> road;
-  for (int p = 0; p < N; p++) {
-    const int k = pring[p];
-    int lab = blabel[p];
-    const bool cov = covered_T(Tf.data(), Tb.data(), k, az[p]);
-    if (cov != covered_by_window(prm, *spm, tab.A[k], k, az[p])) formulation_mismatch++;
-    if (lab != 2 && cov) lab = 1;
-    blabel[p] = (unsigned char)lab;
-    const int idx = URF_F2I(bpt[p].w);
-    if (out->label) out->label[idx] = lab;
-    if (out->ring) out->ring[idx] = k;
-    if (lab == 1) { out->n_road++; road.push_back(p); } else if (lab == 2) out->n_curb++;
-    if (lab != 1 && az[p] >= 0.0f) { const int bin = deg_bin(az[p]); tab.cutbest[bin] = std::min(tab.cutbest[bin], best_key(k, fbits(az[p]), p)); }
+  for (int i = 0; i < n; i++) {
+    const int k = ringid[i];
+    if (alpha[i] < 0.0f) continue;                       // label stays URF_LABEL_OUTSIDE
+    if (k < 0) { if (out->label) out->label[i] = URF_LABEL_NONE; continue; }
+    const bool cov = covered_T(Tf.data(), Tb.data(), k, az[i]);
+    if (cov != covered_by_window(prm, *spm, tab.A[k], k, az[i])) formulation_mismatch++;
+    const int lab = mark[i] == 2 ? 2 : cov ? 1 : 0;
+    if (out->label) out->label[i] = lab;
+    if (out->ring) out->ring[i] = k;
+    if (lab == 1) { out->n_road++; road.push_back(i); } else if (lab == 2) out->n_curb++;
+    if (lab != 1 && az[i] >= 0.0f) { const int bin = deg_bin(az[i]); tab.cutbest[bin] = std::min(tab.cutbest[bin], best_key(k, fbits(az[i]), i)); }
   }
   if (formulation_mismatch) return -100;      // threshold tables disagree with the window search: a logic bug
-  for (int p : road) {
-    if (!(az[p] >= 0.0f)) continue;
-    const int bin = deg_bin(az[p]);
-    if (marker_candidate(tab.cutbest[bin], pring[p], fbits(az[p]), p)) tab.dmax[bin] = std::max(tab.dmax[bin], fbits(d2[p]));
+  for (int i : road) {
+    if (!(az[i] >= 0.0f)) continue;
+    const int bin = deg_bin(az[i]);
+    if (marker_candidate(tab.cutbest[bin], ringid[i], fbits(az[i]), i)) dmax[bin] = std::max(dmax[bin], fbits(d2[i]));
   }
-  for (int p : road) {
-    if (!(az[p] >= 0.0f)) continue;
-    const int bin = deg_bin(az[p]);
-    if (fbits(d2[p]) != 0u && fbits(d2[p]) == tab.dmax[bin] && marker_candidate(tab.cutbest[bin], pring[p], fbits(az[p]), p))
-      tab.best[bin] = std::min(tab.best[bin], best_key(pring[p], fbits(az[p]), p));
+  for (int i : road) {
+    if (!(az[i] >= 0.0f)) continue;
+    const int bin = deg_bin(az[i]);
+    if (fbits(d2[i]) != 0u && fbits(d2[i]) == dmax[bin] && marker_candidate(tab.cutbest[bin], ringid[i], fbits(az[i]), i))
+      best[bin] = std::min(best[bin], best_key(ringid[i], fbits(az[i]), i));
   }
   int cM = 0;
   for (int i = 0; i < kDegBins; i++) {
-    if (tab.best[i] == ~0ull) continue;
-    const int p = (int)(tab.best[i] & 0xffffffull);
-    out->vert[cM][0] = bpt[p].x; out->vert[cM][1] = bpt[p].y; out->vert[cM][2] = bpt[p].z;
+    if (best[i] == ~0ull) continue;
+    const int p = (int)(best[i] & 0xffffffull);
+    out->vert[cM][0] = xyzi[4 * p]; out->vert[cM][1] = xyzi[4 * p + 1]; out->vert[cM][2] = xyzi[4 * p + 2];
     out->vert[cM][3] = tab.cutbest[i] != ~0ull ? 1.0f : 0.0f;
     cM++;
   }
@@ -304,7 +311,7 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
   for (int k = 0; k < R; k++) {
     const int base = ring_start[k], m = ring_start[k + 1] - base;
     std::vector<unsigned long long> keys(m);
-    for (int t = 0; t < m; t++) keys[t] = ((unsigned long long)fbits(az[base + t]) << 32) | (unsigned)t;
+    for (int t = 0; t < m; t++) keys[t] = ((unsigned long long)fbits(az[URF_F2I(bpt[base + t].w)]) << 32) | (unsigned)t;
     std::sort(keys.begin(), keys.end());
     for (int t = 0; t < m; t++) {
       if (out->order) out->order[base + t] = URF_F2I(bpt[base + (unsigned)keys[t]].w);

@@ -38,13 +38,12 @@ class GpuDebug:
         self.__dict__.update(res.__dict__ if hasattr(res, "__dict__") else {s: getattr(res, s) for s in res.__slots__})
         a = det.debug_fetch(0, 0, np.float32, n)
         self.alpha_v = np.where(a < 0, np.nan, a).astype(np.float32)
-        self.star_mark = det.debug_fetch(0, 1, np.uint8, n).astype(np.int8)
-        idx = det.debug_fetch(0, 7, np.int32, N)
-        self.az = np.full(n, np.nan, np.float32)
-        self.d2 = np.full(n, np.nan, np.float32)
-        self.az[idx] = det.debug_fetch(0, 4, np.float32, N)
-        self.d2[idx] = det.debug_fetch(0, 5, np.float32, N)
-        self.det_label = None      # blabel is overwritten with final labels by k_label
+        ring = det.debug_fetch(0, 2, np.int16, n)
+        in_ring = ring >= 0
+        self.az = np.where(in_ring, det.debug_fetch(0, 4, np.float32, n), np.float32(np.nan)).astype(np.float32)
+        self.d2 = np.where(in_ring, det.debug_fetch(0, 5, np.float32, n), np.float32(np.nan)).astype(np.float32)
+        self.star_mark = None      # the device keeps one mark for all three detectors
+        self.det_label = np.where(in_ring, det.debug_fetch(0, 1, np.uint8, n).astype(np.int8), np.int8(-1)).astype(np.int8)
         self.ring_angle = None
 
 
@@ -128,6 +127,28 @@ def test_gpu_edge_cases(det, port):
     check(det, port, make_scan("C1", 0), make_params(min_x=100, max_x=101))      # empty ROI
     with pytest.raises(api.UrfError):
         det.filtered(np.zeros((400_000, 4), np.float32))                         # larger than the ctx capacity
+
+
+def test_gpu_profile_option_after_graphed_call(port):
+    """urf_set_option(1, ...) after a CUDA-graph replay: the graph handle is dropped and rebuilt, nothing is destroyed twice
+    (the documented flow filtered -> set_option(1, n) -> kernel_times -> set_option(1, 0) -> filtered -> close)."""
+    d = api.Detector(max_points=30_000, max_batch=2)
+    try:
+        prm = make_params(**FULL_ROI)
+        d.set_params(prm)
+        pts = make_scan("C1", 12)
+        o = port.run(pts, prm)
+        assert np.array_equal(d.filtered(pts).label, o.label)          # captures the graph
+        d.set_option(1, 2)
+        assert np.array_equal(d.filtered(pts).label, o.label)          # per-kernel events, no graph
+        names = [k for k, _ in d.kernel_times(0)]
+        assert "k_ring_detect" in names and "k_label" in names
+        d.set_option(1, 0)
+        d.set_option(1, 0)
+        assert np.array_equal(d.filtered(pts).label, o.label)          # graph captured again
+        d.set_option(1, 1)
+    finally:
+        d.close()
 
 
 def test_gpu_batch_equals_single(det, port):
@@ -230,6 +251,36 @@ def test_gpu_fallback_paths_big_sector_big_ring_large_cp(det, port):
     check(det, port, make_scan("C2", 6, order="ring"), make_params(curb_points=33, beamZone=12.5, **FULL_ROI))
 
 
+def _one_ring_cloud(az_deg, seed):
+    rng = np.random.default_rng(seed)
+    n = len(az_deg)
+    az = np.deg2rad(np.asarray(az_deg, np.float64))
+    t = rng.uniform(2.0, 50.0, n)
+    e = np.deg2rad(-12.0)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = t * np.cos(e) * np.cos(az); pts[:, 1] = t * np.cos(e) * np.sin(az); pts[:, 2] = t * np.sin(e) + rng.normal(0, 0.02, n)
+    from urban_road_filter_b200.synth import _detie_radius
+    _detie_radius(pts, seed)
+    return pts
+
+
+def test_gpu_ring_sort_paths(det, port):
+    """k_sort_rings: counting sort over azimuth bins (rings up to 4096 points) and its fallbacks — a ring whose points
+    crowd into one bin, a ring confined to a two-degree arc (bins adapt to the ring's azimuth range), a ring beyond 4096
+    points — all against the oracle's emission order."""
+    rng = np.random.default_rng(13)                                  # a seed whose clouds have no exact azimuth ties
+    prm = make_params(interval=3.0, **FULL_ROI)
+    crowded = rng.permutation(np.concatenate([rng.uniform(100.0, 100.08, 60), rng.uniform(0.0, 359.0, 1940)]))
+    arc = rng.uniform(100.0, 130.0, 1200)
+    r = check(det, port, _one_ring_cloud(crowded, 1), prm)           # 60 points inside one of the 4096 bins: fallback
+    assert r.n_rings == 1 and r.n_order == 2000 and not (r.flags & 4)
+    r = check(det, port, _one_ring_cloud(arc, 2), prm)
+    assert not (r.flags & 4)
+    check(det, port, _one_ring_cloud(rng.uniform(0.0, 359.9, 4096), 3), prm)
+    check(det, port, _one_ring_cloud(rng.uniform(0.0, 359.9, 4097), 4), prm)
+    check(det, port, _one_ring_cloud(np.sort(rng.uniform(0.0, 359.9, 2048))[::-1], 5), prm)      # descending: the reference's O(n^2) case
+
+
 def test_gpu_radius_ties_follow_input_order(det):
     """Exact radius ties inside a sector: the reference's order is whatever its introsort leaves; ours is (radius, input
     index) — flagged in urf_result.flags bit1 and identical to the CPU model of the same policy."""
@@ -294,6 +345,43 @@ def test_gpu_pointcloud2_unpack_on_device(det, port, step, ox, oy, oz):
     r = det.filtered_cloud2(raw, n, step, ox, oy, oz)
     o = port.run(pts, prm)
     assert stage_diffs(o, r, n) == []
+
+
+def test_gpu_lean_and_batched_record_entries(port):
+    """urf_process_batch_xyz (12-byte points in, int8 labels out) and urf_process_cloud2_batch (raw PointCloud2 records of a
+    whole batch unpacked on the device), ragged batches large enough for the chunked copy/compute pipeline: labels, order
+    and vertices equal the oracle's on the float4 clouds."""
+    d = api.Detector(max_points=30_000, max_batch=20)
+    try:
+        prm = make_params(**FULL_ROI)
+        d.set_params(prm)
+        clouds = [make_scan("C1", 80 + s, order=("column", "ring")[s % 2])[: 28800 - 911 * (s % 5)] for s in range(18)]
+        clouds[5] = clouds[5][:17]
+        clouds[9] = random_cloud(5000, 5)
+        exp = [port.run(c, prm) for c in clouds]
+        xyz = [np.ascontiguousarray(c[:, :3]) for c in clouds]
+        for label8 in (True, False):
+            rs = d.filtered_batch_records(xyz, 12, 0, 4, 8, -1, want_order=True, label8=label8)
+            for o, r, c in zip(exp, rs, clouds):
+                assert o.status == r.status
+                if o.status == 0:
+                    r.ring = None
+                    assert stage_diffs(o, r, c.shape[0]) == []
+                else:
+                    assert np.all(r.label == -1)
+        recs = [_cloud2_records(c, 22, 0, 4, 8, 12, seed=i).reshape(-1) for i, c in enumerate(clouds)]     # Velodyne-like, unaligned
+        rs = d.filtered_batch_records(recs, 22, 0, 4, 8, 12, want_order=True, label8=True)
+        for o, r, c in zip(exp, rs, clouds):
+            assert o.status == r.status
+            if o.status == 0:
+                r.ring = None
+                assert stage_diffs(o, r, c.shape[0]) == []
+        one = d.filtered_batch_records(recs[:3], 22, 0, 4, 8, 12, want_order=True, label8=False)              # small batch: one chunk
+        for o, r, c in zip(exp[:3], one, clouds[:3]):
+            r.ring = None
+            assert stage_diffs(o, r, c.shape[0]) == []
+    finally:
+        d.close()
 
 
 def _cloud2_records(pts, step, ox, oy, oz, oi, seed=0):

@@ -186,10 +186,13 @@ def test_queue_argument_checks():
     q.destroy()
 
 
-@pytest.mark.parametrize("args", [("4", "1500", "6", "4", "0"), ("8", "600", "3", "2", "0"), ("4", "1500", "4", "3", "1")])
+@pytest.mark.parametrize("args", [("4", "1500", "6", "4", "0"), ("8", "600", "3", "2", "0"), ("4", "1500", "4", "3", "1"),
+                                  ("close", "40"), ("mq", "4", "3", "1500"), ("mq", "2", "1", "2000"), ("mq", "8", "6", "500")])
 def test_queue_thread_sanitizer_stress(args):
-    """urf_queue.cpp built with -fsanitize=thread: producers x scans x slots x max_batch x policy; the binary checks that
-    every accepted scan is delivered once with its payload and per-producer order, TSAN that there is no data race."""
+    """urf_queue.cpp + urf_mq.cpp built with -fsanitize=thread. Plain arguments: producers x scans x slots x max_batch x
+    policy; "close": the queue is closed while producers sit inside submit (nobody may hang); "mq": devices x producers x
+    scans through the multi-GPU ingest around stand-in devices. The binary checks that every accepted scan is delivered
+    once with its payload and per-producer order, TSAN that there is no data race."""
     import os
     import subprocess
     from util import ROOT

@@ -15,11 +15,13 @@ from .ctypes_abi import (QUEUE_PROCESS_FN, URF_ERR_CLOSED, URF_ERR_TIMEOUT, URF_
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liburf_b200.so")
 
-EXPORTS = ["urf_process_cloud2", "urf_process_cloud2_packed", "urf_pinned_alloc", "urf_pinned_free", "urf_queue_create",
+EXPORTS = ["urf_queue_submit_ref", "urf_queue_create_cloud2", "urf_queue_submit_cloud2", "urf_mq_create", "urf_mq_create_with",
+           "urf_mq_set_params", "urf_mq_submit", "urf_mq_submit_ref", "urf_mq_next", "urf_mq_get_stats", "urf_mq_close", "urf_mq_destroy",
+           "urf_process_cloud2", "urf_process_cloud2_packed", "urf_pinned_alloc", "urf_pinned_free", "urf_queue_create",
            "urf_queue_create_with", "urf_queue_submit", "urf_queue_next", "urf_queue_get_stats", "urf_queue_close", "urf_queue_destroy",
            "urf_version", "urf_strerror", "urf_last_cuda_error", "urf_default_params", "urf_create", "urf_destroy",
            "urf_set_params", "urf_get_params", "urf_process", "urf_process_batch", "urf_process_batch_device",
-           "urf_enqueue_batch_device", "urf_enqueue_batch_device_ex", "urf_finish_batch_device", "urf_stream", "urf_last_device_ms",
+           "urf_process_batch_xyz", "urf_process_cloud2_batch", "urf_enqueue_batch_device", "urf_enqueue_batch_device_ex", "urf_finish_batch_device", "urf_stream", "urf_last_device_ms",
            "urf_last_launch_count", "urf_build_markers"]
 
 _lib = None
@@ -56,6 +58,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.urf_process_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(ip), ip, C.POINTER(UrfResult)]
     lib.urf_process_cloud2.argtypes = [vp, vp, ip, ip, ip, ip, ip, C.POINTER(UrfResult)]
     lib.urf_process_cloud2_packed.argtypes = [vp, vp, ip, ip, ip, ip, ip, ip, C.POINTER(UrfResult), C.POINTER(UrfClouds)]
+    lib.urf_process_batch_xyz.argtypes = [vp, C.POINTER(vp), C.POINTER(ip), ip, C.POINTER(UrfResult), C.POINTER(vp)]
+    lib.urf_process_cloud2_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(ip), ip, ip, ip, ip, ip, ip, C.POINTER(UrfResult), C.POINTER(vp)]
     lib.urf_process_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp, C.POINTER(UrfResult)]
     lib.urf_enqueue_batch_device.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp]
     lib.urf_enqueue_batch_device_ex.argtypes = [vp, vp, ip, C.POINTER(ip), ip, vp, vp]
@@ -199,6 +203,51 @@ class Detector:
                 setattr(r, f, int(getattr(res[b], f)))
             r.label = lab[:n]
             r.ring = ring[:n] if want_ring else None
+            r.order = order[: r.n_order].copy() if want_order else None
+            r.ring_start = rs[: r.n_rings + 1].copy()
+            r.vert = np.ctypeslib.as_array(res[b].vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()
+            out.append(r)
+        return out
+
+    def filtered_batch_records(self, records, point_step: int, off_x: int, off_y: int, off_z: int, off_intensity: int = -1,
+                               want_order: bool = False, label8: bool = True) -> list[ScanResult]:
+        """`batch` scans given as raw PointCloud2 record arrays (uint8, n * point_step bytes each) of one sensor format,
+        unpacked on the device (urf_process_cloud2_batch). point_step == 12 with offsets 0, 4, 8 is the packed-xyz lean
+        input of urf_process_batch_xyz, which this method then calls. label8: labels come back as int8."""
+        B = len(records)
+        raws = [np.ascontiguousarray(r).view(np.uint8).reshape(-1) for r in records]
+        ns = [r.size // point_step for r in raws]
+        ptrs = (C.c_void_p * B)(*[r.ctypes.data for r in raws])
+        cn = (C.c_int * B)(*ns)
+        res = (UrfResult * B)()
+        keep = []
+        l8 = (C.c_void_p * B)()
+        for b, n in enumerate(ns):
+            m = max(n, 1)
+            lab = np.full(m, -1, np.int8 if label8 else np.int32)
+            order = np.zeros(m, np.int32) if want_order else None
+            rs = np.zeros(URF_MAX_CHANNELS + 1, np.int32)
+            if label8:
+                l8[b] = lab.ctypes.data
+            else:
+                res[b].label = lab.ctypes.data_as(C.POINTER(C.c_int32))
+            if want_order:
+                res[b].order = order.ctypes.data_as(C.POINTER(C.c_int32))
+            res[b].ring_start = rs.ctypes.data_as(C.POINTER(C.c_int32))
+            keep.append((lab, order, rs))
+        if point_step == 12 and (off_x, off_y, off_z) == (0, 4, 8) and off_intensity < 0:
+            self._check(self.lib.urf_process_batch_xyz(self._ctx, ptrs, cn, B, res, l8 if label8 else None), "urf_process_batch_xyz")
+        else:
+            self._check(self.lib.urf_process_cloud2_batch(self._ctx, ptrs, cn, B, point_step, off_x, off_y, off_z, off_intensity, res,
+                                                          l8 if label8 else None), "urf_process_cloud2_batch")
+        out = []
+        for b, n in enumerate(ns):
+            lab, order, rs = keep[b]
+            r = ScanResult()
+            for f in ("status", "n_in", "n_roi", "n_rings", "n_order", "n_road", "n_curb", "n_vert", "flags"):
+                setattr(r, f, int(getattr(res[b], f)))
+            r.label = lab[:n].astype(np.int32)
+            r.ring = None
             r.order = order[: r.n_order].copy() if want_order else None
             r.ring_start = rs[: r.n_rings + 1].copy()
             r.vert = np.ctypeslib.as_array(res[b].vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()

@@ -13,7 +13,7 @@ LIB = os.path.join(PKG, "liburf_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC"]
 SOURCES = ["urf_api.cu"]
-HOST_SOURCES = ["urf_markers.cpp", "urf_queue.cpp"]
+HOST_SOURCES = ["urf_markers.cpp", "urf_queue.cpp", "urf_mq.cpp"]
 HEADERS = ["urf_kernels.cuh", "urf_logic.cuh", "urf_device.cuh", "urf_math.cuh", "urf_host.hpp"]
 
 
@@ -79,7 +79,7 @@ def build_kat() -> None:
                         os.path.join(kat, "star_prefix_check.cpp")], check=True)
     # ThreadSanitizer build of the streaming queue around a stand-in batch function (no CUDA involved)
     tgt = os.path.join(bdir, "queue_stress")
-    qsrc = [os.path.join(kat, "queue_stress.cpp"), os.path.join(CSRC, "urf_queue.cpp")]
+    qsrc = [os.path.join(kat, "queue_stress.cpp"), os.path.join(CSRC, "urf_queue.cpp"), os.path.join(CSRC, "urf_mq.cpp")]
     if _stale(tgt, qsrc + [os.path.join(ROOT, "include", "urf.h")]):
         subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-o", tgt, *qsrc], check=True)
 

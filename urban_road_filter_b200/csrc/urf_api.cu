@@ -43,6 +43,9 @@ struct urf_ctx {
   DevBuffers buf{};
   float4* own_in = nullptr;
   unsigned char* raw = nullptr;        // PointCloud2 staging: max_points * URF_MAX_POINT_STEP bytes (urf_process_cloud2)
+  unsigned char* rawb = nullptr;       // batched record staging (urf_process_cloud2_batch / _xyz): P * rawb_step bytes, first use
+  int rawb_step = 0;
+  signed char* label8 = nullptr;       // int8 labels (P bytes), allocated when a caller first asks for them
   int* own_label = nullptr;
   float4* pack = nullptr;              // packed output clouds (urf_process_cloud2_packed): 3 * max_points 32-byte records, allocated on first use
   int* packcnt = nullptr;              // [3][tiles] per-tile counts / offsets
@@ -94,7 +97,7 @@ template <class T> int dalloc(urf_ctx* ctx, T** p, size_t count) {
 
 __global__ void k_ring32(DevBuffers buf, int* dst, int S) {
   const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < buf.n[b]) dst[(size_t)b * S + i] = buf.ringid[(size_t)b * S + i];
+  if (i < buf.n[b]) dst[(size_t)b * S + i] = max((int)buf.ringid[(size_t)b * S + i], -1);
 }
 
 // View of `buf` for a sub-batch: what belongs to a scan for good (input, labels, point count, results, emission order) is
@@ -104,8 +107,9 @@ DevBuffers slot_view(const DevBuffers& a, int b0, int w0, int S, int T, int chan
   DevBuffers v = a;
   const size_t o = (size_t)b0 * S, w = (size_t)w0 * S;
   v.in += o; v.label += o; v.order += o; v.n += b0; v.out += b0;
+  if (v.label8) v.label8 += o;
   v.alpha_v += w; v.mark += w; v.ringid += w; v.sect += w; v.bpt += w; v.spt += w; v.ssorted += w;
-  v.az += w; v.d2 += w; v.blabel += w; v.bring += w; v.bidx += w; v.roadlist += w; v.sortbuf += 2 * w;
+  v.az += w; v.d2 += w; v.roadlist += w; v.sortbuf += 2 * w;
   v.Tf += (size_t)w0 * channels * kTStride; v.Tb += (size_t)w0 * channels * kTStride;
   v.lut += (size_t)w0 * (kElevBins + 1); v.firstidx += (size_t)w0 * (kElevBins + 1);
   v.hist += (size_t)w0 * T * kRingKeys;
@@ -143,36 +147,22 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   K("k_reset", k_reset<<<dim3(8, B), 256, 0, st>>>(buf, dp));
   K("k_points", k_points<<<gpts, 256, 0, st>>>(buf, dp, S));
   K("k_register", k_register<<<B, 256, 0, st>>>(buf, dp, S));
-  K("k_assign", k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 0));
-  if (!dp.force_exact) {
-    K("k_register_exact", k_register_exact<<<B, 256, 0, st>>>(buf, dp, S));
-    K("k_assign_redo", k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T, 1));
-    K("k_mark_exact", k_mark_exact<<<(B + 127) / 128, 128, 0, st>>>(buf, B));
-  }
-  K("k_scan_offsets", k_scan_offsets<<<B, 1024, 0, st>>>(buf, T));
+  K("k_assign", k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
+  K("k_scan_offsets", k_scan_offsets<<<B, 1024, 0, st>>>(buf, dp, S, T));   // + exact re-registration of refuted scans
   K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
   if (dp.star) {
-    const int gbig = std::max(4, std::min(kSectKeys, 2048 / B)), gslow = std::max(2, std::min(kSectKeys, 512 / B));
+    const int gbig = std::max(4, std::min(kSectKeys, 2048 / B));
     const dim3 gscan((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B);
     K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, dp, S));
-    K("k_star_sort_cta", k_star_sort_cta<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
-    K("k_star_sort", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S, 0));
+    K("k_star_sort_big", k_star_sort_big<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
     K("k_star_scan", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S));
-    if (dp.star_prefix) {          // sectors whose edge search ran off the near-first prefix: full sort, search resumed
-      K("k_star_sort_refine", k_star_sort_refine<<<dim3(std::max(8, std::min(kSectKeys, 4096 / B)), B), 32, 0, st>>>(buf, S));
-      K("k_star_sort_2", k_star_sort<<<dim3(gslow, B), 128, 0, st>>>(buf, S, 1));
-      K("k_star_scan_resume", k_star_scan_resume<<<dim3((kSectKeys + 63) / 64, B), 64, 0, st>>>(buf, dp, S));
-    }
+    if (dp.star_prefix)            // sectors whose edge search ran off the near-first prefix: full sort, search resumed
+      K("k_star_refine", k_star_refine<<<dim3(std::max(8, std::min(kSectKeys, 4096 / B)), B), 32, 0, st>>>(buf, dp, S));
   }
   K("k_ring_detect", k_ring_detect<8><<<gpts, 256, 0, st>>>(buf, dp, S));   // 8 CTAs/SM (32 registers): measured 2 % faster than 6, 25 % faster than 4
-  K("k_tab1", k_tab1<<<dim3((dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
-  K("k_reach", k_reach<<<dim3((2 * kDegBins + 7) / 8, B), 256, 0, st>>>(buf, dp));
-  K("k_tab2", k_tab2<<<dim3((2 * dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
+  K("k_tabs", k_tabs<<<dim3(kTabCtas, B), kTabThreads, 0, st>>>(buf, dp));          // cluster of kTabCtas CTAs per scan
   K("k_label", k_label<<<gpts, 256, 0, st>>>(buf, dp, S));
-  const dim3 groad(std::max(1, std::min((S + 255) / 256, 96)), B);        // grid-stride over the compact road list
-  K("k_dmax", k_dmax<<<groad, 256, 0, st>>>(buf, S));
-  K("k_best", k_best<<<groad, 256, 0, st>>>(buf, S));
-  K("k_verts", k_verts<<<B, 384, 0, st>>>(buf, S));
+  K("k_markers", k_markers<<<dim3(kMarkCtas, B), kMarkThreads, 0, st>>>(buf, S));   // cluster of kMarkCtas CTAs per scan
   if (want_order) K("k_sort_rings", k_sort_rings<<<dim3(dp.channels, B), 256, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S));
 #undef K
   if (last) CK(cudaEventRecord(ctx->ev1, st));
@@ -309,9 +299,6 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   TRY(dalloc(ctx, &b.ssorted, P));
   TRY(dalloc(ctx, &b.az, P));
   TRY(dalloc(ctx, &b.d2, P));
-  TRY(dalloc(ctx, &b.blabel, P));
-  TRY(dalloc(ctx, &b.bring, P));
-  TRY(dalloc(ctx, &b.bidx, P));
   TRY(dalloc(ctx, &b.roadlist, P));
   TRY(dalloc(ctx, &b.Tf, (size_t)max_batch * kTStride * URF_MAX_CHANNELS));
   TRY(dalloc(ctx, &b.Tb, (size_t)max_batch * kTStride * URF_MAX_CHANNELS));
@@ -345,7 +332,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
     CKF(cudaMemcpyToSymbol(c_beam_yx, byx, sizeof(byx)));
     ctx->dp.Kfi = Kfi;
   }
-  CKF(cudaFuncSetAttribute(k_star_sort_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
+  CKF(cudaFuncSetAttribute(k_star_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
   CKF(cudaFuncSetAttribute(k_sort_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingSmemKeys * sizeof(unsigned long long))));
   urf_default_params(&ctx->params);
   const char* fe = std::getenv("URF_FORCE_EXACT_REGISTRATION");
@@ -579,23 +566,48 @@ int urf_process_batch_device(urf_ctx* ctx, const float* d_xyzi, int stride_point
   return urf_finish_batch_device(ctx, outs);
 }
 
-int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int batch, urf_result* outs) {
-  if (!ctx || !xyzi || !n || !outs || batch < 1) return URF_ERR_INVALID;
+namespace {
+// Shared body of the host-buffer batch entry points. step == 0: data[b] holds n[b] (x, y, z, intensity) float4 records that
+// are copied straight into the input buffer; step > 0: data[b] holds n[b] records of `step` bytes with FLOAT32 x / y / z /
+// intensity at the given byte offsets (oi < 0: none) — the raw bytes cross PCIe and are unpacked on the device.
+// label8 (or NULL): per scan an int8 HOST buffer for the labels (one byte per point instead of four).
+int process_batch_impl(urf_ctx* ctx, const void* const* data, const int* n, int batch, int step, int ox, int oy, int oz, int oi,
+                       urf_result* outs, int8_t* const* label8) {
+  if (!ctx || !data || !n || !outs || batch < 1) return URF_ERR_INVALID;
   if (batch > ctx->max_batch) return URF_ERR_CAPACITY;
+  if (step != 0) {
+    if (step < 12 || step > URF_MAX_POINT_STEP) return URF_ERR_INVALID;
+    for (int o : {ox, oy, oz}) if (o < 0 || o + 4 > step) return URF_ERR_INVALID;
+    if (oi >= 0 && oi + 4 > step) return URF_ERR_INVALID;
+  }
   CK(cudaSetDevice(ctx->device));
   int nmax = 1;
-  bool want_order = false, want_ring = false;
+  bool want_order = false, want_ring = false, want_l8 = false;
   for (int b = 0; b < batch; b++) {
-    if (n[b] < 0 || (n[b] > 0 && !xyzi[b])) return URF_ERR_INVALID;
+    if (n[b] < 0 || (n[b] > 0 && !data[b])) return URF_ERR_INVALID;
     if (n[b] > ctx->max_points) return URF_ERR_CAPACITY;
     nmax = n[b] > nmax ? n[b] : nmax;
     want_order |= outs[b].order != nullptr;
     want_ring |= outs[b].ring != nullptr;
+    want_l8 |= label8 && label8[b];
     ctx->h_n[b] = n[b];
+  }
+  if (step != 0 && (!ctx->rawb || ctx->rawb_step < step)) {      // first use (or a wider record than before): P * step bytes
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->rawb) { cudaFree(ctx->rawb); ctx->allocs.erase(std::find(ctx->allocs.begin(), ctx->allocs.end(), (void*)ctx->rawb)); ctx->rawb = nullptr; }
+    const int rc = dalloc(ctx, &ctx->rawb, ctx->P * (size_t)step);
+    if (rc != URF_OK) return rc;
+    ctx->rawb_step = step;
+  }
+  if (want_l8 && !ctx->label8) {
+    const int rc = dalloc(ctx, &ctx->label8, ctx->P);
+    if (rc != URF_OK) return rc;
   }
   const int S = ((nmax + 255) / 256) * 256;
   const int T = (S + kChunk - 1) / kChunk;
   cudaStream_t st = ctx->stream;
+  DevBuffers bufv = ctx->buf;
+  bufv.label8 = want_l8 ? ctx->label8 : nullptr;
   // Software pipeline over chunks of scans: H2D of chunk c+1 (s_in), kernels of chunk c (stream) and D2H of chunk c-1
   // (s_out) overlap; scans are independent, every chunk owns its slice of every buffer.
   const int chunk = batch >= 16 ? std::max(4, (batch + 15) / 16) : batch;     // short fill / drain of the pipeline
@@ -607,16 +619,22 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
     ctx->ev_in.push_back(a); ctx->ev_comp.push_back(c);
   }
   int* ring32 = reinterpret_cast<int*>(ctx->buf.sortbuf);     // free once the sorts of a chunk are done (chunk-private slice)
+  const bool graphed = nchunks == 1 && batch <= 8 && !want_l8;
   for (int c = 0; c < nchunks; c++) {
     const int b0 = c * chunk, nb = std::min(chunk, batch - b0);
     CK(cudaMemcpyAsync(ctx->buf.n + b0, ctx->h_n + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->s_in));
-    for (int b = b0; b < b0 + nb; b++)
-      if (n[b] > 0) CK(cudaMemcpyAsync(ctx->own_in + (size_t)b * S, xyzi[b], sizeof(float) * 4 * (size_t)n[b], cudaMemcpyHostToDevice, ctx->s_in));
+    for (int b = b0; b < b0 + nb; b++) {
+      if (n[b] <= 0) continue;
+      if (step == 0) CK(cudaMemcpyAsync(ctx->own_in + (size_t)b * S, data[b], sizeof(float) * 4 * (size_t)n[b], cudaMemcpyHostToDevice, ctx->s_in));
+      else CK(cudaMemcpyAsync(ctx->rawb + (size_t)b * S * step, data[b], (size_t)step * (size_t)n[b], cudaMemcpyHostToDevice, ctx->s_in));
+    }
     CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
     CK(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
-    const DevBuffers view = offset_view(ctx->buf, b0, S, T, ctx->dp.channels);
-    int rc = (nchunks == 1 && batch <= 8) ? launch_pipeline_graphed(ctx, nb, S, want_order)
-                                          : launch_pipeline(ctx, view, nb, S, want_order, c == 0, c == nchunks - 1);
+    if (step != 0)
+      k_unpack_cloud2_batch<<<dim3((S + 255) / 256, nb), 256, 0, st>>>(ctx->rawb + (size_t)b0 * S * step, ctx->own_in + (size_t)b0 * S, ctx->buf.n + b0, S,
+                                                                          step, ox, oy, oz, oi);
+    const DevBuffers view = offset_view(bufv, b0, S, T, ctx->dp.channels);
+    int rc = graphed ? launch_pipeline_graphed(ctx, nb, S, want_order) : launch_pipeline(ctx, view, nb, S, want_order, c == 0, c == nchunks - 1);
     if (rc != URF_OK) {                                 // nothing of this call may still be writing into the caller's buffers
       cudaStreamSynchronize(ctx->s_in); cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->s_out);
       return rc;
@@ -628,6 +646,7 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
     for (int b = b0; b < b0 + nb; b++) {
       if (n[b] <= 0) continue;
       if (outs[b].label) CK(cudaMemcpyAsync(outs[b].label, ctx->own_label + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, ctx->s_out));
+      if (label8 && label8[b]) CK(cudaMemcpyAsync(label8[b], ctx->label8 + (size_t)b * S, (size_t)n[b], cudaMemcpyDeviceToHost, ctx->s_out));
       if (outs[b].ring) CK(cudaMemcpyAsync(outs[b].ring, ring32 + (size_t)b0 * S * 4 + (size_t)(b - b0) * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, ctx->s_out));
       if (outs[b].order) CK(cudaMemcpyAsync(outs[b].order, ctx->buf.order + (size_t)b * S, sizeof(int) * (size_t)n[b], cudaMemcpyDeviceToHost, ctx->s_out));
     }
@@ -640,6 +659,21 @@ int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int 
     if (outs[b].status == URF_TOO_FEW_POINTS && outs[b].ring) for (int i = 0; i < n[b]; i++) outs[b].ring[i] = -1;
   }
   return URF_OK;
+}
+}  // namespace
+
+int urf_process_batch(urf_ctx* ctx, const float* const* xyzi, const int* n, int batch, urf_result* outs) {
+  return process_batch_impl(ctx, reinterpret_cast<const void* const*>(xyzi), n, batch, 0, 0, 0, 0, -1, outs, nullptr);
+}
+
+int urf_process_batch_xyz(urf_ctx* ctx, const float* const* xyz, const int* n, int batch, urf_result* outs, int8_t* const* label8) {
+  return process_batch_impl(ctx, reinterpret_cast<const void* const*>(xyz), n, batch, 12, 0, 4, 8, -1, outs, label8);
+}
+
+int urf_process_cloud2_batch(urf_ctx* ctx, const void* const* data, const int* n_points, int batch, int point_step, int off_x, int off_y,
+                             int off_z, int off_intensity, urf_result* outs, int8_t* const* label8) {
+  if (point_step == 0) return URF_ERR_INVALID;
+  return process_batch_impl(ctx, data, n_points, batch, point_step, off_x, off_y, off_z, off_intensity, outs, label8);
 }
 
 namespace {
@@ -739,8 +773,8 @@ int urf_test_math(int device, int which, const float* a, const float* b, float* 
 }
 
 // Copy a device-side intermediate of scan `b` of the last call into host memory (stage-level differential tests).
-//   what: 0 alpha_v[f32,n]  1 mark[u8,n]  2 ringid[i16,n]  3 sect[i16,n]  4 az[f32,n_order]  5 d2[f32,n_order]
-//         6 blabel[u8,n_order]  7 bucket input index[i32,n_order]  8 ScanTab (raw)
+//   what: 0 alpha_v[f32,n]  1 mark[u8,n] (all detectors)  2 ringid[i16,n]  3 sect[i16,n]  4 az[f32,n]  5 d2[f32,n]
+//         (4, 5: defined for ROI points only)  8 ScanTab (raw)
 int urf_debug_fetch(urf_ctx* ctx, int b, int what, void* dst, size_t bytes) {
   if (!ctx || !dst || b < 0 || b >= ctx->last_B) return URF_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
@@ -754,8 +788,6 @@ int urf_debug_fetch(urf_ctx* ctx, int b, int what, void* dst, size_t bytes) {
     case 3: src = ctx->buf.sect + off; break;
     case 4: src = ctx->buf.az + off; break;
     case 5: src = ctx->buf.d2 + off; break;
-    case 6: src = ctx->buf.blabel + off; break;
-    case 7: src = ctx->buf.bidx + off; break;
     case 8: src = ctx->buf.tab + b; if (bytes > sizeof(ScanTab)) bytes = sizeof(ScanTab); break;
     default: return URF_ERR_INVALID;
   }

@@ -58,7 +58,8 @@ struct ScanTab {
   float angle[kRingKeys];          // sorted registered elevation angles (lidar_segmentation.cpp:205)
   int regidx[kRingKeys];           // input index that registered angle[j]
   int regorder[kRingKeys];         // registration input indices in registration (= ascending) order
-  unsigned maxdist[kRingKeys];     // float bits of maxDistance[j] (:271-274); non-negative floats order like uints
+  unsigned long long maxs[kRingKeys];   // bits of the ring's largest (double)x*x + y*y (k_ring_detect); see planar_sum_bits
+  unsigned maxdist[kRingKeys];     // float bits of maxDistance[j] (:271-274) = (float)sqrt(maxs[j]), taken in k_tab1
   double A[kRingKeys];             // arcDistance / ((maxDistance[k] * M_PI) / 180)  (blind_spots.cpp:142)
   int sect_start[kSectKeys + 1];
   int sect_cnt[kSectKeys];         // points per star sector (unstable partition: counted with atomics)
@@ -67,13 +68,11 @@ struct ScanTab {
   unsigned short biglist[kSectKeys], slowlist[kSectKeys];
   float q[4];                      // q1..q4 (blind_spots.cpp:13-57)
   int reach[2][kDegBins];          // rings accepted by window start i, forward / backward (atomicMin over cells)
-  unsigned long long cutbest[kDegBins];              // min (ring, azimuth bits, bucket pos) over the bin's non-road points
-  unsigned dmax[kDegBins];         // float bits of the farthest candidate road point
-  unsigned long long best[kDegBins];                 // (ring, azimuth bits, bucket pos) of the first candidate reaching dmax
+  unsigned long long cutbest[kDegBins];              // min (ring, azimuth bits, input index) over the bin's non-road points
   // near-first star sort (k_star_sort_warp): only the points below a sampled pivot radius are sorted at first
   int sorted_len[kSectKeys];       // length of the radius-sorted prefix of the sector in `ssorted` (== size when fully sorted)
-  int nrefine, nslow2;             // sectors whose edge search ran off the sorted prefix / ties found while redoing them
-  unsigned short refine[kSectKeys], slowlist2[kSectKeys];
+  int nrefine, pad_;               // sectors whose edge search ran off the sorted prefix
+  unsigned short refine[kSectKeys];
   float resume[kSectKeys][4];      // per refine entry: running mean, deviation, NaN count of the walk over the prefix, its length
 };
 
@@ -81,19 +80,17 @@ struct ScanTab {
 struct DevBuffers {
   float4* in;            // [P]   x, y, z, intensity (input order)
   float* alpha_v;        // [P]   elevation angle in degrees, -1 = outside ROI
-  unsigned char* mark;   // [P]   star-shaped mark (2) per input point
-  short* ringid;         // [P]   ring index or -1
+  unsigned char* mark;   // [P]   detector mark per input point: 2 = curb (star-shaped, x-zero or z-zero), else 0
+  short* ringid;         // [P]   ring index; -1 = in the ROI but no registered ring matches; -2 = not in the ROI cloud
   short* sect;           // [P]   star sector or -1
   int* label;            // [P]   output labels, input order
+  signed char* label8;   // [P] or NULL: the same labels as one byte per point (callers that ask for int8 labels)
   float4* bpt;           // [P]   ring buckets (ring-major, input order inside a ring): x, y, z, input index bits
   float4* spt;           // [P]   sector buckets (unordered inside a sector): r, z, input index bits, -
   float4* ssorted;       // [P]   sector buckets sorted by r
-  float* az;             // [P]   azimuth per bucket position
-  float* d2;             // [P]   planar range per bucket position
-  unsigned char* blabel; // [P]   label per bucket position
-  unsigned char* bring;  // [P]   ring index per bucket position
-  int* bidx;             // [P]   input index per bucket position
-  uint4* roadlist;       // [P]   compact list of road points: (bin | ring << 16, azimuth bits, range bits, bucket pos)
+  float* az;             // [P]   azimuth per input point (ROI points only)
+  float* d2;             // [P]   planar range per input point (ROI points only)
+  uint4* roadlist;       // [P]   compact list of road points: (bin | ring << 16, azimuth bits, range bits, input index)
   float* Tf;             // [B][channels][kTStride] forward threshold table (urf_logic.cuh build_T_row)
   float* Tb;             // [B][channels][kTStride] backward threshold table
   unsigned short* lut;   // [B][kElevBins + 1] ring-search start per fine elevation bin

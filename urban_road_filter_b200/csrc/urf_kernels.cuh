@@ -6,19 +6,22 @@
 // there); the kernels add indexing, staging, atomics and synchronisation.
 //
 // Pipeline (DESIGN.md has the picture):
-//   k_reset -> k_points -> k_register -> k_assign -> [k_register_exact -> k_assign(redo) -> k_mark_exact]
-//   -> k_scan_offsets -> k_scatter -> k_star_sort_warp (near-first) / k_star_sort_cta / k_star_sort(fallback) -> k_star_scan
-//   -> [k_star_sort_refine -> k_star_sort(fallback, second list) -> k_star_scan_resume: sectors without an edge in their prefix]
-//   -> k_ring_detect -> k_tab1 -> k_reach -> k_tab2 -> k_label -> k_dmax -> k_best -> k_verts
+//   k_reset -> k_points -> k_register -> k_assign -> k_scan_offsets (+ exact re-registration of refuted scans)
+//   -> k_scatter -> k_star_sort_warp (near-first) -> k_star_sort_big (large sectors, exact fallback) -> k_star_scan
+//   -> k_star_refine (sectors without an edge in their prefix: full sort, walk resumed)
+//   -> k_ring_detect -> k_tab1 -> k_reach -> k_tab2 -> k_label (input order) -> k_dmax -> k_best -> k_verts
 //   [-> k_sort_rings when the emission order is requested]
 //   PointCloud2 entry points: k_unpack_cloud2 in front, k_pack_count -> k_pack_scan -> k_pack_write behind
 #pragma once
+#include <cooperative_groups.h>
 #include <type_traits>
 
 #include "urf_device.cuh"
 #include "urf_logic.cuh"
 
 namespace urf {
+
+namespace cg = cooperative_groups;
 
 __constant__ float c_beam_d[kSectKeys];
 __constant__ float c_beam_o[kSectKeys];
@@ -48,6 +51,27 @@ __device__ void cta_bitonic(T* a, int npad) {
 
 __device__ __forceinline__ int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
+// A detector found input point idx of scan b to be a curb point (star_shaped_search.cpp:146, x_zero_method.cpp:66,
+// z_zero_method.cpp:71): mark it and, if it sits in a ring bucket (k = its ring, or -1 = look it up), enter its azimuth
+// into the curb aggregates of that ring's integer-degree bin — what blindSpots reads. NaN azimuths fall out.
+__device__ __forceinline__ void curb_hit(const DevBuffers& buf, const DevParams& prm, int b, unsigned gb, int idx, int k) {
+  buf.mark[gb + (unsigned)idx] = 2;
+  if (k < 0) k = buf.ringid[gb + (unsigned)idx];
+  if (k < 0) return;                                   // not in array3D: the mark is never read (lidar_segmentation.cpp:241)
+  const float a = buf.az[gb + (unsigned)idx];
+  if (a >= 0.0f) {
+    const unsigned o = ((unsigned)b * (unsigned)prm.channels + (unsigned)k) * kDegBins + (unsigned)deg_bin(a);
+    atomicMin(&buf.cmin[o], fbits(a));
+    atomicMax(&buf.cmax[o], fbits(a));
+  }
+}
+// ring of bucket position p: rings are contiguous in bucket order, ring_start has kRingKeys + 1 non-decreasing entries
+__device__ __forceinline__ int ring_of_position(const int* __restrict__ ring_start, int p) {
+  int lo = 0, hi = kRingKeys;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (ring_start[mid] <= p) lo = mid + 1; else hi = mid; }
+  return lo - 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // k_reset: per-call initialisation of the per-scan tables.
 __global__ void k_reset(DevBuffers buf, DevParams prm) {
@@ -60,10 +84,10 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
     o.n_in = buf.n[b]; o.n_roi = 0; o.n_rings = 0; o.n_order = 0; o.n_road = 0; o.n_curb = 0; o.n_vert = 0; o.flags = 0;
   }
   for (int i = tid; i <= kRingKeys; i += nth) o.ring_start[i] = 0;
-  for (int i = tid; i < kRingKeys; i += nth) { t.maxdist[i] = 0u; t.angle[i] = 0.f; t.regidx[i] = 0x7fffffff; t.regorder[i] = 0x7fffffff; }
-  for (int i = tid; i < kDegBins; i += nth) { t.cutbest[i] = ~0ull; t.dmax[i] = 0u; t.best[i] = ~0ull; }
+  for (int i = tid; i < kRingKeys; i += nth) { t.maxs[i] = 0ull; t.maxdist[i] = 0u; t.angle[i] = 0.f; t.regidx[i] = 0x7fffffff; t.regorder[i] = 0x7fffffff; }
+  for (int i = tid; i < kDegBins; i += nth) t.cutbest[i] = ~0ull;
   for (int i = tid; i < kSectKeys; i += nth) t.sect_cnt[i] = 0;
-  if (tid == 0) { t.nbig = 0; t.nslow = 0; t.nrefine = 0; t.nslow2 = 0; }
+  if (tid == 0) { t.nbig = 0; t.nslow = 0; t.nrefine = 0; }
   unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1);
   for (int i = tid; i <= kElevBins; i += nth) fi[i] = 0xffffffffu;
   const size_t nb = (size_t)prm.channels * kDegBins;
@@ -73,8 +97,10 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_points: ROI crop predicate + range + elevation angle per input point (lidar_segmentation.cpp:106-113,148-166).
-// Also records, per fine elevation bin, the first input index that falls into it (speculation input for k_register).
+// k_points: everything that depends on one input point alone — ROI crop predicate, range and elevation angle
+// (lidar_segmentation.cpp:106-113,148-166), planar range and azimuth (:245-269; the squares are shared with the range) and
+// the star sector (star_shaped_search.cpp:164-173). Also records, per fine elevation bin, the first input index that
+// falls into it (speculation input for k_register).
 __global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   const int n = buf.n[b];
@@ -86,11 +112,14 @@ __global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, i
     keep = roi_keep(prm, p.x, p.y, p.z);
     float a = -1.0f;
     if (keep) {
-      a = elev_alpha(p.x, p.y, p.z);
+      float d, az;
+      point_angles(p.x, p.y, p.z, &a, &d, &az);
       unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1) + elev_bin(a);
       if (*fi > (unsigned)i) atomicMin(fi, (unsigned)i);      // plain (possibly stale) read: a stale value is only larger
       if (a == 0.0f) atomicOr(&buf.out[b].flags, F_ZERO_ALPHA);
       if (prm.star) sec = star_sector(prm, p.x, p.y, c_beam_d, c_beam_o, c_beam_yx);   // star_shaped_search.cpp:164-173
+      buf.az[g] = az;
+      buf.d2[g] = d;
     }
     buf.alpha_v[g] = a;
     buf.mark[g] = 0;
@@ -239,35 +268,41 @@ __global__ void __launch_bounds__(256) k_register(DevBuffers buf, DevParams prm,
   publish_rings_cta(tab, out, buf.lut + (size_t)b * (kElevBins + 1), prm.interval, s_reg, s_idx, s_m, s_keys, s_sorted);
 }
 
-// k_register_exact: repairs scans whose speculation failed verification in k_assign (F_SPEC_VIOLATION).
-__global__ void __launch_bounds__(256) k_register_exact(DevBuffers buf, DevParams prm, int S) {
-  const int b = blockIdx.x;
-  ScanOut& out = buf.out[b];
-  if (!(out.flags & F_SPEC_VIOLATION) || (out.flags & F_EXACT_REG)) return;
-  __shared__ float s_vis[kRingKeys];
-  __shared__ float s_reg[kRingKeys];
-  __shared__ float s_sorted[kRingKeys];
-  __shared__ int s_idx[kRingKeys];
-  __shared__ unsigned long long s_keys[kRingKeys];
-  __shared__ int s_red[8];
-  __shared__ int s_m;
-  int m;
-  register_exact_cta(buf.alpha_v + (size_t)b * S, buf.n[b], prm.interval, prm.channels, s_vis, s_reg, s_idx, s_red, &m);
-  if (threadIdx.x == 0) s_m = m;
-  __syncthreads();
-  publish_rings_cta(buf.tab[b], out, buf.lut + (size_t)b * (kElevBins + 1), prm.interval, s_reg, s_idx, s_m, s_keys, s_sorted);
-  // F_EXACT_REG is set by k_mark_exact after the redo pass of k_assign (every redo CTA must still see the old flags)
+// ---------------------------------------------------------------------------------------------------------------------
+// k_assign: per input point — ring index (lidar_segmentation.cpp:226-233: first sorted angle within `interval`) and the
+// per-warp-chunk ring histogram of the stable ring partition. assign_chunk is one warp's chunk of kChunk points; cnt is
+// the warp's zeroed shared histogram. Returns true (per lane) where the speculated registration is refuted.
+__device__ __forceinline__ bool assign_chunk(const DevBuffers& buf, const DevParams& prm, int b, int S, int T, int chunk, int n, bool live,
+                                             bool verify, const float* s_angle, const int* s_regidx, const int* regorder, int R,
+                                             const unsigned short* __restrict__ lut, unsigned* cnt, int lane) {
+  bool violation = false;
+  for (int it = 0; it < kChunk / 32; it++) {
+    const int i = chunk * kChunk + it * 32 + lane;
+    int ring = -1;
+    if (i < n) {
+      const unsigned g = scan_base(b, S) + (unsigned)i;
+      const float a = buf.alpha_v[g];
+      const bool kept = live && a >= 0.0f;
+      if (kept) {
+        int lo;
+        ring = assign_ring_from(s_angle, R, a, prm.interval, lut[elev_bin(a)], &lo);
+        if (verify && registration_violation(s_angle, s_regidx, regorder, R, prm.channels, prm.interval, a, i, lo)) violation = true;
+      }
+      buf.ringid[g] = kept ? (short)ring : (short)-2;     // -2: not part of the ROI cloud (k_label writes URF_LABEL_OUTSIDE)
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, ring);
+    if (ring >= 0 && lane == __ffs(peers) - 1) cnt[ring] += __popc(peers);
+    __syncwarp();
+  }
+  unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
+  for (int t = lane; t < kRingKeys; t += 32) row[t] = cnt[t];
+  return violation;
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// k_assign: per input point — ring index (lidar_segmentation.cpp:226-233: first sorted angle within `interval`), default
-// label and the per-warp-chunk ring histogram of the stable ring partition.
-// redo=1 re-runs only for scans whose registration was repaired.
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, DevParams prm, int S, int T, int redo) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, DevParams prm, int S, int T) {
   const int b = blockIdx.y;
   ScanOut& out = buf.out[b];
   const int flags = out.flags;
-  if (redo && (!(flags & F_SPEC_VIOLATION) || (flags & F_EXACT_REG))) return;
   const int n = buf.n[b];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int chunk = blockIdx.x * kWarpsPerBlock + warp;
@@ -280,52 +315,50 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_assign(DevBuffers buf, 
   for (int t = lane; t < kRingKeys; t += 32) s_cnt[warp][t] = 0;
   __syncthreads();
   if (chunk * kChunk >= n) return;             // whole warp; no block-level sync follows
-  const bool live = out.n_roi >= 30;
-  const bool verify = !redo && !(flags & F_EXACT_REG);
-  const unsigned short* lut = buf.lut + (size_t)b * (kElevBins + 1);
-  unsigned* cnt = s_cnt[warp];
-  bool violation = false;
-  for (int it = 0; it < kChunk / 32; it++) {
-    const int i = chunk * kChunk + it * 32 + lane;
-    int ring = -1;
-    if (i < n) {
-      const unsigned g = scan_base(b, S) + (unsigned)i;
-      const float a = buf.alpha_v[g];
-      const bool kept = live && a >= 0.0f;
-      if (kept) {
-        int lo;
-        ring = assign_ring_from(s_angle, R, a, prm.interval, lut[elev_bin(a)], &lo);
-        if (verify && registration_violation(s_angle, s_regidx, tab.regorder, R, prm.channels, prm.interval, a, i, lo))
-          violation = true;
-      }
-      buf.ringid[g] = (short)ring;
-      buf.label[g] = kept ? URF_LABEL_NONE : URF_LABEL_OUTSIDE;
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, ring);
-    if (ring >= 0 && lane == __ffs(peers) - 1) cnt[ring] += __popc(peers);
-    __syncwarp();
-  }
+  const bool violation = assign_chunk(buf, prm, b, S, T, chunk, n, out.n_roi >= 30, !(flags & F_EXACT_REG), s_angle, s_regidx, tab.regorder, R,
+                                      buf.lut + (size_t)b * (kElevBins + 1), s_cnt[warp], lane);
   if (__any_sync(0xffffffffu, violation) && lane == 0) atomicOr(&out.flags, F_SPEC_VIOLATION);
-  unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
-  for (int t = lane; t < kRingKeys; t += 32) row[t] = cnt[t];
-}
-
-// After the redo pass: mark repaired scans as exact (separate tiny kernel so every k_assign(redo) CTA saw the old flags).
-__global__ void k_mark_exact(DevBuffers buf, int B) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B && (buf.out[b].flags & F_SPEC_VIOLATION)) buf.out[b].flags |= F_EXACT_REG;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_scan_offsets: one CTA (1024 threads) per scan turns hist[chunk][ring] into exclusive scatter offsets (ring-major
 // bases + prefix over chunks), publishes ring_start, and turns the sector counts into sect_start + scatter cursors.
-__global__ void __launch_bounds__(1024) k_scan_offsets(DevBuffers buf, int T) {
+// In front of that it repairs a scan whose speculated registration k_assign refuted (F_SPEC_VIOLATION, rare): the exact
+// registration, then ring ids and chunk histograms of the whole scan again, one chunk per warp at a time.
+__global__ void __launch_bounds__(1024) k_scan_offsets(DevBuffers buf, DevParams prm, int S, int T) {
   __shared__ unsigned s_part[32][kRingKeys];     // per-warp partial sums, then per-warp exclusive prefixes
   __shared__ unsigned s_base[kRingKeys];
   const int b = blockIdx.x;
   const int n = buf.n[b];
   const int rows = (n + kChunk - 1) / kChunk;
   const int warp = threadIdx.x >> 5, lane = lane_id();
+  {
+    ScanOut& out = buf.out[b];
+    const int flags = out.flags;
+    if ((flags & F_SPEC_VIOLATION) && !(flags & F_EXACT_REG)) {      // uniform across the CTA
+      __shared__ float s_vis[kRingKeys], s_reg[kRingKeys], s_sorted[kRingKeys];
+      __shared__ int s_idx[kRingKeys];
+      __shared__ unsigned long long s_keys[kRingKeys];
+      __shared__ int s_red[32];
+      __shared__ int s_m;
+      int m;
+      register_exact_cta(buf.alpha_v + (size_t)b * S, n, prm.interval, prm.channels, s_vis, s_reg, s_idx, s_red, &m);
+      if (threadIdx.x == 0) s_m = m;
+      __syncthreads();
+      const unsigned short* lut = buf.lut + (size_t)b * (kElevBins + 1);
+      publish_rings_cta(buf.tab[b], out, buf.lut + (size_t)b * (kElevBins + 1), prm.interval, s_reg, s_idx, s_m, s_keys, s_sorted);
+      __syncthreads();                                                // s_sorted = the sorted angles, lut written
+      const int R = s_m;
+      for (int c0 = 0; c0 < rows; c0 += 32) {
+        for (int t = lane; t < kRingKeys; t += 32) s_part[warp][t] = 0;
+        __syncwarp();
+        if (c0 + warp < rows) assign_chunk(buf, prm, b, S, T, c0 + warp, n, true, false, s_sorted, nullptr, nullptr, R, lut, s_part[warp], lane);
+        __syncwarp();
+      }
+      if (threadIdx.x == 0) out.flags = flags | F_EXACT_REG;
+      __syncthreads();                                                // the histogram rows are read back below
+    }
+  }
   const int rpw = (rows + 31) / 32;
   const int r0 = min(rows, warp * rpw), r1 = min(rows, (warp + 1) * rpw);
   unsigned* hist = buf.hist + (size_t)b * T * kRingKeys;
@@ -377,12 +410,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   __shared__ unsigned s_delta[kWarpsPerBlock][kChunk];            // bucket slot of ring-ordered slot t, minus t
   __shared__ unsigned short s_lcnt[kWarpsPerBlock][kRingKeys];    // per-ring count, then exclusive local start
   __shared__ unsigned short s_perm[kWarpsPerBlock][kChunk];       // chunk-local point index in ring order
-  __shared__ unsigned char s_pring[kWarpsPerBlock][kChunk];       // ring of that slot
   if (chunk * kChunk >= n) return;
   unsigned* delta = s_delta[warp];
   unsigned short* lcnt = s_lcnt[warp];
   unsigned short* perm = s_perm[warp];
-  unsigned char* pring = s_pring[warp];
   ScanTab& tab = buf.tab[b];
   const unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
   for (int t = lane; t < kRingKeys; t += 32) lcnt[t] = 0;
@@ -464,7 +495,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
       const unsigned lstart = lcnt[ring];
       const int slot = lstart + (pk & 0xffffu);
       perm[slot] = (unsigned short)(it * 32 + lane);
-      pring[slot] = (unsigned char)ring;
       delta[slot] = __ldg(&row[ring]) - lstart;        // global offset of the chunk's ring group - its local start
     }
     total += __popc(__ballot_sync(0xffffffffu, pk != 0));
@@ -473,13 +503,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   // walk the chunk in ring order, four warp-rows at a time so that four point gathers are in flight per lane
   for (int t0 = 0; t0 < total; t0 += 128) {
     float4 p[4];
-    int li[4], ring[4];
+    int li[4];
     unsigned dl[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int t = t0 + j * 32 + lane;
       li[j] = t < total ? perm[t] : 0;
-      ring[j] = t < total ? pring[t] : 0;
       dl[j] = t < total ? delta[t] : 0;
     }
 #pragma unroll
@@ -490,8 +519,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
       if (t < total) {
         const unsigned dst = gb + dl[j] + (unsigned)t;
         buf.bpt[dst] = make_float4(p[j].x, p[j].y, p[j].z, __int_as_float(chunk * kChunk + li[j]));
-        buf.bring[dst] = (unsigned char)ring[j];
-        buf.bidx[dst] = chunk * kChunk + li[j];
       }
     }
   }
@@ -684,32 +711,43 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, DevParams
   if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;   // sets F_TIE_SECTOR there
 }
 
-// Sectors whose edge search ran off their sorted prefix (tab.refine): sort them completely.
-__global__ void __launch_bounds__(32) k_star_sort_refine(DevBuffers buf, int S) {
-  const int b = blockIdx.y, lane = threadIdx.x;
-  ScanTab& tab = buf.tab[b];
-  const int nref = tab.nrefine;
-  for (int w = blockIdx.x; w < nref; w += gridDim.x) {
-    const int s = tab.refine[w];
-    const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
-    const float4* src = buf.spt + (size_t)b * S + base;
-    float4* dst = buf.ssorted + (size_t)b * S + base;
-    const bool tie = sort_sector_warp(src, dst, n, lane);
-    if (lane == 0) tab.sorted_len[s] = n;
-    if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist2[atomicAdd(&tab.nslow2, 1)] = (unsigned short)s;
-    __syncwarp();
+// Exact fallback sort of one sector on (radius bits, input index) keys by all threads of the CTA (bitonic; shared memory
+// up to `cap` keys, global scratch beyond): sectors larger than kCtaCap and sectors holding equal radii, whose order must
+// follow the input index (the push_back order of star_shaped_search.cpp:173). Raises F_TIE_SECTOR for equal radii.
+__device__ void slow_sort_sector(const DevBuffers& buf, int b, int S, int base, int n, unsigned long long* s_keys, int cap) {
+  const float4* src = buf.spt + (size_t)b * S + base;
+  float4* dst = buf.ssorted + (size_t)b * S + base;
+  const int npad = next_pow2(n < 2 ? 2 : n);
+  unsigned long long* keys = npad <= cap ? s_keys : buf.sortbuf + 2 * ((size_t)b * S + base);
+  __syncthreads();
+  for (int t = threadIdx.x; t < npad; t += blockDim.x)
+    keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
+  __syncthreads();
+  cta_bitonic(keys, npad);
+  // keys hold (radius bits, input index) ascending: rebuild the records (z comes from the input record of that index)
+  bool tie = false;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const unsigned long long k = keys[t];
+    if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
+    const int idx = (int)(unsigned)k;
+    dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
   }
+  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+  __syncthreads();
 }
 
-constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap;
-__global__ void __launch_bounds__(256) k_star_sort_cta(DevBuffers buf, int S) {
+// k_star_sort_big: the sectors k_star_sort_warp handed over. tab.biglist (1025 .. kCtaCap points): eight-warp register
+// network, redone at once by the exact fallback when it meets equal radii; tab.slowlist (larger sectors, and sectors in
+// which the single-warp sort met equal radii): exact fallback. Whole sectors get sorted: sorted_len = size.
+constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap;            // 64 KB: exchange buffers / 8192 64-bit keys
+__global__ void __launch_bounds__(256) k_star_sort_big(DevBuffers buf, int S) {
   extern __shared__ unsigned s_dyn[];
   const int b = blockIdx.y;
   ScanTab& tab = buf.tab[b];
   unsigned* s_xk = s_dyn;
   unsigned* s_xe = s_dyn + kCtaCap;
   __shared__ int s_tie;
-  const int nbig = tab.nbig;
+  const int nbig = tab.nbig, nslow = tab.nslow;
   for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
     const int s = tab.biglist[w];
     const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
@@ -723,43 +761,55 @@ __global__ void __launch_bounds__(256) k_star_sort_cta(DevBuffers buf, int S) {
     __syncthreads();
     if (tie) s_tie = 1;
     __syncthreads();
-    if (threadIdx.x == 0 && s_tie) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;
+    const bool redo = s_tie != 0;
     __syncthreads();
+    if (redo) slow_sort_sector(buf, b, S, base, n, reinterpret_cast<unsigned long long*>(s_dyn), kCtaCap);
+  }
+  for (int w = blockIdx.x; w < nslow; w += gridDim.x) {
+    const int s = tab.slowlist[w];
+    const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+    if (threadIdx.x == 0) tab.sorted_len[s] = n;
+    slow_sort_sector(buf, b, S, base, n, reinterpret_cast<unsigned long long*>(s_dyn), kCtaCap);
   }
 }
 
-// Fallback: CTA-wide bitonic sort on (radius bits, input index) keys (shared memory up to 4096 keys, global scratch
-// beyond) for sectors larger than kCtaCap or holding long runs of identical radii.
-constexpr int kStarSmemKeys = 4096;
-__global__ void __launch_bounds__(128) k_star_sort(DevBuffers buf, int S, int second) {
-  const int b = blockIdx.y;
+// k_star_refine: second pass for the sectors whose edge search ran off their sorted prefix (tab.refine, filled by
+// k_star_scan): one warp sorts the sector completely (exact fallback on equal radii), then lane 0 resumes the walk at
+// point n0 with the saved running mean / deviation — the first n0 points of the full order are the prefix already walked
+// (all of them are closer than the rest).
+__global__ void __launch_bounds__(32) k_star_refine(DevBuffers buf, DevParams prm, int S) {
+  __shared__ unsigned long long s_keys[kWarpCap];
+  const int b = blockIdx.y, lane = threadIdx.x;
   ScanTab& tab = buf.tab[b];
-  __shared__ unsigned long long s_keys[kStarSmemKeys];
-  const int nslow = second ? tab.nslow2 : tab.nslow;
-  const unsigned short* list = second ? tab.slowlist2 : tab.slowlist;
-  for (int w = blockIdx.x; w < nslow; w += gridDim.x) {
-    const int s = list[w];
-    if (threadIdx.x == 0) tab.sorted_len[s] = tab.sect_start[s + 1] - tab.sect_start[s];   // the whole sector gets sorted
-    const int base = tab.sect_start[s];
-    const int n = tab.sect_start[s + 1] - base;
+  const int nref = tab.nrefine;
+  for (int w = blockIdx.x; w < nref; w += gridDim.x) {
+    const int s = tab.refine[w];
+    const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
     const float4* src = buf.spt + (size_t)b * S + base;
     float4* dst = buf.ssorted + (size_t)b * S + base;
-    const int npad = next_pow2(n);
-    unsigned long long* keys = npad <= kStarSmemKeys ? s_keys : buf.sortbuf + 2 * ((size_t)b * S + base);
-    for (int t = threadIdx.x; t < npad; t += blockDim.x)
-      keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
-    __syncthreads();
-    cta_bitonic(keys, npad);
-    // keys hold (radius bits, input index) ascending: rebuild the records (z comes from the input record of that index)
-    bool tie = false;
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-      const unsigned long long k = keys[t];
-      if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
-      const int idx = (int)(unsigned)k;
-      dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
+    const bool tie = sort_sector_warp(src, dst, n, lane);
+    if (__any_sync(0xffffffffu, tie)) slow_sort_sector(buf, b, S, base, n, s_keys, kWarpCap);
+    __syncwarp();
+    if (lane == 0) {
+      tab.sorted_len[s] = n;
+      StarState st;
+      st.avg = tab.resume[w][0]; st.dev = tab.resume[w][1]; st.nan = tab.resume[w][2];
+      int i = __float_as_int(tab.resume[w][3]);            // >= 32: a prefix is never shorter
+      const float4 last = dst[i - 1];
+      st.bx = last.x; st.by = last.y;
+      int hit = -1;
+      while (i < n && hit < 0) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) p[u] = dst[min(i + u, n - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (hit < 0 && i + u < n && star_step(prm, st, i + u, p[u].x, p[u].y)) hit = i + u;
+        i += 4;
+      }
+      if (hit >= 0) curb_hit(buf, prm, b, scan_base(b, S), __float_as_int(dst[hit].z), -1);     // star_shaped_search.cpp:146
     }
-    if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -826,7 +876,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
     __syncwarp();
     if (__all_sync(0xffffffffu, done)) break;
   }
-  if (hit >= 0) buf.mark[scan_base(b, S) + (unsigned)__float_as_int(all[base + hit].z)] = 2;   // star_shaped_search.cpp:146
+  if (hit >= 0) curb_hit(buf, prm, b, scan_base(b, S), __float_as_int(all[base + hit].z), -1);   // star_shaped_search.cpp:146
   else if (n < whole) {                               // ran off the sorted prefix: sort in full, k_star_scan_resume continues from here
     const int w = atomicAdd(&tab.nrefine, 1);
     tab.refine[w] = (unsigned short)s;
@@ -834,70 +884,40 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
   }
 }
 
-// Second pass of the edge search for the sectors on tab.refine, now sorted in full: the first n points of the full order
-// are the prefix already walked (all of them are closer than the rest), so the walk resumes at point n with the saved
-// running mean / deviation. One lane per sector, four records in flight.
-__global__ void __launch_bounds__(64) k_star_scan_resume(DevBuffers buf, DevParams prm, int S) {
-  const int b = blockIdx.y;
-  ScanTab& tab = buf.tab[b];
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= tab.nrefine) return;
-  const int s = tab.refine[w];
-  const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
-  const float4* pts = buf.ssorted + (size_t)b * S + base;
-  StarState st;
-  st.avg = tab.resume[w][0]; st.dev = tab.resume[w][1]; st.nan = tab.resume[w][2];
-  int i = __float_as_int(tab.resume[w][3]);            // >= 32: a prefix is never shorter
-  const float4 last = pts[i - 1];
-  st.bx = last.x; st.by = last.y;
-  int hit = -1;
-  while (i < n && hit < 0) {
-    float4 p[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) p[u] = pts[min(i + u, n - 1)];
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-      if (hit < 0 && i + u < n && star_step(prm, st, i + u, p[u].x, p[u].y)) hit = i + u;
-    i += 4;
-  }
-  if (hit >= 0) buf.mark[scan_base(b, S) + (unsigned)__float_as_int(pts[hit].z)] = 2;           // star_shaped_search.cpp:146
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// k_ring_detect: one thread per ring-bucket position. Planar range + azimuth (lidar_segmentation.cpp:245-274), the
-// x-zero test for which this point is the middle point p2 (x_zero_method.cpp:30-67), the z-zero test centred on it
-// (z_zero_method.cpp:21-72), the curb aggregates blindSpots needs and maxDistance per ring. The CTA stages its 256
+// k_ring_detect: one thread per ring-bucket position: the x-zero test for which this point is the middle point p2
+// (x_zero_method.cpp:30-67), the z-zero test centred on it (z_zero_method.cpp:21-72), and the ring's largest planar range
+// (maxDistance, lidar_segmentation.cpp:271-274, as the largest double sum — see planar_sum_bits). The CTA stages its 256
 // bucket positions plus a halo of curb_points on each side in shared memory as three coordinate arrays (plain global
 // reads when curb_points exceeds kHalo). Both detectors are a cheap height gate followed by an expensive angle test
 // (four double square roots, a double divide, acosf); about one point in eight passes a gate, scattered over most warps,
 // so every thread evaluates only the gates and the CTA compacts the survivors into a work list that full warps then run
-// the angle tests over (x-zero items from thread 0 upwards, z-zero items from thread 255 downwards).
+// the angle tests over (x-zero items from thread 0 upwards, z-zero items from thread 255 downwards). Points found to be
+// curb points are marked in input order and entered into the curb bins (curb_hit); nothing else is written per point.
 constexpr int kHalo = 32;
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
+  const int p0 = blockIdx.x * 256, tid = threadIdx.x, p = p0 + tid;
+  const unsigned gb = scan_base(b, S);
+  const float4* bucket = buf.bpt + gb;
   // inside the scan's slot whatever n_order is, so the load need not wait for it
-  const float4 me0 = (int)(blockIdx.x * blockDim.x + threadIdx.x) < S ? buf.bpt[scan_base(b, S) + blockIdx.x * blockDim.x + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 me0 = p < S ? bucket[p] : make_float4(0.f, 0.f, 0.f, 0.f);
   const int N = out.n_order;
   __shared__ float s_x[256 + 2 * kHalo], s_y[256 + 2 * kHalo], s_z[256 + 2 * kHalo];
-  __shared__ int s_rs[kRingKeys + 1];                     // ring_start of the rings this CTA touches, indexed by ring - k_lo
+  __shared__ int s_rs[kRingKeys + 2];                     // ring_start of the rings this CTA touches, indexed by ring - k_lo
   __shared__ int s_base[256];                             // ring_start of each thread's ring
   __shared__ unsigned short s_item[512];                  // x-zero work items grow from 0 up, z-zero items from 511 down
-  __shared__ unsigned char s_hit[2][256];
+  __shared__ unsigned char s_hit[256];
   __shared__ int s_klo, s_nx, s_nz;
-  const int p0 = blockIdx.x * blockDim.x;
   if (p0 >= N) return;
-  const int tid = threadIdx.x;
   if (tid < 32) {                                         // rings are contiguous in bucket order: first .. last ring of the CTA
-    const int k_lo = buf.bring[scan_base(b, S) + (unsigned)p0], k_hi = buf.bring[scan_base(b, S) + (unsigned)min(p0 + 255, N - 1)];
+    const int k_lo = ring_of_position(out.ring_start, p0), k_hi = ring_of_position(out.ring_start, min(p0 + 255, N - 1));
     if (tid == 0) { s_klo = k_lo; s_nx = 0; s_nz = 0; }
     for (int t = tid; t <= k_hi - k_lo + 1; t += 32) s_rs[t] = out.ring_start[k_lo + t];
   }
-  const unsigned gb = scan_base(b, S);
-  const float4* bucket = buf.bpt + gb;
   const bool tiled = prm.curbPoints <= kHalo;
-  const int p = p0 + tid;
   const bool act = p < N;
   const float4 me = act ? me0 : make_float4(0.f, 0.f, 0.f, 0.f);
   if (tiled) {                                            // one bucket record per thread + a halo record for the first 64 threads
@@ -907,33 +927,26 @@ __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevPa
       const int sh = tid < kHalo ? tid : 256 + tid;
       if (ph >= 0 && ph < N) { const float4 h = bucket[ph]; s_x[sh] = h.x; s_y[sh] = h.y; s_z[sh] = h.z; }
     }
-    s_hit[0][tid] = 0; s_hit[1][tid] = 0;
+    s_hit[tid] = 0;
   }
   __syncthreads();
-  int k = -1, lab = 0;
-  unsigned dbits = 0;
-  float az = 0.f;
-  bool need_x = false, need_z = false;
+  int k = -1;
+  bool hit = false, need_x = false, need_z = false;
   if (act) {
-    k = buf.bring[gb + (unsigned)p];
-    const int base = s_rs[k - s_klo], n = s_rs[k - s_klo + 1] - base, m = p - base;
-    const int idx = __float_as_int(me.w);
-    float d;
-    planar_az(me.x, me.y, &d, &az);                                     // lidar_segmentation.cpp:245-269
-    buf.az[gb + (unsigned)p] = az;
-    buf.d2[gb + (unsigned)p] = d;
-    dbits = fbits(d);
-    lab = prm.star ? buf.mark[gb + (unsigned)idx] : 0;                  // :241-242
+    int r = 0;
+    while (p >= s_rs[r + 1]) r++;                         // p < N = the last staged entry at the latest
+    k = s_klo + r;
+    const int base = s_rs[r], n = s_rs[r + 1] - base, m = p - base;
     if (tiled) {
       s_base[tid] = base;
-      const int off = base - (p0 - kHalo);                              // ring-local index q lives at tile slot off + q
+      const int off = base - (p0 - kHalo);                // ring-local index q lives at tile slot off + q
       const RingSoA ring{s_x + off, s_y + off, s_z + off};
-      need_x = prm.x_zero && lab != 2 && xzero_pre(prm, ring, n, m);
-      need_z = prm.z_zero && lab != 2 && (prm.curbPoints == 5 ? zzero_pre_t<5>(prm, ring, n, m) : zzero_pre_t<0>(prm, ring, n, m));
-    } else {                                                            // huge curb_points: straight from global memory
+      need_x = prm.x_zero && xzero_pre(prm, ring, n, m);
+      need_z = prm.z_zero && (prm.curbPoints == 5 ? zzero_pre_t<5>(prm, ring, n, m) : zzero_pre_t<0>(prm, ring, n, m));
+    } else {                                              // huge curb_points: straight from global memory
       const float4* ring = bucket + base;
-      if (prm.x_zero && lab != 2 && xzero_mark(prm, ring, n, m, buf.newY)) lab = 2;   // x_zero_method.cpp:66
-      if (prm.z_zero && lab != 2 && zzero_mark(prm, ring, n, m)) lab = 2;             // z_zero_method.cpp:71
+      hit = (prm.x_zero && xzero_mark(prm, ring, n, m, buf.newY)) ||                  // x_zero_method.cpp:66
+            (prm.z_zero && zzero_mark(prm, ring, n, m));                              // z_zero_method.cpp:71
     }
   }
   if (tiled) {
@@ -952,49 +965,55 @@ __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevPa
     for (int it = tid; it < nx; it += 256) {                            // x-zero angle tests, x_zero_method.cpp:35-61
       const int t = s_item[it], base = s_base[t], off = base - (p0 - kHalo);
       const RingSoA ring{s_x + off, s_y + off, s_z + off};
-      if (xzero_post(prm, ring, p0 + t - base, buf.newY)) s_hit[0][t] = 1;
+      if (xzero_post(prm, ring, p0 + t - base, buf.newY)) s_hit[t] = 1;
     }
     for (int it = 255 - tid; it < nz; it += 256) {                      // z-zero angle tests, z_zero_method.cpp:23-66
       const int t = s_item[511 - it], base = s_base[t], off = base - (p0 - kHalo);
       const RingSoA ring{s_x + off, s_y + off, s_z + off};
-      if (prm.curbPoints == 5 ? zzero_post_t<5>(prm, ring, p0 + t - base) : zzero_post_t<0>(prm, ring, p0 + t - base)) s_hit[1][t] = 1;
+      if (prm.curbPoints == 5 ? zzero_post_t<5>(prm, ring, p0 + t - base) : zzero_post_t<0>(prm, ring, p0 + t - base)) s_hit[t] = 1;
     }
     __syncthreads();
-    if (act && (s_hit[0][tid] | s_hit[1][tid])) lab = 2;               // x_zero_method.cpp:66, z_zero_method.cpp:71
+    hit = act && s_hit[tid];                                            // x_zero_method.cpp:66, z_zero_method.cpp:71
   }
-  if (act) {
-    buf.blabel[gb + (unsigned)p] = (unsigned char)lab;
-    if (lab == 2 && az >= 0.0f) {            // curb aggregates per (ring, integer-degree bin); NaN azimuths fall out
-      const unsigned o = ((unsigned)b * (unsigned)prm.channels + (unsigned)k) * kDegBins + (unsigned)deg_bin(az);
-      atomicMin(&buf.cmin[o], fbits(az));
-      atomicMax(&buf.cmax[o], fbits(az));
-    }
-  }
+  if (hit) curb_hit(buf, prm, b, gb, __float_as_int(me.w), k);
   // maxDistance[k], lidar_segmentation.cpp:271-274 (warp-aggregated when the whole warp sits in one ring)
+  const unsigned long long sb = act ? planar_sum_bits(me.x, me.y) : 0ull;
   const int k0 = __shfl_sync(0xffffffffu, k, 0);
   if (__all_sync(0xffffffffu, k == k0)) {
     if (k0 >= 0) {
-      const unsigned mx = __reduce_max_sync(0xffffffffu, dbits);
-      if (lane_id() == 0) atomicMax(&buf.tab[b].maxdist[k0], mx);      // result unused: a fire-and-forget RED
+      const unsigned hi = (unsigned)(sb >> 32), mh = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned)sb : 0u);
+      if (lane_id() == 0) atomicMax(&buf.tab[b].maxs[k0], ((unsigned long long)mh << 32) | ml);   // result unused: a RED
     }
-  } else if (act) atomicMax(&buf.tab[b].maxdist[k], dbits);
+  } else if (act) atomicMax(&buf.tab[b].maxs[k], sb);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// blindSpots as tables (urf_logic.cuh: CurbView, window_blocked, build_T_column, covered_T).
-// k_tab1: per scan — prefix counts of non-empty curb bins per ring, arc widths, q1..q4, reach := n_rings.
-__global__ void __launch_bounds__(256) k_tab1(DevBuffers buf, DevParams prm) {
+// blindSpots as tables (urf_logic.cuh: CurbView, window_blocked, build_T_row, covered_T): one thread-block CLUSTER of
+// kTabCtas CTAs per scan runs the three dependent phases back to back, separated by cluster barriers instead of kernel
+// boundaries (the hardware co-schedules the CTAs of a cluster, so the barrier cannot deadlock):
+//   phase 1  per ring: prefix counts of non-empty curb bins; maxDistance / arc widths; q1..q4; reach := n_rings
+//   phase 2  one warp per (direction, window start i): lanes test 32 rings at a time whether ring k holds a curb point
+//            inside window i and stop at the first blocked ring — reach[dir][i] (blind_spots.cpp:107-171 / :216-280)
+//   phase 3  one warp per (ring, direction): a row of a threshold table by a warp max/min scan over the 361 window
+//            starts (same result as the sequential build_T_row of urf_logic.cuh)
+constexpr int kTabCtas = 8, kTabThreads = 512;
+__global__ void __cluster_dims__(kTabCtas, 1, 1) __launch_bounds__(kTabThreads) k_tabs(DevBuffers buf, DevParams prm) {
+  cg::cluster_group cluster = cg::this_cluster();
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
   const int R = out.n_rings;
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  if (blockIdx.x == 0) for (int t = threadIdx.x; t < 2 * kDegBins; t += blockDim.x) tab.reach[t / kDegBins][t % kDegBins] = R;
-  if (R <= 0) return;
+  const int lane = lane_id();
+  const int gw = blockIdx.x * (kTabThreads / 32) + (threadIdx.x >> 5);     // warp index inside the cluster
+  constexpr int NW = kTabCtas * (kTabThreads / 32);
   const size_t nb = (size_t)prm.channels * kDegBins;
   const unsigned* cmin = buf.cmin + (size_t)b * nb;
   unsigned short* ne = buf.ne + (size_t)b * prm.channels * (kDegBins + 1);
-  for (int k = blockIdx.x * 8 + warp; k < R; k += gridDim.x * 8) {        // one warp per ring: 12 x 32 bins with a running carry
+  const CurbView cv{cmin, buf.cmax + (size_t)b * nb, ne};
+  // ---- phase 1
+  if (blockIdx.x == 0) for (int t = threadIdx.x; t < 2 * kDegBins; t += kTabThreads) tab.reach[t / kDegBins][t % kDegBins] = R;
+  for (int k = gw; k < R; k += NW) {                                      // one warp per ring: 12 x 32 bins with a running carry
     unsigned carry = 0;
     for (int c = 0; c < (kDegBins + 31) / 32; c++) {
       const int bin = c * 32 + lane;
@@ -1005,183 +1024,195 @@ __global__ void __launch_bounds__(256) k_tab1(DevBuffers buf, DevParams prm) {
     }
     if (lane == 0) ne[(size_t)k * (kDegBins + 1) + kDegBins] = (unsigned short)carry;
   }
-  if (blockIdx.x != 0) return;
-  const float arc = arc_distance(prm, bitsf(tab.maxdist[0]));            // blind_spots.cpp:65
-  for (int k = threadIdx.x; k < R; k += blockDim.x) tab.A[k] = ring_width(arc, bitsf(tab.maxdist[k]));   // :142
-  if (threadIdx.x < 4) {
-    CurbView cv{cmin, buf.cmax + (size_t)b * nb, ne};
-    tab.q[threadIdx.x] = blind_quarter(prm, cv, R, threadIdx.x);         // :13-57
+  if (blockIdx.x == kTabCtas - 1 && R > 0) {
+    const float arc = arc_distance(prm, maxdist_from_bits(tab.maxs[0]));   // blind_spots.cpp:65
+    for (int k = threadIdx.x; k < R; k += kTabThreads) {
+      const float md = maxdist_from_bits(tab.maxs[k]);                     // lidar_segmentation.cpp:271-274
+      tab.maxdist[k] = fbits(md);
+      tab.A[k] = ring_width(arc, md);                                      // :142
+    }
+    if (threadIdx.x < 4) tab.q[threadIdx.x] = blind_quarter(prm, cv, R, threadIdx.x);   // :13-57 (reads the curb bins only)
   }
-}
-
-// k_reach: one warp per (direction, window start i): lanes test 32 rings at a time whether ring k holds a curb point
-// inside window i and stop at the first blocked ring — reach[dir][i] (blind_spots.cpp:107-171 / :216-280 stop there too).
-__global__ void __launch_bounds__(256) k_reach(DevBuffers buf, DevParams prm) {
-  const int b = blockIdx.y;
-  const ScanOut& out = buf.out[b];
-  ScanTab& tab = buf.tab[b];
-  const int R = out.n_rings;
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id();
-  if (w >= 2 * kDegBins || R <= 0) return;
-  const int dir = w / kDegBins, i = w % kDegBins;
-  if (dir == 0 ? i > prm.fwd_last : i < prm.bwd_first) return;          // outside the loop range: never accepted anyway
-  const size_t nb = (size_t)prm.channels * kDegBins;
-  CurbView cv{buf.cmin + (size_t)b * nb, buf.cmax + (size_t)b * nb, buf.ne + (size_t)b * prm.channels * (kDegBins + 1)};
-  int reach = R;
-  for (int k0 = 0; k0 < R; k0 += 32) {
-    const int k = k0 + lane;
-    const bool blocked = k < R && window_blocked(prm, cv, tab.A[k], dir, i, k);
-    const unsigned bal = __ballot_sync(0xffffffffu, blocked);
-    if (bal) { reach = k0 + __ffs(bal) - 1; break; }
+  __threadfence();
+  cluster.sync();
+  // ---- phase 2
+  for (int w = gw; w < 2 * kDegBins && R > 0; w += NW) {
+    const int dir = w / kDegBins, i = w % kDegBins;
+    if (dir == 0 ? i > prm.fwd_last : i < prm.bwd_first) continue;        // outside the loop range: never accepted anyway
+    int reach = R;
+    for (int k0 = 0; k0 < R; k0 += 32) {
+      const int k = k0 + lane;
+      const bool blocked = k < R && window_blocked(prm, cv, tab.A[k], dir, i, k);
+      const unsigned bal = __ballot_sync(0xffffffffu, blocked);
+      if (bal) { reach = k0 + __ffs(bal) - 1; break; }
+    }
+    if (lane == 0) tab.reach[dir][i] = reach;
   }
-  if (lane == 0) tab.reach[dir][i] = reach;
-}
-
-// k_tab2: one warp per (ring, direction) builds a row of a threshold table with a warp max/min scan over the 361
-// window starts (same result as the sequential build_T_row of urf_logic.cuh).
-__global__ void __launch_bounds__(256) k_tab2(DevBuffers buf, DevParams prm) {
-  const int b = blockIdx.y;
-  const ScanOut& out = buf.out[b];
-  const ScanTab& tab = buf.tab[b];
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id();
-  const int k = w >> 1, dir = w & 1;
-  if (k >= out.n_rings) return;
-  const double A = tab.A[k];
-  const size_t o = ((size_t)b * prm.channels + k) * kTStride;
+  __threadfence();
+  cluster.sync();
+  // ---- phase 3: degree-major tables, entry (j, k) at (j * channels + k) — a warp of k_label reads one or a few
+  // contiguous runs whether the sensor emits column-major (32 rings at one azimuth) or ring-major (one ring, a few degrees)
+  const size_t ch = prm.channels;
   constexpr int NCH = (kDegBins + 31) / 32;
-  if (dir == 0) {
-    int carry = -1;
-    for (int c = 0; c < NCH; c++) {
-      const int j = c * 32 + lane;
-      int m = (j < kDegBins && accepted_fwd(prm, tab.reach[0], tab.q, k, j)) ? j : -1;
-      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, m, d); if (lane >= d) m = max(m, v); }
-      m = max(m, carry);
-      if (j < kDegBins) buf.Tf[o + j] = T_fwd_value(prm, k, m, A);
-      carry = __shfl_sync(0xffffffffu, m, 31);
-    }
-  } else {
-    int carry = 361;
-    for (int c = NCH - 1; c >= 0; c--) {
-      const int j = c * 32 + lane;
-      int m = (j < kDegBins && accepted_bwd(prm, tab.reach[1], tab.q, k, j)) ? j : 361;
-      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_down_sync(0xffffffffu, m, d); if (lane + d < 32) m = min(m, v); }
-      m = min(m, carry);
-      if (j < kDegBins) buf.Tb[o + j] = T_bwd_value(prm, k, m, A);
-      carry = __shfl_sync(0xffffffffu, m, 0);
+  for (int w = gw; w < 2 * R; w += NW) {
+    const int k = w >> 1, dir = w & 1;
+    const double A = tab.A[k];
+    const size_t o = (size_t)b * ch * kTStride + k;
+    if (dir == 0) {
+      int carry = -1;
+      for (int c = 0; c < NCH; c++) {
+        const int j = c * 32 + lane;
+        int m = (j < kDegBins && accepted_fwd(prm, tab.reach[0], tab.q, k, j)) ? j : -1;
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, m, d); if (lane >= d) m = max(m, v); }
+        m = max(m, carry);
+        if (j < kDegBins) buf.Tf[o + j * ch] = T_fwd_value(prm, k, m, A);
+        carry = __shfl_sync(0xffffffffu, m, 31);
+      }
+    } else {
+      int carry = 361;
+      for (int c = NCH - 1; c >= 0; c--) {
+        const int j = c * 32 + lane;
+        int m = (j < kDegBins && accepted_bwd(prm, tab.reach[1], tab.q, k, j)) ? j : 361;
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_down_sync(0xffffffffu, m, d); if (lane + d < 32) m = min(m, v); }
+        m = min(m, carry);
+        if (j < kDegBins) buf.Tb[o + j * ch] = T_bwd_value(prm, k, m, A);
+        carry = __shfl_sync(0xffffffffu, m, 0);
+      }
     }
   }
 }
 
-// k_label: final label per ring-bucket position, scattered back to input order; counts; per degree bin the first
-// non-road point in the reference's scan order; road points are appended to a compact list for the marker search.
+// k_label: final label per input point, in input order (coalesced): -1 outside the ROI cloud, 2 where a detector marked
+// the point, 1 where a blindSpots window covers it (two threshold look-ups, covered_from), else 0. Also the counts, per
+// degree bin the first non-road point in the reference's scan order (ring, azimuth; equal azimuths in input order), and
+// the compact list of road points for the marker search.
 __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned gb = scan_base(b, S), g = gb + (unsigned)p;
-  // p < S: the four loads stay inside the scan's slot whatever n_order is, so they are issued together with its load
-  const bool in_slot = p < S;
-  const int k0 = in_slot ? buf.bring[g] : 0, lab0 = in_slot ? buf.blabel[g] : 0, idx = in_slot ? buf.bidx[g] : 0;
-  const float a0 = in_slot ? buf.az[g] : 0.f;
-  const int N = out.n_order;
-  if ((int)(blockIdx.x * blockDim.x) >= N) return;
-  int lab = -1, k = 0, bin = 0;
-  float a = 0.f;
-  if (p < N) {
-    k = k0;
-    a = a0;
-    lab = lab0;
-    // everything the decision needs is loaded up front (independent loads, one round trip): the two threshold entries
-    // and the bin's current first-non-road key
-    const unsigned o = ((unsigned)b * (unsigned)prm.channels + (unsigned)k) * kTStride;
-    const bool valid = a >= 0.0f;
-    int j = 0, jc = 0;
-    if (valid) T_indices(a, &j, &jc);
-    const float tf = buf.Tf[o + j], tb = buf.Tb[o + jc];
-    bin = j;                                          // == deg_bin(a)
-    const unsigned long long cb = tab.cutbest[bin];
-    if (lab != 2 && valid && covered_from(a, tf, tb)) lab = 1;       // covered_T of urf_logic.cuh with the loads hoisted
-    buf.blabel[g] = (unsigned char)lab;
-    buf.label[gb + (unsigned)idx] = lab;
-    if (valid && lab != 1) {                          // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
-      const unsigned long long key = best_key(k, fbits(a), p);
-      if (cb > key) atomicMin(&tab.cutbest[bin], key);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = buf.n[b];
+  if ((int)(blockIdx.x * blockDim.x) >= n) return;
+  __shared__ int s_road[8], s_curb[8], s_base;
+  const unsigned gb = scan_base(b, S), g = gb + (unsigned)i;
+  int lab = -2, k = -2, bin = 0;                        // -2: past the end of the scan
+  float a = 0.f, d = 0.f;
+  if (i < n) {
+    k = buf.ringid[g];
+    lab = k == -2 ? URF_LABEL_OUTSIDE : URF_LABEL_NONE;
+    if (k >= 0) {
+      a = buf.az[g];
+      d = buf.d2[g];
+      const int m = buf.mark[g];
+      // everything the decision needs is loaded up front (independent loads, one round trip): the two threshold entries
+      // (degree-major table, see k_tab2) and the bin's current first-non-road key (from L2: L1 would keep serving the
+      // value of the first look, and every later non-road point of the CTA would fire an atomic)
+      const unsigned o = (unsigned)b * (unsigned)prm.channels * kTStride + (unsigned)k;
+      const bool valid = a >= 0.0f;
+      int j = 0, jc = 0;
+      if (valid) T_indices(a, &j, &jc);
+      const float tf = buf.Tf[o + (unsigned)j * prm.channels], tb = buf.Tb[o + (unsigned)jc * prm.channels];
+      bin = j;                                          // == deg_bin(a)
+      const unsigned long long cb = __ldcg(&tab.cutbest[bin]);
+      lab = m == 2 ? 2 : (valid && covered_from(a, tf, tb)) ? 1 : 0;   // covered_T of urf_logic.cuh with the loads hoisted
+      if (valid && lab != 1) {                          // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
+        const unsigned long long key = best_key(k, fbits(a), i);
+        if (cb > key) atomicMin(&tab.cutbest[bin], key);
+      }
     }
+    buf.label[g] = lab;
+    if (buf.label8) buf.label8[g] = (signed char)lab;
   }
+  // one list slot per road point: counts per warp, ONE atomic per CTA on the scan's running road count
   const unsigned br = __ballot_sync(0xffffffffu, lab == 1), bc = __ballot_sync(0xffffffffu, lab == 2);
-  int base = 0;
-  if (lane_id() == 0) {
-    if (br) base = atomicAdd(&out.n_road, __popc(br));
-    if (bc) atomicAdd(&out.n_curb, __popc(bc));
+  const int warp = threadIdx.x >> 5;
+  if (lane_id() == 0) { s_road[warp] = __popc(br); s_curb[warp] = __popc(bc); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tr = 0, tc = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { tr += s_road[w]; tc += s_curb[w]; }
+    s_base = tr ? atomicAdd(&out.n_road, tr) : 0;
+    if (tc) atomicAdd(&out.n_curb, tc);
   }
-  base = __shfl_sync(0xffffffffu, base, 0);
+  __syncthreads();
   if (lab == 1) {
-    // one list slot per road point, handed out per warp from the running road count; a road point whose azimuth is NaN
-    // belongs to no degree bin and is listed as a placeholder
-    const int slot = base + __popc(br & ((1u << lane_id()) - 1u));
-    buf.roadlist[gb + (unsigned)slot] = a >= 0.0f ? make_uint4((unsigned)bin | ((unsigned)k << 16), fbits(a), fbits(buf.d2[g]), (unsigned)p)
-                                                   : make_uint4(0xffffffffu, 0u, 0u, 0u);
+    int slot = s_base + __popc(br & ((1u << lane_id()) - 1u));
+    for (int w = 0; w < warp; w++) slot += s_road[w];
+    buf.roadlist[gb + (unsigned)slot] = make_uint4((unsigned)bin | ((unsigned)k << 16), fbits(a), fbits(d), (unsigned)i);
   }
 }
 
-// Marker candidate vertices, lidar_segmentation.cpp:305-351, over the compact road list:
-//   k_dmax: farthest candidate road point per bin (candidates: road points scanned before the bin's first non-road point)
-//   k_best: first candidate in scan order that reaches that distance (`d > maxDistanceRoad` is strict, :329)
-__global__ void __launch_bounds__(256) k_dmax(DevBuffers buf, int S) {
+// k_markers: marker candidate vertices, lidar_segmentation.cpp:305-351, over the compact road list — one thread-block
+// CLUSTER of kMarkCtas CTAs per scan, the per-bin aggregates in the shared memory of the cluster's first CTA (distributed
+// shared memory, reached by the other CTAs through cluster.map_shared_rank), the passes separated by cluster barriers:
+//   pass 1  farthest candidate road point per bin (candidates: road points scanned before the bin's first non-road point)
+//   pass 2  first candidate in scan order that reaches that distance (`d > maxDistanceRoad` is strict, :329)
+//   then    the first CTA compacts the per-bin winners in bin order into markerPointsArray (:343-350)
+constexpr int kMarkCtas = 8, kMarkThreads = 512;
+__global__ void __cluster_dims__(kMarkCtas, 1, 1) __launch_bounds__(kMarkThreads) k_markers(DevBuffers buf, int S) {
+  cg::cluster_group cluster = cg::this_cluster();
   const int b = blockIdx.y;
-  ScanTab& tab = buf.tab[b];
-  const int nroad = buf.out[b].n_road;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nroad; t += gridDim.x * blockDim.x) {
-    const uint4 e = buf.roadlist[scan_base(b, S) + (unsigned)t];
-    if (e.x == 0xffffffffu) continue;
-    const int bin = e.x & 0xffff, k = e.x >> 16;
-    if (marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w) && tab.dmax[bin] < e.z) atomicMax(&tab.dmax[bin], e.z);
-  }
-}
-
-__global__ void __launch_bounds__(256) k_best(DevBuffers buf, int S) {
-  const int b = blockIdx.y;
-  ScanTab& tab = buf.tab[b];
-  const int nroad = buf.out[b].n_road;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nroad; t += gridDim.x * blockDim.x) {
-    const uint4 e = buf.roadlist[scan_base(b, S) + (unsigned)t];
-    if (e.x == 0xffffffffu) continue;
-    const int bin = e.x & 0xffff, k = e.x >> 16;
-    if (e.z != 0u && e.z == tab.dmax[bin] && marker_candidate(tab.cutbest[bin], k, e.y, (int)e.w))
-      atomicMin(&tab.best[bin], best_key(k, e.y, (int)e.w));
-  }
-}
-
-// k_verts: compact the per-bin winners in bin order into markerPointsArray (lidar_segmentation.cpp:343-350).
-__global__ void __launch_bounds__(384) k_verts(DevBuffers buf, int S) {
-  const int b = blockIdx.x;
   ScanOut& out = buf.out[b];
   const ScanTab& tab = buf.tab[b];
-  __shared__ int s_wsum[12];
+  __shared__ unsigned long long s_cut[kDegBins];       // every CTA's own copy of the first-non-road keys (read only here)
+  __shared__ unsigned s_dmax[kDegBins];                // used in CTA 0 only
+  __shared__ unsigned long long s_best[kDegBins];      // used in CTA 0 only
+  __shared__ int s_wsum[kMarkThreads / 32];
+  unsigned* dmax0 = cluster.map_shared_rank(s_dmax, 0);
+  unsigned long long* best0 = cluster.map_shared_rank(s_best, 0);
+  for (int t = threadIdx.x; t < kDegBins; t += kMarkThreads) { s_cut[t] = tab.cutbest[t]; s_dmax[t] = 0u; s_best[t] = ~0ull; }
+  cluster.sync();
+  const int nroad = out.n_road;
+  const uint4* list = buf.roadlist + scan_base(b, S);
+  const int t0 = blockIdx.x * kMarkThreads + threadIdx.x;
+  constexpr int STEP = kMarkCtas * kMarkThreads;
+  for (int t = t0; t < nroad; t += STEP) {
+    const uint4 e = list[t];
+    const int bin = e.x & 0xffff, k = e.x >> 16;
+    if (marker_candidate(s_cut[bin], k, e.y, (int)e.w) && dmax0[bin] < e.z) atomicMax(&dmax0[bin], e.z);
+  }
+  cluster.sync();
+  for (int t = t0; t < nroad; t += STEP) {
+    const uint4 e = list[t];
+    const int bin = e.x & 0xffff, k = e.x >> 16;
+    if (e.z != 0u && e.z == dmax0[bin] && marker_candidate(s_cut[bin], k, e.y, (int)e.w)) {
+      const unsigned long long key = best_key(k, e.y, (int)e.w);
+      if (best0[bin] > key) atomicMin(&best0[bin], key);
+    }
+  }
+  cluster.sync();                                      // the other CTAs are done with CTA 0's shared memory
+  if (blockIdx.x != 0) return;
   const int i = threadIdx.x;
-  const bool has = i < kDegBins && tab.best[i] != ~0ull;
+  const bool has = i < kDegBins && s_best[i] != ~0ull;
   const unsigned bal = __ballot_sync(0xffffffffu, has);
   const int warp = i >> 5, lane = lane_id();
   if (lane == 0) s_wsum[warp] = __popc(bal);
   __syncthreads();
   int off = 0, total = 0;
-  for (int w = 0; w < 12; w++) { if (w < warp) off += s_wsum[w]; total += s_wsum[w]; }
+  for (int w = 0; w < kMarkThreads / 32; w++) { if (w < warp) off += s_wsum[w]; total += s_wsum[w]; }
   if (has) {
     const int slot = off + __popc(bal & ((1u << lane) - 1u));
-    const int p = (int)(tab.best[i] & 0xffffffull);
-    const float4 q = buf.bpt[(size_t)b * S + p];
+    const int p = (int)(s_best[i] & 0xffffffull);      // input index of the winner
+    const float4 q = buf.in[(size_t)b * S + p];
     out.vert[slot][0] = q.x; out.vert[slot][1] = q.y; out.vert[slot][2] = q.z;
-    out.vert[slot][3] = tab.cutbest[i] != ~0ull ? 1.0f : 0.0f;          // redPoints, :320,348
+    out.vert[slot][3] = s_cut[i] != ~0ull ? 1.0f : 0.0f;                // redPoints, :320,348
   }
   if (i == 0) out.n_vert = total;
   if (i >= total && i < URF_MAX_VERTS) { out.vert[i][0] = 0.f; out.vert[i][1] = 0.f; out.vert[i][2] = 0.f; out.vert[i][3] = 0.f; }   // defined tail
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_sort_rings (only when the emission order is requested): per-ring sort by azimuth, lidar_segmentation.cpp:289-291.
+// k_sort_rings (only when the emission order is requested): per-ring sort by azimuth, lidar_segmentation.cpp:70-93,289-291.
 // Tie policy: (azimuth, input order) — the reference's Lomuto quicksort is unstable; ties raise F_TIE_AZIMUTH.
-constexpr int kRingSmemKeys = 8192;
+// One CTA per ring. Rings of up to kRingFast points take a counting sort in shared memory: azimuths are spread over
+// kRingBins equal-width bins between the ring's smallest and largest azimuth (a monotone map, so bin order = azimuth
+// order), a histogram + exclusive scan places every point in its bin, and the few points that share a bin (LiDAR rings
+// are close to uniform in azimuth) are ordered by one thread with an insertion sort on (azimuth bits, position). A ring
+// with a crowded bin (more than kBinCap points) or more than kRingFast points falls back to the CTA-wide bitonic sort on
+// 64-bit (azimuth bits, position) keys. Both paths produce the same total order.
+constexpr int kRingSmemKeys = 8192;                     // 64 KB of dynamic shared memory
+constexpr int kRingFast = 4096, kRingBins = 4096, kBinCap = 48;
 __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
   extern __shared__ unsigned long long s_rkeys[];
   const int b = blockIdx.y, k = blockIdx.x;
@@ -1189,17 +1220,96 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
   if (k >= out.n_rings) return;
   const int base = out.ring_start[k], n = out.ring_start[k + 1] - base;
   if (n <= 0) return;
-  const size_t g0 = (size_t)b * S + base;
+  const size_t gb = (size_t)b * S, g0 = gb + base;
+  const int tid = threadIdx.x;
+  if (n <= kRingFast) {
+    unsigned* s_az = reinterpret_cast<unsigned*>(s_rkeys);            // [kRingFast] azimuth bits by ring position
+    unsigned* s_idx = s_az + kRingFast;                               // [kRingFast] input index by ring position
+    unsigned* s_cnt = s_idx + kRingFast;                              // [kRingBins] bin counts, then exclusive starts
+    unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_cnt + kRingBins);   // [kRingFast] arrival rank inside the bin
+    unsigned short* s_slot = s_rank + kRingFast;                      // [kRingFast] ring position by sorted position
+    __shared__ unsigned s_lo, s_hi, s_over, s_wsum[8];
+    if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; s_over = 0u; }
+    for (int t = tid; t < kRingBins; t += 256) s_cnt[t] = 0u;
+    __syncthreads();
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (int t = tid; t < n; t += 256) {
+      const unsigned idx = (unsigned)__float_as_int(buf.bpt[g0 + t].w);
+      const unsigned a = fbits(buf.az[gb + idx]);
+      s_az[t] = a; s_idx[t] = idx;
+      if (a <= 0x7f800000u) { lo = min(lo, a); hi = max(hi, a); }   // azimuths are >= +0: their bits order them; NaN stays out
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane_id() == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    __syncthreads();
+    const float flo = bitsf(s_lo), fhi = bitsf(s_hi);
+    const float scale = fhi > flo ? __fdiv_rn((float)(kRingBins - 2), __fsub_rn(fhi, flo)) : 0.0f;
+    auto bin_of = [&](unsigned a) -> int {                           // monotone in a; NaN azimuths go to the last bin
+      if (a > 0x7f800000u) return kRingBins - 1;
+      const int v = __float2int_rz(__fmul_rn(__fsub_rn(bitsf(a), flo), scale));
+      return v < 0 ? 0 : (v > kRingBins - 2 ? kRingBins - 2 : v);
+    };
+    for (int t = tid; t < n; t += 256) s_rank[t] = (unsigned short)atomicAdd(&s_cnt[bin_of(s_az[t])], 1u);
+    __syncthreads();
+    {   // exclusive scan over the bins: 16 consecutive bins per thread, warp scan, eight warp totals
+      constexpr int PER = kRingBins / 256;
+      unsigned v[PER], sum = 0, mx = 0;
+#pragma unroll
+      for (int j = 0; j < PER; j++) { v[j] = s_cnt[tid * PER + j]; sum += v[j]; mx = max(mx, v[j]); }
+      if (mx > (unsigned)kBinCap) s_over = 1u;
+      unsigned inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, inc, o); if (lane_id() >= o) inc += y; }
+      if (lane_id() == 31) s_wsum[tid >> 5] = inc;
+      __syncthreads();
+      unsigned run = inc - sum;
+      for (int w = 0; w < (tid >> 5); w++) run += s_wsum[w];
+#pragma unroll
+      for (int j = 0; j < PER; j++) { s_cnt[tid * PER + j] = run; run += v[j]; }
+    }
+    __syncthreads();
+    if (!s_over) {
+      for (int t = tid; t < n; t += 256) s_slot[s_cnt[bin_of(s_az[t])] + s_rank[t]] = (unsigned short)t;
+      __syncthreads();
+      constexpr int PER = kRingBins / 256;
+      for (int j = 0; j < PER; j++) {                                  // order the points that share a bin
+        const int bin = tid * PER + j;
+        const int s0 = (int)s_cnt[bin], s1 = bin + 1 < kRingBins ? (int)s_cnt[bin + 1] : n;
+        for (int e = s0 + 1; e < s1; e++) {
+          const unsigned short cur = s_slot[e];
+          const unsigned ca = s_az[cur];
+          int f = e - 1;
+          while (f >= s0) {
+            const unsigned short o = s_slot[f];
+            const unsigned oa = s_az[o];
+            if (oa < ca || (oa == ca && o < cur)) break;
+            s_slot[f + 1] = o; f--;
+          }
+          s_slot[f + 1] = cur;
+        }
+      }
+      __syncthreads();
+      bool tie = false;
+      for (int p = tid; p < n; p += 256) {
+        const unsigned short slot = s_slot[p];
+        buf.order[g0 + p] = (int)s_idx[slot];
+        if (p > 0 && s_az[s_slot[p - 1]] == s_az[slot]) tie = true;
+      }
+      if (tie) atomicOr(&out.flags, F_TIE_AZIMUTH);
+      return;
+    }
+    __syncthreads();                                                   // the fallback reuses the shared memory
+  }
   const int npad = next_pow2(n < 2 ? 2 : n);
   unsigned long long* keys = npad <= kRingSmemKeys ? s_rkeys : buf.sortbuf + 2 * g0;
-  for (int t = threadIdx.x; t < npad; t += blockDim.x)
-    keys[t] = t < n ? (((unsigned long long)fbits(buf.az[g0 + t]) << 32) | (unsigned)t) : ~0ull;
+  for (int t = tid; t < npad; t += blockDim.x)
+    keys[t] = t < n ? (((unsigned long long)fbits(buf.az[gb + (unsigned)__float_as_int(buf.bpt[g0 + t].w)]) << 32) | (unsigned)t) : ~0ull;
   __syncthreads();
   cta_bitonic(keys, npad);
   bool tie = false;
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+  for (int t = tid; t < n; t += blockDim.x) {
     const unsigned long long key = keys[t];
-    buf.order[g0 + t] = buf.bidx[g0 + (unsigned)key];
+    buf.order[g0 + t] = __float_as_int(buf.bpt[g0 + (unsigned)key].w);
     if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(key >> 32)) tie = true;
   }
   if (tie) atomicOr(&out.flags, F_TIE_AZIMUTH);
@@ -1219,6 +1329,16 @@ __global__ void __launch_bounds__(256) k_unpack_cloud2(const unsigned char* __re
   const unsigned char* rec = raw + (size_t)i * point_step;
   dst[i] = make_float4(load_f32_unaligned(rec + off_x), load_f32_unaligned(rec + off_y), load_f32_unaligned(rec + off_z),
                        off_i >= 0 ? load_f32_unaligned(rec + off_i) : 0.f);
+}
+// the same for a batch: scan b = blockIdx.y, its records at raw + b * S * point_step, its points at dst + b * S
+__global__ void __launch_bounds__(256) k_unpack_cloud2_batch(const unsigned char* __restrict__ raw, float4* __restrict__ dst,
+                                                              const int* __restrict__ n, int S, int point_step, int off_x, int off_y,
+                                                              int off_z, int off_i) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n[b]) return;
+  const unsigned char* rec = raw + ((size_t)b * S + i) * point_step;
+  dst[(size_t)b * S + i] = make_float4(load_f32_unaligned(rec + off_x), load_f32_unaligned(rec + off_y), load_f32_unaligned(rec + off_z),
+                                       off_i >= 0 ? load_f32_unaligned(rec + off_i) : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

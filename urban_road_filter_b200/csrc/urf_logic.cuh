@@ -51,9 +51,9 @@ URF_HD float elev_alpha(float x, float y, float z) {
   return URF_D2F(URF_DADD(deg_d(urfm::asinf_glibc(br)), 90.0));                        // :165
 }
 
-// planar range and azimuth, lidar_segmentation.cpp:245-269
-URF_HD void planar_az(float x, float y, float* d_out, float* az_out) {
-  const float d = URF_D2F(URF_DSQRT(URF_DADD(dsq(x), dsq(y))));
+// planar range and azimuth, lidar_segmentation.cpp:245-269; sxy = (double)x*x + (double)y*y (the caller may share it)
+URF_HD void planar_az_from(float x, float y, double sxy, float* d_out, float* az_out) {
+  const float d = URF_D2F(URF_DSQRT(sxy));
   const float br = clamp_unit(URF_FDIV(fabsf(x), d));
   const double t = deg_d(urfm::asinf_glibc(br));
   float az;
@@ -63,6 +63,36 @@ URF_HD void planar_az(float x, float y, float* d_out, float* az_out) {
   else az = URF_D2F(URF_DSUB(360.0, t));
   *d_out = d;
   *az_out = az;
+}
+URF_HD void planar_az(float x, float y, float* d_out, float* az_out) { planar_az_from(x, y, URF_DADD(dsq(x), dsq(y)), d_out, az_out); }
+
+// everything k_points derives from one point: elevation angle (:148-166) and planar range / azimuth (:245-269), with the
+// squares shared: (x*x + y*y) + z*z is the reference's left-to-right sum, x*x + y*y its planar one
+URF_HD void point_angles(float x, float y, float z, float* alpha, float* d2, float* az) {
+  const double sxy = URF_DADD(dsq(x), dsq(y));
+  const float d = URF_D2F(URF_DSQRT(URF_DADD(sxy, dsq(z))));                           // :148
+  const float br = clamp_unit(URF_FDIV(fabsf(z), d));                                  // :151-157
+  *alpha = z < 0.0f ? URF_D2F(deg_d(urfm::acosf_glibc(br)))                            // :162
+                    : URF_D2F(URF_DADD(deg_d(urfm::asinf_glibc(br)), 90.0));           // :165
+  planar_az_from(x, y, sxy, d2, az);
+}
+
+// maxDistance[k] (lidar_segmentation.cpp:271-274) is the largest (float)sqrt((double)x*x + y*y) of the ring. Square root
+// and narrowing are both monotone, so it equals (float)sqrt(max of the double sums): the kernels keep the maximum of the
+// sums (non-negative doubles order like their bit patterns) and take one square root per ring.
+URF_HD unsigned long long planar_sum_bits(float x, float y) {
+#if defined(__CUDA_ARCH__)
+  return (unsigned long long)__double_as_longlong(URF_DADD(dsq(x), dsq(y)));
+#else
+  const double s = URF_DADD(dsq(x), dsq(y)); unsigned long long u; memcpy(&u, &s, 8); return u;
+#endif
+}
+URF_HD float maxdist_from_bits(unsigned long long u) {
+#if defined(__CUDA_ARCH__)
+  return URF_D2F(URF_DSQRT(__longlong_as_double((long long)u)));
+#else
+  double s; memcpy(&s, &u, 8); return URF_D2F(URF_DSQRT(s));
+#endif
 }
 
 // star-shaped sector of a point, star_shaped_search.cpp:164-173 (+ rectangular beam filter :73-107): sector or -1

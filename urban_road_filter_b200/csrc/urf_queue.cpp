@@ -25,7 +25,8 @@ struct Slot {
   SlotState state = FREE;
   uint64_t seq = 0, tag = 0;
   int n = 0, rc = URF_OK;
-  float* in = nullptr;       // max_points * 4 floats (pinned for the real queue)
+  float* in = nullptr;       // max_points * bytes_per_point bytes (pinned for the real queue)
+  const float* ext = nullptr;   // urf_queue_submit_ref: the caller's buffer is used in place (no copy)
   int32_t* label = nullptr;  // max_points
   urf_result res{};
 };
@@ -36,6 +37,10 @@ struct urf_queue {
   void* user = nullptr;
   bool pinned = false;
   int max_points = 0, max_batch = 1, policy = URF_QUEUE_BLOCK;
+  // record format of the scans: step == 0: (x, y, z, intensity) float4 points; step > 0: raw PointCloud2 records of `step`
+  // bytes (urf_queue_create_cloud2), handed to urf_process_cloud2_batch and unpacked on the device
+  int step = 0, ox = 0, oy = 4, oz = 8, oi = -1;
+  size_t bytes_per_point = 16;
   std::vector<Slot> slots;
   std::mutex mu;
   std::condition_variable cv_free, cv_pending, cv_done;
@@ -90,10 +95,12 @@ void worker_loop(urf_queue* q) {
     ptrs.resize(B); ns.resize(B); outs.assign(B, urf_result{});
     for (int j = 0; j < B; j++) {
       Slot& s = q->slots[idx[j]];
-      ptrs[j] = s.in; ns[j] = s.n;
+      ptrs[j] = s.ext ? s.ext : s.in; ns[j] = s.n;
       outs[j].label = s.label;
     }
-    const int rc = q->fn(q->user, ptrs.data(), ns.data(), B, outs.data());
+    const int rc = q->step == 0 ? q->fn(q->user, ptrs.data(), ns.data(), B, outs.data())
+                                : urf_process_cloud2_batch(static_cast<urf_ctx*>(q->user), reinterpret_cast<const void* const*>(ptrs.data()), ns.data(), B,
+                                                           q->step, q->ox, q->oy, q->oz, q->oi, outs.data(), nullptr);
     {
       std::lock_guard<std::mutex> lk(q->mu);
       for (int j = 0; j < B; j++) {
@@ -106,14 +113,17 @@ void worker_loop(urf_queue* q) {
   }
 }
 
-int create_common(urf_queue** out, urf_queue_process_fn fn, void* user, bool pinned, int max_points, int slots, int max_batch, int policy) {
+int create_common(urf_queue** out, urf_queue_process_fn fn, void* user, bool pinned, int max_points, int slots, int max_batch, int policy,
+                  int step = 0, int ox = 0, int oy = 4, int oz = 8, int oi = -1) {
   if (!out || !fn || max_points < 1 || slots < 1 || max_batch < 1 || (policy != URF_QUEUE_BLOCK && policy != URF_QUEUE_DROP_OLDEST))
     return URF_ERR_INVALID;
   urf_queue* q = new urf_queue;
   q->fn = fn; q->user = user; q->pinned = pinned; q->max_points = max_points; q->max_batch = max_batch; q->policy = policy;
+  q->step = step; q->ox = ox; q->oy = oy; q->oz = oz; q->oi = oi;
+  q->bytes_per_point = step > 0 ? (size_t)step : 16;
   q->slots.resize(slots);
   for (Slot& s : q->slots) {
-    const size_t in_bytes = sizeof(float) * 4 * (size_t)max_points, lab_bytes = sizeof(int32_t) * (size_t)max_points;
+    const size_t in_bytes = q->bytes_per_point * (size_t)max_points, lab_bytes = sizeof(int32_t) * (size_t)max_points;
     s.in = static_cast<float*>(pinned ? urf_pinned_alloc(in_bytes) : std::malloc(in_bytes));
     s.label = static_cast<int32_t*>(pinned ? urf_pinned_alloc(lab_bytes) : std::malloc(lab_bytes));
     if (!s.in || !s.label) {
@@ -138,12 +148,21 @@ int urf_queue_create(urf_queue** out, urf_ctx* ctx, int max_points, int slots, i
   return create_common(out, real_process, ctx, true, max_points, slots, max_batch, policy);
 }
 
+int urf_queue_create_cloud2(urf_queue** out, urf_ctx* ctx, int max_points, int slots, int max_batch, int policy, int point_step, int off_x,
+                            int off_y, int off_z, int off_intensity) {
+  if (!ctx || point_step < 12 || point_step > URF_MAX_POINT_STEP) return URF_ERR_INVALID;
+  for (int o : {off_x, off_y, off_z}) if (o < 0 || o + 4 > point_step) return URF_ERR_INVALID;
+  if (off_intensity >= 0 && off_intensity + 4 > point_step) return URF_ERR_INVALID;
+  return create_common(out, real_process, ctx, true, max_points, slots, max_batch, policy, point_step, off_x, off_y, off_z, off_intensity);
+}
+
 int urf_queue_create_with(urf_queue** out, urf_queue_process_fn fn, void* user, int max_points, int slots, int max_batch, int policy) {
   return create_common(out, fn, user, false, max_points, slots, max_batch, policy);
 }
 
-int urf_queue_submit(urf_queue* q, const float* xyzi, int n, uint64_t tag, int timeout_ms) {
-  if (!q || n < 0 || (n > 0 && !xyzi)) return URF_ERR_INVALID;
+namespace {
+int submit_common(urf_queue* q, const void* data, int n, uint64_t tag, int timeout_ms, bool by_reference) {
+  if (!q || n < 0 || (n > 0 && !data)) return URF_ERR_INVALID;
   if (n > q->max_points) return URF_ERR_CAPACITY;
   int slot = -1;
   {
@@ -167,7 +186,8 @@ int urf_queue_submit(urf_queue* q, const float* xyzi, int n, uint64_t tag, int t
   }
   Slot& s = q->slots[slot];
   bool closed_late = false;
-  if (n > 0) std::memcpy(s.in, xyzi, sizeof(float) * 4 * (size_t)n);
+  if (by_reference) s.ext = static_cast<const float*>(data);
+  else { s.ext = nullptr; if (n > 0) std::memcpy(s.in, data, q->bytes_per_point * (size_t)n); }
   {
     std::lock_guard<std::mutex> lk(q->mu);
     if (q->closed) {                                      // closed while copying: the worker may already be gone
@@ -190,6 +210,22 @@ int urf_queue_submit(urf_queue* q, const float* xyzi, int n, uint64_t tag, int t
   q->cv_pending.notify_one();
   q->cv_done.notify_all();                                // a consumer waiting on a dropped sequence number re-evaluates
   return URF_OK;
+}
+}  // namespace
+
+int urf_queue_submit(urf_queue* q, const float* xyzi, int n, uint64_t tag, int timeout_ms) {
+  if (q && q->step != 0) return URF_ERR_INVALID;           // a record queue takes urf_queue_submit_cloud2
+  return submit_common(q, xyzi, n, tag, timeout_ms, false);
+}
+
+int urf_queue_submit_ref(urf_queue* q, const float* xyzi, int n, uint64_t tag, int timeout_ms) {
+  if (q && q->step != 0) return URF_ERR_INVALID;
+  return submit_common(q, xyzi, n, tag, timeout_ms, true);
+}
+
+int urf_queue_submit_cloud2(urf_queue* q, const void* data, int n_points, uint64_t tag, int timeout_ms) {
+  if (q && q->step == 0) return URF_ERR_INVALID;
+  return submit_common(q, data, n_points, tag, timeout_ms, false);
 }
 
 int urf_queue_next(urf_queue* q, uint64_t* tag, urf_result* out, int timeout_ms) {
