@@ -14,6 +14,8 @@
 #include <atomic>
 #include <random>
 #include "../../urban_road_filter_b200/csrc/urf_math.cuh"
+#include "../../urban_road_filter_b200/csrc/urf_logic.cuh"
+#include "../../urban_road_filter_b200/csrc/urf_host.hpp"
 
 static inline uint32_t bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float fl(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
@@ -121,6 +123,53 @@ int main(int argc, char** argv) {
     }
     bad += b; cnt += c;
     printf("atan2f checked=%llu mismatches=%llu\n", (unsigned long long)cnt.load(), (unsigned long long)bad.load());
+    rc |= bad != 0;
+  }
+  {
+    // star_sector_fast (urf_logic.cuh): every decided point must get the sector the reference's expression gives with the
+    // REAL libm (star_shaped_search.cpp:166-171); undecided points (-1) take the exact path in the product. Random points
+    // in several distributions plus points placed within +-2e-3 degrees of every sector boundary at many radii.
+    float bd[urf::kSectKeys], bo[urf::kSectKeys], Kfi; unsigned char byx[urf::kSectKeys];
+    urf::host_beam_init(bd, bo, byx, &Kfi);
+    auto exact = [&](float x, float y) {
+      float fi = atan2f(y, x);
+      if (fi < 0) fi = (float)((double)fi + 2 * M_PI);
+      int f = (int)(fi * Kfi);
+      if (f >= urf::kSectKeys || f < 0) f = 0;
+      return f;
+    };
+    std::atomic<uint64_t> bad{0}, cnt{0}, undecided{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+      th.emplace_back([&, t]() {
+        std::mt19937_64 g(99 + t);
+        std::uniform_real_distribution<float> U(-100.f, 100.f), S(-1e-3f, 1e-3f);
+        std::uniform_real_distribution<double> R(0.3, 250.0), E(-2e-3, 2e-3);
+        uint64_t b = 0, c = 0, u = 0;
+        for (uint64_t i = t; i < nrand; i += threads) {
+          float y, x;
+          switch (i & 7) {
+            case 0: case 1: y = U(g); x = U(g); break;
+            case 2: y = S(g); x = U(g); break;
+            case 3: y = fl((uint32_t)g()); x = fl((uint32_t)g()); break;      // arbitrary bit patterns (NaN, inf, denormals)
+            case 4: y = U(g); x = S(g) * 1e-3f; break;
+            default: {                                                        // next to a sector boundary
+              const double deg = (double)(g() % 361) + E(g), r = R(g);
+              x = (float)(r * cos(deg * M_PI / 180)); y = (float)(r * sin(deg * M_PI / 180));
+            } break;
+          }
+          const int fast = urf::star_sector_fast(x, y);
+          if (fast < 0) { u++; c++; continue; }
+          if (!std::isfinite(x) || !std::isfinite(y)) { if (b < 3) fprintf(stderr, "sector_fast decided a non-finite point (%a, %a)\n", x, y); b++; }
+          else if (fast != exact(x, y)) { if (b < 3) fprintf(stderr, "sector_fast(%a, %a) = %d, reference %d\n", x, y, fast, exact(x, y)); b++; }
+          c++;
+        }
+        bad += b; cnt += c; undecided += u;
+      });
+    }
+    for (auto& x : th) x.join();
+    printf("sector checked=%llu mismatches=%llu undecided=%llu\n", (unsigned long long)cnt.load(), (unsigned long long)bad.load(),
+           (unsigned long long)undecided.load());
     rc |= bad != 0;
   }
   return rc;

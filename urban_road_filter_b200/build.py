@@ -67,7 +67,7 @@ def build_kat() -> None:
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     tgt = os.path.join(bdir, "math_sweep")
     if _stale(tgt, [os.path.join(kat, "math_sweep.cpp")] + hdrs):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", tgt, os.path.join(kat, "math_sweep.cpp"),
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I/usr/local/cuda/include", "-o", tgt, os.path.join(kat, "math_sweep.cpp"),
                         "-lpthread", "-lm"], check=True)
     tgt = os.path.join(bdir, "libmodel.so")
     if _stale(tgt, [os.path.join(kat, "model_check.cpp")] + hdrs):

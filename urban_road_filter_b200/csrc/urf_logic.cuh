@@ -95,13 +95,48 @@ URF_HD float maxdist_from_bits(unsigned long long u) {
 #endif
 }
 
-// star-shaped sector of a point, star_shaped_search.cpp:164-173 (+ rectangular beam filter :73-107): sector or -1
-URF_HD int star_sector(const DevParams& prm, float x, float y, const float* beam_d, const float* beam_o,
-                       const unsigned char* beam_yx) {
+// star-shaped sector of a point, star_shaped_search.cpp:164-173: f = (int)(fi * Kfi) with fi = atan2f(y, x), wrapped into
+// [0, 2 pi). The exact index needs glibc's atan2f bit for bit:
+URF_HD int star_sector_exact(const DevParams& prm, float x, float y) {
   float fi = urfm::atan2f_glibc(y, x);                                       // :166
   if (fi < 0.0f) fi = URF_D2F(URF_DADD((double)fi, URF_TWO_PI_D));           // :168-169
   int f = URF_F2I_RZ(URF_FMUL(fi, prm.Kfi));                                 // :171
   if (f >= kSectKeys || f < 0) f = 0;   // reference: null-pointer dereference for f == 360 (UB); we wrap
+  return f;
+}
+// ... but only the INTEGER part of fi * Kfi is used, so a cheap angle decides almost every point: a degree-13 odd polynomial
+// for atan on [0, 1] (|error| < 3.5e-7 rad), octant fix-ups, degrees = angle * 57.29578. The value the reference computes
+// lies within 6e-5 degrees of the true angle in degrees (atan2f < 1 ulp, the float rounding of fi + 2 pi, of the product and
+// of Kfi), the cheap one within 3e-5; when the cheap value is at least 1e-3 degrees away from both neighbouring integers
+// the two truncate to the same sector. Everything else (boundaries, the 0/360 wrap, zero / non-finite input) returns -1
+// and takes the exact path. tests/kat/math_sweep.cpp checks "fast < 0 or fast == exact" on random and on near-boundary
+// points; the arithmetic is the same on host and device (single roundings, fmaf).
+URF_HD int star_sector_fast(float x, float y) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool steep = ay > ax;
+  const float t = URF_FDIV(steep ? ax : ay, steep ? ay : ax);                // tan of the angle to the nearer axis, in [0, 1]
+  const float s = URF_FMUL(t, t);
+  float p = 0.006811792496591806f;
+  p = URF_FFMA(p, s, -0.0336042195558548f);
+  p = URF_FFMA(p, s, 0.07962366938591003f);
+  p = URF_FFMA(p, s, -0.1323334276676178f);
+  p = URF_FFMA(p, s, 0.19807815551757812f);
+  p = URF_FFMA(p, s, -0.3331736922264099f);
+  p = URF_FFMA(p, s, 0.9999961256980896f);
+  float a = URF_FMUL(t, p);                                                   // atan(t) in [0, pi / 4]
+  if (steep) a = URF_FSUB(1.57079637f, a);
+  if (x < 0.0f) a = URF_FSUB(3.14159274f, a);
+  if (y < 0.0f) a = URF_FSUB(6.28318548f, a);
+  const float u = URF_FMUL(a, 57.2957802f);                                   // degrees in [0, 360]
+  const int f = URF_F2I_RZ(u);
+  const float fr = URF_FSUB(u, (float)f);
+  return (fr > 1e-3f && fr < 0.999f && f >= 0 && f < kSectKeys) ? f : -1;     // NaN / inf fail the compares
+}
+// sector or -1 (outside the rectangular beam filter :73-107)
+URF_HD int star_sector(const DevParams& prm, float x, float y, const float* beam_d, const float* beam_o,
+                       const unsigned char* beam_yx) {
+  int f = star_sector_fast(x, y);
+  if (f < 0) f = star_sector_exact(prm, x, y);
   if (prm.starbeam) {                                                        // :73-107
     const float bd = beam_d[f], bo = beam_o[f];
     if (beam_yx[f]) { const float c = URF_FMUL(bd, y); if (!(URF_FSUB(c, bo) < x && x < URF_FADD(c, bo))) return -1; }

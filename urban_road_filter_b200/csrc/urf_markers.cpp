@@ -7,6 +7,7 @@
 // max_distance^2, computed in the coordinate type float) — PARITY UNPINNED for simple_poly_allow=1, see DESIGN.md.
 #include <cmath>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "../../include/urf.h"
@@ -26,28 +27,38 @@ float sq_dist_seg(const XY& p, const XY& a, const XY& b) {
   return dx * dx + dy * dy;
 }
 
-void dp_mark(const std::vector<XY>& pts, std::vector<char>& keep, size_t first, size_t last, float max_sq) {
-  if (last <= first + 1) return;
-  float md = -1.f;
-  size_t cand = first;
-  for (size_t i = first + 1; i < last; i++) {
-    const float d = sq_dist_seg(pts[i], pts[first], pts[last]);
-    if (d > md) { md = d; cand = i; }
-  }
-  if (max_sq < md) {
-    keep[cand] = 1;
-    dp_mark(pts, keep, first, cand, max_sq);
-    dp_mark(pts, keep, cand, last, max_sq);
-  }
-}
-
+// Douglas-Peucker without recursion: a work list of open spans [first, last] whose end points are kept; the farthest
+// intermediate point of a span (strictly farther than every earlier one) is kept iff its squared distance to the span's
+// chord exceeds max_distance^2, and splits the span in two. (oracle/shim/boost/geometry.hpp states the same published
+// algorithm recursively, for the reference build; tests/test_markers.py checks both against the algorithm's properties —
+// end points kept, output nested in max_distance, every dropped point within max_distance of the output — and each other.)
 std::vector<XY> simplify(const std::vector<XY>& in, float max_distance) {
-  if (in.size() <= 2 || max_distance < 0.f) return in;
-  std::vector<char> keep(in.size(), 0);
-  keep.front() = keep.back() = 1;
-  dp_mark(in, keep, 0, in.size() - 1, max_distance * max_distance);
+  const size_t n = in.size();
+  if (n <= 2 || max_distance < 0.f) return in;
+  const float max_sq = max_distance * max_distance;
+  std::vector<char> keep(n, 0);
+  keep[0] = keep[n - 1] = 1;
+  std::vector<std::pair<size_t, size_t>> open;
+  open.emplace_back(0, n - 1);
+  while (!open.empty()) {
+    const std::pair<size_t, size_t> span = open.back();
+    open.pop_back();
+    if (span.second <= span.first + 1) continue;
+    float far = -1.f;
+    size_t at = span.first;
+    for (size_t i = span.first + 1; i < span.second; i++) {
+      const float d = sq_dist_seg(in[i], in[span.first], in[span.second]);
+      if (far < d) { far = d; at = i; }
+    }
+    if (max_sq < far) {
+      keep[at] = 1;
+      open.emplace_back(at, span.second);
+      open.emplace_back(span.first, at);
+    }
+  }
   std::vector<XY> out;
-  for (size_t i = 0; i < in.size(); i++) if (keep[i]) out.push_back(in[i]);
+  out.reserve(n);
+  for (size_t i = 0; i < n; i++) if (keep[i]) out.push_back(in[i]);
   return out;
 }
 

@@ -34,6 +34,7 @@
 #define URF_DDIV(a, b) __ddiv_rn((a), (b))
 #define URF_DSQRT(a) __dsqrt_rn((a))
 #define URF_DFMA(a, b, c) __fma_rn((a), (b), (c))
+#define URF_FFMA(a, b, c) __fmaf_rn((a), (b), (c))
 #define URF_F2I(x) __float_as_int((x))
 #define URF_I2F(x) __int_as_float((x))
 #define URF_FABS(x) fabsf((x))
@@ -51,6 +52,7 @@
 #define URF_DDIV(a, b) ((double)(a) / (double)(b))
 #define URF_DSQRT(a) sqrt((a))
 #define URF_DFMA(a, b, c) fma((double)(a), (double)(b), (double)(c))   /* correctly rounded with or without hardware FMA */
+#define URF_FFMA(a, b, c) fmaf((float)(a), (float)(b), (float)(c))
 static inline int32_t urf_f2i_(float x) { int32_t i; memcpy(&i, &x, 4); return i; }
 static inline float urf_i2f_(int32_t i) { float x; memcpy(&x, &i, 4); return x; }
 #define URF_F2I(x) urf_f2i_((x))
