@@ -44,4 +44,8 @@ inline void spin() {}
 
 #ifndef ROS_INFO
 #define ROS_INFO(...) do { } while (0)
+#define ROS_ERROR(...) do { std::fprintf(stderr, "[ROS_ERROR] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
+#define ROS_FATAL(...) do { std::fprintf(stderr, "[ROS_FATAL] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
+#define ROS_ERROR_THROTTLE(period, ...) do { std::fprintf(stderr, "[ROS_ERROR] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
+#define ROS_WARN_THROTTLE(period, ...) do { std::fprintf(stderr, "[ROS_WARN] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
 #endif

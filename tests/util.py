@@ -23,6 +23,19 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 VERT_TOL = 1e-4     # metres: BASELINE.json north_star tolerance for curb-polyline vertices
 
 
+_SCAN_CACHE: dict = {}
+
+
+def cached_scan(shape, seed, order):
+    """make_scan with a one-entry cache per (shape, seed, order): the four C5 fixtures share one 1M-point cloud."""
+    key = (shape, seed, order)
+    if key not in _SCAN_CACHE:
+        if len(_SCAN_CACHE) > 3:
+            _SCAN_CACHE.clear()
+        _SCAN_CACHE[key] = make_scan(shape, seed, order=order)
+    return _SCAN_CACHE[key]
+
+
 def golden_names() -> list[str]:
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
@@ -37,7 +50,7 @@ class Golden:
         if "cloud" in z.files:
             self.cloud = z["cloud"]
         else:
-            self.cloud = make_scan(rc["shape"], rc["seed"], order=rc["order"]) if rc["kind"] == "scan" else random_cloud(rc["n"], rc["seed"])
+            self.cloud = cached_scan(rc["shape"], rc["seed"], rc["order"]) if rc["kind"] == "scan" else random_cloud(rc["n"], rc["seed"])
             if "head" in rc:
                 self.cloud = self.cloud[: rc["head"]].copy()
         sha = hashlib.sha256(np.ascontiguousarray(self.cloud).tobytes()).hexdigest()

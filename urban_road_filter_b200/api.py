@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from .ctypes_abi import (QUEUE_PROCESS_FN, URF_ERR_CLOSED, URF_ERR_TIMEOUT, URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_QUEUE_BLOCK,
+from .ctypes_abi import (UrfMqStats, QUEUE_PROCESS_FN, URF_ERR_CLOSED, URF_ERR_TIMEOUT, URF_MAX_CHANNELS, URF_MAX_VERTS, URF_OK, URF_QUEUE_BLOCK,
                          URF_QUEUE_DROP_OLDEST, URF_TOO_FEW_POINTS, UrfClouds, UrfParams, UrfQueueStats, UrfResult, UrfStrip,
                          make_params)
 
@@ -84,6 +84,20 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.urf_queue_close.argtypes = [vp]
     lib.urf_queue_destroy.restype = None
     lib.urf_queue_destroy.argtypes = [vp]
+    lib.urf_queue_submit_ref.argtypes = [vp, vp, ip, C.c_uint64, ip]
+    lib.urf_queue_create_cloud2.argtypes = [C.POINTER(vp), vp, ip, ip, ip, ip, ip, ip, ip, ip, ip]
+    lib.urf_queue_submit_cloud2.argtypes = [vp, vp, ip, C.c_uint64, ip]
+    lib.urf_mq_create.argtypes = [C.POINTER(vp), C.POINTER(ip), ip, ip, ip, ip, C.POINTER(UrfParams)]
+    lib.urf_mq_create_with.argtypes = [C.POINTER(vp), QUEUE_PROCESS_FN, C.POINTER(vp), ip, ip, ip, ip]
+    lib.urf_mq_set_params.argtypes = [vp, C.POINTER(UrfParams)]
+    lib.urf_mq_submit.argtypes = [vp, vp, ip, C.c_uint64, ip]
+    lib.urf_mq_submit_ref.argtypes = [vp, vp, ip, C.c_uint64, ip]
+    lib.urf_mq_next.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(UrfResult), ip]
+    lib.urf_mq_get_stats.argtypes = [vp, C.POINTER(UrfMqStats)]
+    lib.urf_mq_close.argtypes = [vp]
+    lib.urf_mq_close.restype = None
+    lib.urf_mq_destroy.argtypes = [vp]
+    lib.urf_mq_destroy.restype = None
     lib.urf_test_math.argtypes = [ip, ip, vp, vp, vp, ip]
     lib.urf_debug_fetch.argtypes = [vp, ip, ip, vp, C.c_size_t]
     lib.urf_debug_sizeof_tab.restype = C.c_size_t
@@ -335,6 +349,82 @@ class Detector:
         a = np.zeros(max(count, 1), dtype)
         self._check(self.lib.urf_debug_fetch(self._ctx, scan, what, a.ctypes.data, a.nbytes if count else 0), "urf_debug_fetch")
         return a[:count]
+
+
+class MultiGpuQueue:
+    """One ingest stream over several GPUs (include/urf.h urf_mq, BASELINE config 4): a context + streaming queue per device,
+    every scan goes to the device with the fewest scans in flight, results come back in submission order. Any number of
+    producer threads, one consumer. `by_reference` submits hand the array to the library without a copy: keep it alive and
+    unchanged until its result has come back."""
+
+    def __init__(self, devices, max_points: int, slots_per_device: int = 8, max_batch: int = 4, params: UrfParams | None = None,
+                 process_fn=None):
+        self.lib = load_library()
+        self._m = C.c_void_p()
+        self.max_points = max_points
+        self._cb = None
+        if process_fn is not None:                      # tests: stand-in devices, no GPU
+            self._cb = QUEUE_PROCESS_FN(process_fn)
+            rc = self.lib.urf_mq_create_with(C.byref(self._m), self._cb, None, len(devices), max_points, slots_per_device, max_batch)
+        else:
+            dv = (C.c_int * len(devices))(*devices)
+            rc = self.lib.urf_mq_create(C.byref(self._m), dv, len(devices), max_points, slots_per_device, max_batch,
+                                        C.byref(params) if params is not None else None)
+        if rc != URF_OK:
+            raise UrfError(rc, "urf_mq_create", self.lib.urf_last_cuda_error(None).decode())
+        self._keep = {}
+
+    def set_params(self, prm: UrfParams):
+        rc = self.lib.urf_mq_set_params(self._m, C.byref(prm))
+        if rc != URF_OK:
+            raise UrfError(rc, "urf_mq_set_params")
+
+    def submit(self, cloud: np.ndarray, tag: int = 0, timeout_ms: int = -1, by_reference: bool = False) -> int:
+        pts = np.ascontiguousarray(cloud, np.float32)
+        if by_reference:
+            self._keep[tag] = pts
+            rc = self.lib.urf_mq_submit_ref(self._m, pts.ctypes.data, pts.shape[0], tag, timeout_ms)
+        else:
+            rc = self.lib.urf_mq_submit(self._m, pts.ctypes.data, pts.shape[0], tag, timeout_ms)
+        if rc not in (URF_OK, URF_ERR_TIMEOUT, URF_ERR_CLOSED):
+            raise UrfError(rc, "urf_mq_submit")
+        return rc
+
+    def next(self, timeout_ms: int = -1):
+        """(tag, ScanResult) of the oldest scan, or None on timeout / when the closed queue is drained."""
+        lab = np.full(self.max_points, -1, np.int32)
+        res = UrfResult()
+        res.label = lab.ctypes.data_as(C.POINTER(C.c_int32))
+        tag = C.c_uint64()
+        rc = self.lib.urf_mq_next(self._m, C.byref(tag), C.byref(res), timeout_ms)
+        if rc in (URF_ERR_TIMEOUT, URF_ERR_CLOSED):
+            return None
+        if rc != URF_OK:
+            raise UrfError(rc, "urf_mq_next")
+        self._keep.pop(tag.value, None)
+        r = ScanResult()
+        for f in ("status", "n_in", "n_roi", "n_rings", "n_order", "n_road", "n_curb", "n_vert", "flags"):
+            setattr(r, f, int(getattr(res, f)))
+        r.label = lab[: r.n_in].copy()
+        r.ring = r.order = r.ring_start = None
+        r.vert = np.ctypeslib.as_array(res.vert).reshape(URF_MAX_VERTS, 4)[: r.n_vert].copy()
+        return tag.value, r
+
+    def stats(self) -> dict:
+        st = UrfMqStats()
+        self.lib.urf_mq_get_stats(self._m, C.byref(st))
+        n = st.n_devices
+        return dict(n_devices=n, pending=st.pending, submitted=list(st.submitted[:n]), delivered=list(st.delivered[:n]),
+                    batches=list(st.batches[:n]), largest_batch=list(st.largest_batch[:n]))
+
+    def close(self):
+        if self._m:
+            self.lib.urf_mq_close(self._m)
+
+    def destroy(self):
+        if self._m:
+            self.lib.urf_mq_destroy(self._m)
+            self._m = C.c_void_p()
 
 
 class ScanQueue:

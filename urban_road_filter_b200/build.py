@@ -84,12 +84,26 @@ def build_kat() -> None:
         subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-o", tgt, *qsrc], check=True)
 
 
+def build_tools() -> str:
+    """Host tools that link liburf_b200.so (tools/mq_bench: throughput of the multi-GPU ingest)."""
+    bdir = os.path.join(ROOT, "build")
+    os.makedirs(bdir, exist_ok=True)
+    tgt = os.path.join(bdir, "mq_bench")
+    src = os.path.join(ROOT, "tools", "mq_bench.cpp")
+    if _stale(tgt, [src, os.path.join(ROOT, "include", "urf.h"), LIB]):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-o", tgt, src, "-L" + PKG, "-l:liburf_b200.so",
+                        "-Wl,-rpath,$ORIGIN/../urban_road_filter_b200"], check=True)
+    return tgt
+
+
 def build_glue() -> str:
     """ros/urf_node.cpp (the ROS glue) compiled against the shim ROS/PCL headers of oracle/shim + a C test entry."""
     bdir = os.path.join(ROOT, "build")
     os.makedirs(bdir, exist_ok=True)
     tgt = os.path.join(bdir, "libglue.so")
-    deps = [os.path.join(ROOT, "ros", "urf_node.cpp"), os.path.join(ROOT, "tests", "kat", "glue_entry.cpp"),
+    deps = [os.path.join(ROOT, "ros", "urf_node.cpp"), os.path.join(ROOT, "ros", "urf_node_cloud2.cpp"),
+            os.path.join(ROOT, "ros", "urf_glue_common.hpp"), os.path.join(ROOT, "oracle", "shim", "shim_capture.h"),
+            os.path.join(ROOT, "tests", "kat", "glue_entry.cpp"),
             os.path.join(ROOT, "include", "urf.h"), LIB]
     if _stale(tgt, deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "oracle", "shim"),

@@ -84,6 +84,15 @@ class UrfQueueStats(C.Structure):
                 ("batches", C.c_uint64), ("largest_batch", C.c_int32), ("pending", C.c_int32), ("reserved", C.c_int32)]
 
 
+URF_MQ_MAX_DEVICES = 16
+
+
+class UrfMqStats(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("pending", C.c_int32), ("submitted", C.c_uint64 * URF_MQ_MAX_DEVICES),
+                ("delivered", C.c_uint64 * URF_MQ_MAX_DEVICES), ("batches", C.c_uint64 * URF_MQ_MAX_DEVICES),
+                ("largest_batch", C.c_int32 * URF_MQ_MAX_DEVICES)]
+
+
 URF_QUEUE_BLOCK, URF_QUEUE_DROP_OLDEST = 0, 1
 URF_ERR_TIMEOUT, URF_ERR_CLOSED = -6, -7
 # int (*)(void* user, const float* const* xyzi, const int* n, int batch, urf_result* outs)
