@@ -267,6 +267,8 @@ def main():
     ap.add_argument("--sub", type=int, default=-1, help="scans per sub-batch of a device-resident step (library option 5)")
     ap.add_argument("--graph", type=int, default=-1, help="replay a device-resident step as one CUDA graph (library option 6)")
     ap.add_argument("--reuse", type=int, default=-1, help="sub-batches of a stream share a workspace slot (library option 7)")
+    ap.add_argument("--rd", type=int, default=-1, help="k_ring_detect variant (library option 8: 8, 6, 5 or 4 = four positions per thread)")
+    ap.add_argument("--mk", type=int, default=-1, help="marker search variant (library option 9: 0 cluster of 8 CTAs, 1 one CTA per scan)")
     ap.add_argument("--sweep", default="", help="tuning: ';'-separated groups,sub,graph,reuse settings timed one after the other")
     ap.add_argument("--no-star", action="store_true", help="detector ablation (BASELINE config 5): star_shaped_method off")
     ap.add_argument("--no-xzero", action="store_true", help="detector ablation: x_zero_method off")
@@ -319,7 +321,7 @@ def main():
     det = api.Detector(max_points=n, max_batch=B, device=local, params=prm)
     if args.groups:
         det.set_option(2, args.groups)
-    for opt, v in ((5, args.sub), (6, args.graph), (7, args.reuse)):
+    for opt, v in ((5, args.sub), (6, args.graph), (7, args.reuse), (8, args.rd), (9, args.mk)):
         if v >= 0:
             det.set_option(opt, v)
     lib, ctx = det.lib, det._ctx
@@ -348,8 +350,13 @@ def main():
     if args.sweep:                       # tuning: scheduling settings of the device-resident step, same process, same data
         ref_road = sum(o.n_road for o in outs)
         for cfg in args.sweep.split(";"):
-            g, sub, graph, reuse = (int(v) for v in cfg.split(","))
+            f = [int(v) for v in cfg.split(",")]
+            g, sub, graph, reuse = f[:4]
             det.set_option(2, g); det.set_option(5, sub); det.set_option(6, graph); det.set_option(7, reuse)
+            if len(f) > 4:
+                det.set_option(8, f[4])                 # k_ring_detect variant
+            if len(f) > 5:
+                det.set_option(9, f[5])                 # marker search: cluster (0) or one CTA per scan (1)
             for _ in range(3):
                 step_device()
             torch.cuda.synchronize()
@@ -450,6 +457,28 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    # ---- the lean entry point (opt-in ABI addition): packed xyz in (12 B/pt), int8 labels out (1 B/pt), same results
+    h_xyz = [torch.from_numpy(np.ascontiguousarray(c[:, :3])).pin_memory() for c in clouds]
+    h_l8 = [torch.empty(n, dtype=torch.int8).pin_memory() for _ in range(B)]
+    xptrs = (C.c_void_p * B)(*[t.data_ptr() for t in h_xyz])
+    l8ptrs = (C.c_void_p * B)(*[t.data_ptr() for t in h_l8])
+    res_lean = (UrfResult * B)()
+
+    def step_lean():
+        rc = lib.urf_process_batch_xyz(ctx, xptrs, ns, B, res_lean, l8ptrs)
+        assert rc == 0, lib.urf_last_cuda_error(ctx)
+
+    for _ in range(args.warmup):
+        step_lean()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_lean()
+    torch.cuda.synchronize()
+    lean_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    assert sum(r.n_road for r in res_lean) == n_road, "lean and default host paths disagree"
+    assert all(bool((h_l8[b].to(torch.int32) == h_lab[b]).all()) for b in range(0, B, max(1, B // 4))), "int8 labels differ from the int32 ones"
     if with_order is not None:               # the same call with res[b].order set: the order comes back too (+4 B per point)
         h_ord = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(B)]
         for b in range(B):
@@ -471,7 +500,7 @@ def main():
     assert sum(r.n_road for r in res) == n_road, "device-resident and host-buffer paths disagree"
 
     # max over ranks
-    dev_ms, e2e_ms = allreduce_max([dev_ms, e2e_s * 1e3], device="cuda")
+    dev_ms, e2e_ms, lean_ms = allreduce_max([dev_ms, e2e_s * 1e3, lean_ms], device="cuda")
     if with_order is not None:
         with_order["dev_ms"], with_order["e2e_ms"] = allreduce_max([with_order["dev_ms"], with_order["e2e_ms"]], device="cuda")
     total_road = allreduce_sum([n_road], device="cuda")[0]
@@ -510,6 +539,9 @@ def main():
                          "kernel_ms_per_step": {k: v for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1])}},
             "clocks": clocks,
         }
+        # same scans through urf_process_batch_xyz: 12-byte points in, int8 labels out (13 B per point over PCIe instead of 20)
+        line["e2e_lean"] = {"value": scans / (lean_ms / 1e3), "unit": "scans/s", "h2d_bytes_per_step": B * n * 12,
+                            "d2h_bytes_per_step": B * n + B * C.sizeof(UrfResult), "entry": "urf_process_batch_xyz (opt-in; e2e above is the float4 / int32 drop-in call)"}
         if with_order is not None:           # labels + vertices + emission order (k_sort_rings inside the timed region)
             line["with_order"] = {"value": scans / (with_order["dev_ms"] / 1e3), "unit": "scans/s", "ms_per_step": with_order["dev_ms"] / K,
                                   "e2e": {"value": scans / (with_order["e2e_ms"] / 1e3), "unit": "scans/s", "h2d_bytes_per_step": B * n * 16,

@@ -199,7 +199,7 @@ def test_gpu_device_resident_entry_point(det, port):
     torch.cuda.synchronize()
     rc = det.lib.urf_process_batch_device(det._ctx, x.data_ptr(), S, n, 3, lab.data_ptr(), outs)
     assert rc == 0
-    assert det.last_launch_count() >= 15 and det.last_device_ms() > 0
+    assert det.last_launch_count() >= 10 and det.last_device_ms() > 0
     host = lab.cpu().numpy()
     for b, c in enumerate(clouds):
         o = port.run(c, prm)

@@ -29,6 +29,9 @@ struct urf_ctx {
   // round-robin to the `groups` streams, the whole fork/join captured once as a CUDA graph (bgraph) and replayed; with
   // `slot_reuse` the sub-batches of a stream share one workspace slot (working set = groups * sub scans, L2-resident)
   int sub = 0;
+  int markers_variant = 0;             // 0: cluster of eight CTAs per scan (k_markers), 1: one CTA per scan (k_markers1) (tuning option 9)
+  int rd_variant = 4;                  // 4 / 45 / 46: k_ring_detect4 (four positions per thread; default curb_points only) at 4 / 5 / 6 CTAs per SM;
+                                       // 8 / 6 / 5: k_ring_detect (one position per thread) (tuning option 8)
   bool slot_reuse = false, batch_graph = false;
   cudaGraphExec_t bexec = nullptr;
   struct { int B = -1, S = -1, sub = -1, G = -1, order = -1; bool reuse = false; const void* in = nullptr; void* label = nullptr; void* orderp = nullptr; unsigned long long version = 0; int launches = 0; } bkey;
@@ -109,7 +112,7 @@ DevBuffers slot_view(const DevBuffers& a, int b0, int w0, int S, int T, int chan
   v.in += o; v.label += o; v.order += o; v.n += b0; v.out += b0;
   if (v.label8) v.label8 += o;
   v.alpha_v += w; v.mark += w; v.ringid += w; v.sect += w; v.bpt += w; v.spt += w; v.ssorted += w;
-  v.az += w; v.d2 += w; v.roadlist += w; v.sortbuf += 2 * w;
+  v.az += w; v.d2 += w; v.roadlist += w; v.roadcnt += (size_t)w0 * ((S + 31) >> 5); v.sortbuf += 2 * w;
   v.Tf += (size_t)w0 * channels * kTStride; v.Tb += (size_t)w0 * channels * kTStride;
   v.lut += (size_t)w0 * (kElevBins + 1); v.firstidx += (size_t)w0 * (kElevBins + 1);
   v.hist += (size_t)w0 * T * kRingKeys;
@@ -154,15 +157,25 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
     const int gbig = std::max(4, std::min(kSectKeys, 2048 / B));
     const dim3 gscan((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B);
     K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, dp, S));
-    K("k_star_sort_big", k_star_sort_big<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, S));
+    K("k_star_sort_big", k_star_sort_big<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, dp, S));
     K("k_star_scan", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S));
     if (dp.star_prefix)            // sectors whose edge search ran off the near-first prefix: full sort, search resumed
-      K("k_star_refine", k_star_refine<<<dim3(std::max(8, std::min(kSectKeys, 4096 / B)), B), 32, 0, st>>>(buf, dp, S));
+      K("k_star_refine", k_star_refine<<<dim3(std::max(8, std::min(kSectKeys, 4096 / B)), B), 256, kStarCtaSmem, st>>>(buf, dp, S));
   }
-  K("k_ring_detect", k_ring_detect<8><<<gpts, 256, 0, st>>>(buf, dp, S));   // 8 CTAs/SM (32 registers): measured 2 % faster than 6, 25 % faster than 4
-  K("k_tabs", k_tabs<<<dim3(kTabCtas, B), kTabThreads, 0, st>>>(buf, dp));          // cluster of kTabCtas CTAs per scan
+  const dim3 gtile((S + kTile4 - 1) / kTile4, B);
+  if (ctx->rd_variant == 4 && dp.curbPoints == 5)        // four positions per thread (default curb_points only)
+    K("k_ring_detect4", k_ring_detect4<4><<<gtile, 256, 0, st>>>(buf, dp, S));
+  else if (ctx->rd_variant == 45 && dp.curbPoints == 5) K("k_ring_detect4", k_ring_detect4<5><<<gtile, 256, 0, st>>>(buf, dp, S));
+  else if (ctx->rd_variant == 46 && dp.curbPoints == 5) K("k_ring_detect4", k_ring_detect4<6><<<gtile, 256, 0, st>>>(buf, dp, S));
+  else if (ctx->rd_variant == 6) K("k_ring_detect", k_ring_detect<6><<<gpts, 256, 0, st>>>(buf, dp, S));
+  else if (ctx->rd_variant == 5) K("k_ring_detect", k_ring_detect<5><<<gpts, 256, 0, st>>>(buf, dp, S));
+  else K("k_ring_detect", k_ring_detect<8><<<gpts, 256, 0, st>>>(buf, dp, S));   // 8 CTAs/SM (32 registers)
+  K("k_tab1", k_tab1<<<dim3((dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
+  K("k_reach", k_reach<<<dim3((2 * kDegBins + 7) / 8, B), 256, 0, st>>>(buf, dp));
+  K("k_tab2", k_tab2<<<dim3((dp.channels + kTab2Rings - 1) / kTab2Rings, B), kTab2Rings * 64, 0, st>>>(buf, dp));
   K("k_label", k_label<<<gpts, 256, 0, st>>>(buf, dp, S));
-  K("k_markers", k_markers<<<dim3(kMarkCtas, B), kMarkThreads, 0, st>>>(buf, S));   // cluster of kMarkCtas CTAs per scan
+  if (ctx->markers_variant == 1) K("k_markers1", k_markers1<<<B, kMark1Threads, 0, st>>>(buf, S));   // one CTA per scan
+  else K("k_markers", k_markers<<<dim3(kMarkCtas, B), kMarkThreads, 0, st>>>(buf, S));              // cluster of kMarkCtas CTAs per scan
   if (want_order) K("k_sort_rings", k_sort_rings<<<dim3(dp.channels, B), 256, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S));
 #undef K
   if (last) CK(cudaEventRecord(ctx->ev1, st));
@@ -300,6 +313,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   TRY(dalloc(ctx, &b.az, P));
   TRY(dalloc(ctx, &b.d2, P));
   TRY(dalloc(ctx, &b.roadlist, P));
+  TRY(dalloc(ctx, &b.roadcnt, P / 32 + (size_t)max_batch + 1));
   TRY(dalloc(ctx, &b.Tf, (size_t)max_batch * kTStride * URF_MAX_CHANNELS));
   TRY(dalloc(ctx, &b.Tb, (size_t)max_batch * kTStride * URF_MAX_CHANNELS));
   TRY(dalloc(ctx, &b.lut, (size_t)max_batch * (kElevBins + 1)));
@@ -333,6 +347,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
     ctx->dp.Kfi = Kfi;
   }
   CKF(cudaFuncSetAttribute(k_star_sort_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
+  CKF(cudaFuncSetAttribute(k_star_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStarCtaSmem));
   CKF(cudaFuncSetAttribute(k_sort_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kRingSmemKeys * sizeof(unsigned long long))));
   urf_default_params(&ctx->params);
   const char* fe = std::getenv("URF_FORCE_EXACT_REGISTRATION");
@@ -409,6 +424,8 @@ int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (option == 5) { ctx->sub = value < 0 ? 0 : value; return URF_OK; }
   if (option == 6) { ctx->batch_graph = value != 0; return URF_OK; }
   if (option == 7) { ctx->slot_reuse = value != 0; return URF_OK; }
+  if (option == 8) { ctx->rd_variant = value; return URF_OK; }
+  if (option == 9) { ctx->markers_variant = value; return URF_OK; }
   if (option == 1) {                   // value = number of event slots (0 = off)
     CK(cudaStreamSynchronize(ctx->stream));               // events of the previous setting may still be pending
     if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; ctx->g_B = -1; }

@@ -90,7 +90,8 @@ struct DevBuffers {
   float4* ssorted;       // [P]   sector buckets sorted by r
   float* az;             // [P]   azimuth per input point (ROI points only)
   float* d2;             // [P]   planar range per input point (ROI points only)
-  uint4* roadlist;       // [P]   compact list of road points: (bin | ring << 16, azimuth bits, range bits, input index)
+  uint4* roadlist;       // [P]   road points, 32 slots per warp of input points: (bin | ring << 16, azimuth bits, range bits, input index)
+  unsigned char* roadcnt; // [B][ceil(S / 32)] road points of each input warp (entries used in its 32 list slots)
   float* Tf;             // [B][channels][kTStride] forward threshold table (urf_logic.cuh build_T_row)
   float* Tb;             // [B][channels][kTStride] backward threshold table
   unsigned short* lut;   // [B][kElevBins + 1] ring-search start per fine elevation bin

@@ -9,7 +9,7 @@
 //   k_reset -> k_points -> k_register -> k_assign -> k_scan_offsets (+ exact re-registration of refuted scans)
 //   -> k_scatter -> k_star_sort_warp (near-first) -> k_star_sort_big (large sectors, exact fallback) -> k_star_scan
 //   -> k_star_refine (sectors without an edge in their prefix: full sort, walk resumed)
-//   -> k_ring_detect -> k_tab1 -> k_reach -> k_tab2 -> k_label (input order) -> k_dmax -> k_best -> k_verts
+//   -> k_ring_detect -> k_tab1 -> k_reach -> k_tab2 -> k_label (input order) -> k_markers (cluster of 8 CTAs per scan)
 //   [-> k_sort_rings when the emission order is requested]
 //   PointCloud2 entry points: k_unpack_cloud2 in front, k_pack_count -> k_pack_scan -> k_pack_write behind
 #pragma once
@@ -276,24 +276,43 @@ __device__ __forceinline__ bool assign_chunk(const DevBuffers& buf, const DevPar
                                              bool verify, const float* s_angle, const int* s_regidx, const int* regorder, int R,
                                              const unsigned short* __restrict__ lut, unsigned* cnt, int lane) {
   bool violation = false;
-  for (int it = 0; it < kChunk / 32; it++) {
-    const int i = chunk * kChunk + it * 32 + lane;
-    int ring = -1;
-    if (i < n) {
-      const unsigned g = scan_base(b, S) + (unsigned)i;
-      const float a = buf.alpha_v[g];
-      const bool kept = live && a >= 0.0f;
-      if (kept) {
-        int lo;
-        ring = assign_ring_from(s_angle, R, a, prm.interval, lut[elev_bin(a)], &lo);
-        if (verify && registration_violation(s_angle, s_regidx, regorder, R, prm.channels, prm.interval, a, i, lo)) violation = true;
-      }
-      buf.ringid[g] = kept ? (short)ring : (short)-2;     // -2: not part of the ROI cloud (k_label writes URF_LABEL_OUTSIDE)
+  // two halves of eight iterations: the eight elevation loads are issued together, then the eight table look-ups they
+  // address, and only then the (short, shared-memory) ring searches — two memory round trips per half instead of sixteen
+  constexpr int H = 8;
+  static_assert((kChunk / 32) % H == 0, "chunk iterations come in groups of H");
+#pragma unroll 1
+  for (int h0 = 0; h0 < kChunk / 32; h0 += H) {
+    float av[H];
+    unsigned short start[H];
+#pragma unroll
+    for (int u = 0; u < H; u++) {
+      const int i = chunk * kChunk + (h0 + u) * 32 + lane;
+      av[u] = i < n ? buf.alpha_v[scan_base(b, S) + (unsigned)i] : -1.0f;
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, ring);
-    if (ring >= 0 && lane == __ffs(peers) - 1) cnt[ring] += __popc(peers);
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < H; u++) start[u] = (live && av[u] >= 0.0f) ? lut[elev_bin(av[u])] : (unsigned short)0;
+#pragma unroll
+    for (int u = 0; u < H; u++) {
+      const int i = chunk * kChunk + (h0 + u) * 32 + lane;
+      int ring = -1;
+      if (i < n) {
+        const float a = av[u];
+        const bool kept = live && a >= 0.0f;
+        if (kept) {
+          int lo;
+          ring = assign_ring_from(s_angle, R, a, prm.interval, start[u], &lo);
+          if (verify && registration_violation(s_angle, s_regidx, regorder, R, prm.channels, prm.interval, a, i, lo)) violation = true;
+        }
+        buf.ringid[scan_base(b, S) + (unsigned)i] = kept ? (short)ring : (short)-2;   // -2: not part of the ROI cloud (k_label writes URF_LABEL_OUTSIDE)
+      }
+      // histogram: a ring-major scan puts one ring into a warp (one add of 32), a column-major one 32 different rings
+      // (32 conflict-free shared atomics); results unused, so no read-modify-write chain between iterations
+      const int ring0 = __shfl_sync(0xffffffffu, ring, 0);
+      if (__all_sync(0xffffffffu, ring == ring0)) { if (lane == 0 && ring0 >= 0) atomicAdd(&cnt[ring0], 32u); }
+      else if (ring >= 0) atomicAdd(&cnt[ring], 1u);
+    }
   }
+  __syncwarp();
   unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
   for (int t = lane; t < kRingKeys; t += 32) row[t] = cnt[t];
   return violation;
@@ -399,9 +418,12 @@ __global__ void __launch_bounds__(1024) k_scan_offsets(DevBuffers buf, DevParams
 // ---------------------------------------------------------------------------------------------------------------------
 // k_scatter: stable scatter of every point into its ring bucket (input order inside a ring, lidar_segmentation.cpp:221-
 // 277) and unordered scatter into its star sector (the radius sort that follows breaks ties by input index, which is the
-// push_back order of star_shaped_search.cpp:173).
-// Ring buckets are written coalesced: the warp first ranks its 512-point chunk by ring in shared memory, then walks the
-// chunk in ring order so that consecutive lanes write consecutive bucket slots.
+// push_back order of star_shaped_search.cpp:173). One warp per chunk of kChunk points, kWarpsPerBlock chunks per CTA.
+// Sectors: every point takes a rank inside its sector from a CTA-wide shared counter; after a barrier one thread per
+// sector that occurs in the CTA reserves the CTA's slots from the scan's sector cursor with ONE global atomic (all of them
+// in flight together), and after a second barrier the records are written to base + rank.
+// Ring buckets are written coalesced: the warp first ranks its chunk by ring in shared memory, then walks the chunk in
+// ring order so that consecutive lanes write consecutive bucket slots.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf, DevParams prm, int S, int T) {
   const int b = blockIdx.y;
   const int n = buf.n[b];
@@ -410,115 +432,133 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   __shared__ unsigned s_delta[kWarpsPerBlock][kChunk];            // bucket slot of ring-ordered slot t, minus t
   __shared__ unsigned short s_lcnt[kWarpsPerBlock][kRingKeys];    // per-ring count, then exclusive local start
   __shared__ unsigned short s_perm[kWarpsPerBlock][kChunk];       // chunk-local point index in ring order
-  if (chunk * kChunk >= n) return;
+  __shared__ int s_scnt[kSectKeys], s_sbase[kSectKeys];           // sector: points of this CTA, first slot reserved for them
   unsigned* delta = s_delta[warp];
   unsigned short* lcnt = s_lcnt[warp];
   unsigned short* perm = s_perm[warp];
   ScanTab& tab = buf.tab[b];
+  const bool live = chunk * kChunk < n;                           // a warp past the end only takes part in the barriers
   const unsigned* row = buf.hist + ((size_t)b * T + chunk) * kRingKeys;
+  for (int t = threadIdx.x; t < kSectKeys; t += blockDim.x) s_scnt[t] = 0;
   for (int t = lane; t < kRingKeys; t += 32) lcnt[t] = 0;
-  __syncwarp();
+  __syncthreads();
   const unsigned lt = (1u << lane) - 1u;
   unsigned packed[kChunk / 32];                 // (ring + 1) << 16 | rank inside the chunk's ring group
+  unsigned spack[kChunk / 32];                  // (sector + 1) << 16 | rank inside the CTA's sector group
   const unsigned gb = scan_base(b, S), g0 = gb + (unsigned)chunk * kChunk;
-  // four groups of 4 iterations. Inside a group everything with a long latency is issued before anything depends on it:
-  // ring/sector loads, then the point loads (where a sector record has to be written), then the sector cursor atomics
-  // (one per set of equal sectors, slots handed out in lane order); the shared-memory ring ranking runs while the atomics
-  // are in flight, and the sector records are stored last.
-  constexpr int GRP = 4;
+  if (live) {
+    // groups of 4 iterations: the ring / sector loads of a group are issued together before anything depends on them
+    constexpr int GRP = 4;
 #pragma unroll
-  for (int h = 0; h < kChunk / 32 / GRP; h++) {
-    short rr[GRP], ss[GRP];
-    float4 pp[GRP];
-    int sbase[GRP];
-    unsigned speers[GRP];
+    for (int h = 0; h < kChunk / 32 / GRP; h++) {
+      short rr[GRP], ss[GRP];
 #pragma unroll
-    for (int u = 0; u < GRP; u++) {
-      const int li = (h * GRP + u) * 32 + lane;
-      const bool in = chunk * kChunk + li < n;
-      rr[u] = in ? buf.ringid[g0 + li] : (short)-1;
-      ss[u] = in ? buf.sect[g0 + li] : (short)-1;
-    }
+      for (int u = 0; u < GRP; u++) {
+        const int li = (h * GRP + u) * 32 + lane;
+        const bool in = chunk * kChunk + li < n;
+        rr[u] = in ? buf.ringid[g0 + li] : (short)-1;
+        ss[u] = in ? buf.sect[g0 + li] : (short)-1;
+      }
 #pragma unroll
-    for (int u = 0; u < GRP; u++) {
-      const int li = (h * GRP + u) * 32 + lane;
-      pp[u] = ss[u] >= 0 ? __ldg(&buf.in[g0 + li]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < GRP; u++) {
-      const int sec = ss[u];
-      const unsigned peers = __match_any_sync(0xffffffffu, sec);
-      speers[u] = peers;
-      sbase[u] = 0;
-      if (sec >= 0 && lane == __ffs(peers) - 1) sbase[u] = atomicAdd(&tab.sect_cur[sec], __popc(peers));
-    }
-#pragma unroll
-    for (int u = 0; u < GRP; u++) {
-      const int it = h * GRP + u;
-      const int ring = rr[u];
-      const unsigned peers = __match_any_sync(0xffffffffu, ring);
-      unsigned pk = 0;
-      if (ring >= 0) pk = ((unsigned)(ring + 1) << 16) | (lcnt[ring] + __popc(peers & lt));
-      __syncwarp();
-      if (ring >= 0 && lane == __ffs(peers) - 1) lcnt[ring] += (unsigned short)__popc(peers);
-      packed[it] = pk;
-      __syncwarp();
-    }
-#pragma unroll
-    for (int u = 0; u < GRP; u++) {
-      const int i = chunk * kChunk + (h * GRP + u) * 32 + lane;
-      const unsigned peers = speers[u];
-      const int base = __shfl_sync(0xffffffffu, sbase[u], __ffs(peers) - 1);
-      if (ss[u] >= 0)
-        buf.spt[gb + (unsigned)(base + __popc(peers & lt))] = make_float4(star_radius(pp[u].x, pp[u].y), pp[u].z, __int_as_float(i), 0.f);
+      for (int u = 0; u < GRP; u++) {
+        const int it = h * GRP + u;
+        // sector rank (any order will do): one shared atomic for a warp that sits in one sector (column-major scans: 32
+        // rings of one azimuth), else one per lane
+        const int sec = ss[u];
+        const int sec0 = __shfl_sync(0xffffffffu, sec, 0);
+        int srank = 0;
+        if (__all_sync(0xffffffffu, sec == sec0)) {
+          int sb = 0;
+          if (lane == 0 && sec0 >= 0) sb = atomicAdd(&s_scnt[sec0], 32);
+          srank = __shfl_sync(0xffffffffu, sb, 0) + lane;
+        } else if (sec >= 0) srank = atomicAdd(&s_scnt[sec], 1);
+        spack[it] = sec >= 0 ? (((unsigned)(sec + 1) << 16) | (unsigned)srank) : 0u;
+        const int ring = rr[u];
+        const unsigned peers = __match_any_sync(0xffffffffu, ring);
+        unsigned pk = 0;
+        if (ring >= 0) pk = ((unsigned)(ring + 1) << 16) | (lcnt[ring] + __popc(peers & lt));
+        __syncwarp();
+        if (ring >= 0 && lane == __ffs(peers) - 1) lcnt[ring] += (unsigned short)__popc(peers);
+        packed[it] = pk;
+        __syncwarp();
+      }
     }
   }
-  // exclusive scan of the chunk's ring counts -> local starts
-  {
-    unsigned v[kRingKeys / 32], sum = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < kSectKeys; t += blockDim.x) {     // one reservation per sector present in this CTA
+    const int c = s_scnt[t];
+    s_sbase[t] = c > 0 ? atomicAdd(&tab.sect_cur[t], c) : 0;
+  }
+  int total = 0;
+  if (live) {
+    // exclusive scan of the chunk's ring counts -> local starts (runs while the reservations are in flight)
+    {
+      unsigned v[kRingKeys / 32], sum = 0;
 #pragma unroll
-    for (int j = 0; j < kRingKeys / 32; j++) { v[j] = lcnt[lane * (kRingKeys / 32) + j]; sum += v[j]; }
-    unsigned inc = sum;
-    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    unsigned run = inc - sum;
+      for (int j = 0; j < kRingKeys / 32; j++) { v[j] = lcnt[lane * (kRingKeys / 32) + j]; sum += v[j]; }
+      unsigned inc = sum;
+      for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      unsigned run = inc - sum;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kRingKeys / 32; j++) { lcnt[lane * (kRingKeys / 32) + j] = (unsigned short)run; run += v[j]; }
+    }
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < kRingKeys / 32; j++) { lcnt[lane * (kRingKeys / 32) + j] = (unsigned short)run; run += v[j]; }
-  }
-  __syncwarp();
-  int total = 0;
-#pragma unroll
-  for (int it = 0; it < kChunk / 32; it++) {
-    const unsigned pk = packed[it];
-    if (pk) {
-      const int ring = (int)(pk >> 16) - 1;
-      const unsigned lstart = lcnt[ring];
-      const int slot = lstart + (pk & 0xffffu);
-      perm[slot] = (unsigned short)(it * 32 + lane);
-      delta[slot] = __ldg(&row[ring]) - lstart;        // global offset of the chunk's ring group - its local start
+    for (int it = 0; it < kChunk / 32; it++) {
+      const unsigned pk = packed[it];
+      if (pk) {
+        const int ring = (int)(pk >> 16) - 1;
+        const unsigned lstart = lcnt[ring];
+        const int slot = lstart + (pk & 0xffffu);
+        perm[slot] = (unsigned short)(it * 32 + lane);
+        delta[slot] = __ldg(&row[ring]) - lstart;        // global offset of the chunk's ring group - its local start
+      }
+      total += __popc(__ballot_sync(0xffffffffu, pk != 0));
     }
-    total += __popc(__ballot_sync(0xffffffffu, pk != 0));
-  }
-  __syncwarp();
-  // walk the chunk in ring order, four warp-rows at a time so that four point gathers are in flight per lane
-  for (int t0 = 0; t0 < total; t0 += 128) {
-    float4 p[4];
-    int li[4];
-    unsigned dl[4];
+    __syncwarp();
+    // walk the chunk in ring order, four warp-rows at a time so that four point gathers are in flight per lane
+    for (int t0 = 0; t0 < total; t0 += 128) {
+      float4 p[4];
+      int li[4];
+      unsigned dl[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int t = t0 + j * 32 + lane;
-      li[j] = t < total ? perm[t] : 0;
-      dl[j] = t < total ? delta[t] : 0;
+      for (int j = 0; j < 4; j++) {
+        const int t = t0 + j * 32 + lane;
+        li[j] = t < total ? perm[t] : 0;
+        dl[j] = t < total ? delta[t] : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) p[j] = __ldg(&buf.in[g0 + li[j]]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int t = t0 + j * 32 + lane;
+        if (t < total) {
+          const unsigned dst = gb + dl[j] + (unsigned)t;
+          buf.bpt[dst] = make_float4(p[j].x, p[j].y, p[j].z, __int_as_float(chunk * kChunk + li[j]));
+        }
+      }
     }
+  }
+  __syncthreads();                                                // s_sbase is complete
+  if (live) {
+    // sector records (r, z, input index), four coalesced point loads in flight per lane
 #pragma unroll
-    for (int j = 0; j < 4; j++) p[j] = __ldg(&buf.in[g0 + li[j]]);
+    for (int h = 0; h < kChunk / 32 / 4; h++) {
+      float4 p[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int t = t0 + j * 32 + lane;
-      if (t < total) {
-        const unsigned dst = gb + dl[j] + (unsigned)t;
-        buf.bpt[dst] = make_float4(p[j].x, p[j].y, p[j].z, __int_as_float(chunk * kChunk + li[j]));
+      for (int u = 0; u < 4; u++) {
+        const int li = (h * 4 + u) * 32 + lane;
+        p[u] = spack[h * 4 + u] ? __ldg(&buf.in[g0 + li]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const unsigned sp = spack[h * 4 + u];
+        if (sp) {
+          const int sec = (int)(sp >> 16) - 1;
+          const int i = chunk * kChunk + (h * 4 + u) * 32 + lane;
+          buf.spt[gb + (unsigned)(s_sbase[sec] + (int)(sp & 0xffffu))] = make_float4(star_radius(p[u].x, p[u].y), p[u].z, __int_as_float(i), 0.f);
+        }
       }
     }
   }
@@ -543,7 +583,8 @@ template <int EPL, int WARPS, bool LIST = false>
 __device__ __forceinline__ bool bitonic_sector(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid,
                                                unsigned* s_xk, unsigned* s_xe) {
   constexpr int THREADS = WARPS * 32;                // sorts up to THREADS * EPL elements
-  static_assert(!LIST || WARPS == 1, "list input shares the exchange buffers");
+  // LIST with WARPS > 1: the list lives in the exchange buffers; every thread has taken its entries into registers before
+  // the barrier in front of the first cross-warp exchange lets anybody overwrite them
   const int lane = tid & 31;
   unsigned key[EPL], el[EPL];
 #pragma unroll
@@ -736,17 +777,63 @@ __device__ void slow_sort_sector(const DevBuffers& buf, int b, int S, int base, 
   __syncthreads();
 }
 
+// Near-first selection for the eight-warp sort (see k_star_sort_warp): pivot = the 144th smallest of 256 evenly spaced
+// samples (56 %), the (radius bits, slot) pairs below it appended to the shared lists in any order. Returns their number.
+template <int EPL>
+__device__ __forceinline__ int select_near_cta(const float4* __restrict__ src, int n, int tid, unsigned* s_pk, unsigned* s_pe, unsigned* s_misc) {
+  const unsigned mine = fbits(src[(int)(((unsigned)tid * (unsigned)n) >> 8)].x);
+  unsigned key[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; r++) {
+    const int e = r * 256 + tid;
+    key[r] = e < n ? fbits(src[e].x) : 0xffffffffu;
+  }
+  __syncthreads();                                     // the lists are free (previous sector done)
+  s_pk[tid] = mine;
+  if (tid == 0) s_misc[1] = 0u;
+  __syncthreads();
+  int rank = 0;                                        // ranks of the samples are a permutation (ties broken by thread)
+  for (int j = 0; j < 256; j++) { const unsigned o = s_pk[j]; rank += (o < mine) || (o == mine && j < tid); }
+  if (rank == 143) s_misc[0] = mine;
+  __syncthreads();
+  const unsigned pivot = s_misc[0];
+  __syncthreads();                                     // everybody has read the samples: the lists may be overwritten
+  const unsigned lt = (1u << (tid & 31)) - 1u;
+#pragma unroll
+  for (int r = 0; r < EPL; r++) {
+    const bool sel = key[r] < pivot;                   // padding keys are 0xffffffff: never selected
+    const unsigned bs = __ballot_sync(0xffffffffu, sel);
+    unsigned wb = 0;
+    if ((tid & 31) == 0 && bs) wb = atomicAdd(&s_misc[1], (unsigned)__popc(bs));
+    wb = __shfl_sync(0xffffffffu, wb, 0);
+    if (sel) { const unsigned pos = wb + __popc(bs & lt); s_pk[pos] = key[r]; s_pe[pos] = (unsigned)(r * 256 + tid); }
+  }
+  __syncthreads();
+  return (int)s_misc[1];
+}
+
+// eight-warp register network on a whole sector (LIST = false) or on the m listed elements (LIST = true); true = radius tie
+template <bool LIST>
+__device__ __forceinline__ bool sort_sector_cta(const float4* __restrict__ src, float4* __restrict__ dst, int n, int tid, unsigned* s_xk, unsigned* s_xe) {
+  if (n <= 1024) return bitonic_sector<4, 8, LIST>(src, dst, n, tid, s_xk, s_xe);
+  if (n <= 2048) return bitonic_sector<8, 8, LIST>(src, dst, n, tid, s_xk, s_xe);
+  if (n <= 4096) return bitonic_sector<16, 8, LIST>(src, dst, n, tid, s_xk, s_xe);
+  return bitonic_sector<32, 8, LIST>(src, dst, n, tid, s_xk, s_xe);
+}
+
 // k_star_sort_big: the sectors k_star_sort_warp handed over. tab.biglist (1025 .. kCtaCap points): eight-warp register
-// network, redone at once by the exact fallback when it meets equal radii; tab.slowlist (larger sectors, and sectors in
-// which the single-warp sort met equal radii): exact fallback. Whole sectors get sorted: sorted_len = size.
+// network, near-first like the single-warp sort (only the points below a sampled pivot radius are sorted, sorted_len tells
+// k_star_scan how far it may walk), redone at once in full by the exact fallback when it meets equal radii; tab.slowlist
+// (larger sectors, and sectors in which the single-warp sort met equal radii): exact fallback, whole sector.
 constexpr size_t kStarCtaSmem = 2 * sizeof(unsigned) * kCtaCap;            // 64 KB: exchange buffers / 8192 64-bit keys
-__global__ void __launch_bounds__(256) k_star_sort_big(DevBuffers buf, int S) {
+__global__ void __launch_bounds__(256) k_star_sort_big(DevBuffers buf, DevParams prm, int S) {
   extern __shared__ unsigned s_dyn[];
   const int b = blockIdx.y;
   ScanTab& tab = buf.tab[b];
   unsigned* s_xk = s_dyn;
   unsigned* s_xe = s_dyn + kCtaCap;
   __shared__ int s_tie;
+  __shared__ unsigned s_misc[2];
   const int nbig = tab.nbig, nslow = tab.nslow;
   for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
     const int s = tab.biglist[w];
@@ -754,16 +841,24 @@ __global__ void __launch_bounds__(256) k_star_sort_big(DevBuffers buf, int S) {
     const float4* src = buf.spt + (size_t)b * S + base;
     float4* dst = buf.ssorted + (size_t)b * S + base;
     if (threadIdx.x == 0) s_tie = 0;
-    bool tie;
-    if (n <= 2048) tie = bitonic_sector<8, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
-    else if (n <= 4096) tie = bitonic_sector<16, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
-    else tie = bitonic_sector<32, 8>(src, dst, n, threadIdx.x, s_xk, s_xe);
+    int m = 0;
+    if (prm.star_prefix) {
+      if (n <= 2048) m = select_near_cta<8>(src, n, threadIdx.x, s_xk, s_xe, s_misc);
+      else if (n <= 4096) m = select_near_cta<16>(src, n, threadIdx.x, s_xk, s_xe, s_misc);
+      else m = select_near_cta<32>(src, n, threadIdx.x, s_xk, s_xe, s_misc);
+    }
+    const bool near = m >= 256 && 4 * m <= 3 * n;                          // uniform: m comes from shared memory
+    const bool tie = near ? sort_sector_cta<true>(src, dst, m, threadIdx.x, s_xk, s_xe) : sort_sector_cta<false>(src, dst, n, threadIdx.x, s_xk, s_xe);
+    if (near && threadIdx.x == 0) tab.sorted_len[s] = m;
     __syncthreads();
     if (tie) s_tie = 1;
     __syncthreads();
     const bool redo = s_tie != 0;
     __syncthreads();
-    if (redo) slow_sort_sector(buf, b, S, base, n, reinterpret_cast<unsigned long long*>(s_dyn), kCtaCap);
+    if (redo) {
+      if (threadIdx.x == 0) tab.sorted_len[s] = n;
+      slow_sort_sector(buf, b, S, base, n, reinterpret_cast<unsigned long long*>(s_dyn), kCtaCap);
+    }
   }
   for (int w = blockIdx.x; w < nslow; w += gridDim.x) {
     const int s = tab.slowlist[w];
@@ -774,23 +869,33 @@ __global__ void __launch_bounds__(256) k_star_sort_big(DevBuffers buf, int S) {
 }
 
 // k_star_refine: second pass for the sectors whose edge search ran off their sorted prefix (tab.refine, filled by
-// k_star_scan): one warp sorts the sector completely (exact fallback on equal radii), then lane 0 resumes the walk at
-// point n0 with the saved running mean / deviation — the first n0 points of the full order are the prefix already walked
-// (all of them are closer than the rest).
-__global__ void __launch_bounds__(32) k_star_refine(DevBuffers buf, DevParams prm, int S) {
-  __shared__ unsigned long long s_keys[kWarpCap];
-  const int b = blockIdx.y, lane = threadIdx.x;
+// k_star_scan): the sector is sorted completely (one warp up to kWarpCap points, eight warps beyond; exact fallback on
+// equal radii), then thread 0 resumes the walk at point n0 with the saved running mean / deviation — the first n0 points
+// of the full order are the prefix already walked (all of them are closer than the rest).
+__global__ void __launch_bounds__(256) k_star_refine(DevBuffers buf, DevParams prm, int S) {
+  extern __shared__ unsigned s_dyn[];
+  const int b = blockIdx.y, tid = threadIdx.x;
   ScanTab& tab = buf.tab[b];
+  unsigned* s_xk = s_dyn;
+  unsigned* s_xe = s_dyn + kCtaCap;
+  __shared__ int s_tie;
   const int nref = tab.nrefine;
   for (int w = blockIdx.x; w < nref; w += gridDim.x) {
     const int s = tab.refine[w];
     const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
     const float4* src = buf.spt + (size_t)b * S + base;
     float4* dst = buf.ssorted + (size_t)b * S + base;
-    const bool tie = sort_sector_warp(src, dst, n, lane);
-    if (__any_sync(0xffffffffu, tie)) slow_sort_sector(buf, b, S, base, n, s_keys, kWarpCap);
-    __syncwarp();
-    if (lane == 0) {
+    if (tid == 0) s_tie = 0;
+    __syncthreads();
+    bool tie = false;
+    if (n <= kWarpCap) { if (tid < 32) tie = sort_sector_warp(src, dst, n, tid); }
+    else if (n <= kCtaCap) tie = sort_sector_cta<false>(src, dst, n, tid, s_xk, s_xe);
+    else tie = true;                                                       // beyond the register networks: exact fallback
+    if (tie) s_tie = 1;
+    __syncthreads();
+    if (s_tie) slow_sort_sector(buf, b, S, base, n, reinterpret_cast<unsigned long long*>(s_dyn), kCtaCap);
+    __syncthreads();
+    if (tid == 0) {
       tab.sorted_len[s] = n;
       StarState st;
       st.avg = tab.resume[w][0]; st.dev = tab.resume[w][1]; st.nan = tab.resume[w][2];
@@ -809,7 +914,7 @@ __global__ void __launch_bounds__(32) k_star_refine(DevBuffers buf, DevParams pr
       }
       if (hit >= 0) curb_hit(buf, prm, b, scan_base(b, S), __float_as_int(dst[hit].z), -1);     // star_shaped_search.cpp:146
     }
-    __syncwarp();
+    __syncthreads();
   }
 }
 
@@ -988,32 +1093,179 @@ __global__ void __launch_bounds__(256, MINB) k_ring_detect(DevBuffers buf, DevPa
   } else if (act) atomicMax(&buf.tab[b].maxs[k], sb);
 }
 
+// k_ring_detect4: the same work for the default curb_points = 5 with FOUR consecutive bucket positions per thread (tile of
+// 1024 positions + halo per CTA). The two height gates of a position only read z: of its own ring, 5 positions to either
+// side (z-zero) and at -2 / +3 (x-zero). Four consecutive positions share a window of 14 heights, which the thread fetches
+// with five 16-byte shared-memory loads instead of 4 x 14 scalar ones; ring lookup, work-list compaction and the maximum of
+// the planar sums are amortised over the four positions as well. Same logic functions, same results as k_ring_detect.
+constexpr int kTile4 = 1024;
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ring_detect4(DevBuffers buf, DevParams prm, int S) {
+  constexpr int CP = 5;
+  const int b = blockIdx.y;
+  const ScanOut& out = buf.out[b];
+  const int p0 = blockIdx.x * kTile4, tid = threadIdx.x;
+  const unsigned gb = scan_base(b, S);
+  const float4* bucket = buf.bpt + gb;
+  // inside the scan's slot whatever n_order is, so the loads need not wait for it
+  float4 rec[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) { const int q = p0 + tid + 256 * j; rec[j] = q < S ? bucket[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
+  const int N = out.n_order;
+  __shared__ __align__(16) float s_x[kTile4 + 2 * kHalo], s_y[kTile4 + 2 * kHalo], s_z[kTile4 + 2 * kHalo];
+  __shared__ int s_rs[kRingKeys + 2];                     // ring_start of the rings this CTA touches, indexed by ring - k_lo
+  __shared__ unsigned short s_itx[kTile4], s_itz[kTile4]; // x-zero / z-zero work items: tile positions that passed the gate
+  __shared__ __align__(4) unsigned char s_hit[kTile4];
+  __shared__ int s_klo, s_nx, s_nz;
+  if (p0 >= N) return;
+  if (tid < 32) {                                         // rings are contiguous in bucket order: first .. last ring of the CTA
+    const int k_lo = ring_of_position(out.ring_start, p0), k_hi = ring_of_position(out.ring_start, min(p0 + kTile4 - 1, N - 1));
+    if (tid == 0) { s_klo = k_lo; s_nx = 0; s_nz = 0; }
+    for (int t = tid; t <= k_hi - k_lo + 1; t += 32) s_rs[t] = out.ring_start[k_lo + t];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int t = tid + 256 * j;
+    const bool in = p0 + t < N;
+    s_x[kHalo + t] = in ? rec[j].x : 0.f; s_y[kHalo + t] = in ? rec[j].y : 0.f; s_z[kHalo + t] = in ? rec[j].z : 0.f;
+    s_hit[t] = 0;
+  }
+  if (tid < 2 * kHalo) {
+    const int ph = tid < kHalo ? p0 - kHalo + tid : p0 + kTile4 + tid - kHalo;
+    const int sh = tid < kHalo ? tid : kTile4 + tid;
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ph >= 0 && ph < N) h = bucket[ph];
+    s_x[sh] = h.x; s_y[sh] = h.y; s_z[sh] = h.z;
+  }
+  __syncthreads();
+  // the thread's four consecutive positions t0 .. t0 + 3 of the tile; heights of tile slots t0 - 8 .. t0 + 11
+  const int t0 = 4 * tid;
+  float zw[20];
+#pragma unroll
+  for (int v = 0; v < 5; v++) {
+    const float4 f = *reinterpret_cast<const float4*>(&s_z[kHalo + t0 - 8 + 4 * v]);
+    zw[4 * v] = f.x; zw[4 * v + 1] = f.y; zw[4 * v + 2] = f.z; zw[4 * v + 3] = f.w;
+  }
+  const float4 fx = *reinterpret_cast<const float4*>(&s_x[kHalo + t0]), fy = *reinterpret_cast<const float4*>(&s_y[kHalo + t0]);
+  const float xs[4] = {fx.x, fx.y, fx.z, fx.w}, ys[4] = {fy.x, fy.y, fy.z, fy.w};
+  int r = 0;                                              // ring (relative to s_klo) of the current position
+  unsigned nx_mask = 0, nz_mask = 0;
+  unsigned long long smax = 0ull;                         // largest planar sum among the thread's positions of ring rmax
+  int rmax = -1;
+  const int kbase = s_klo;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int p = p0 + t0 + j;
+    if (p >= N) break;
+    while (p >= s_rs[r + 1]) r++;                         // p < N = the last staged entry at the latest
+    const int base = s_rs[r], n = s_rs[r + 1] - base, m = p - base;
+    const float z = zw[8 + j];
+    // z-zero gate, zzero_pre_t<5> on the register window (z_zero_method.cpp:38-40,47-49,67-69)
+    if (prm.z_zero && m >= CP && m <= (n - 1) - CP) {
+      const float az0 = fabsf(z);
+      float max1 = az0, max2 = az0;
+#pragma unroll
+      for (int u = 1; u <= CP; u++) { const float v = fabsf(zw[8 + j - u]); if (v > max1) max1 = v; }
+#pragma unroll
+      for (int u = 1; u <= CP; u++) { const float v = fabsf(zw[8 + j + u]); if (v > max2) max2 = v; }
+      if ((__fsub_rn(max1, az0) >= prm.curbHeight || __fsub_rn(max2, az0) >= prm.curbHeight) && (double)fabsf(__fsub_rn(max1, max2)) >= 0.05)
+        nz_mask |= 1u << j;
+    }
+    // x-zero gate, xzero_pre with this point as p2 = j + cp / 2 (x_zero_method.cpp:62-64)
+    const int jx = m - CP / 2;
+    if (prm.x_zero && jx >= CP && jx <= (n - 1) - CP) {
+      const float za = zw[8 + j - CP / 2], zc = zw[8 + j - CP / 2 + CP];
+      if ((fabsf(__fsub_rn(za, z)) >= prm.curbHeight || fabsf(__fsub_rn(zc, z)) >= prm.curbHeight) && (double)fabsf(__fsub_rn(za, zc)) >= 0.05)
+        nx_mask |= 1u << j;
+    }
+    // maxDistance: the thread keeps the maximum for the ring of its last position; an earlier ring's goes out at once
+    const unsigned long long sb = planar_sum_bits(xs[j], ys[j]);
+    if (r != rmax) {
+      if (rmax >= 0) atomicMax(&buf.tab[b].maxs[kbase + rmax], smax);
+      rmax = r; smax = sb;
+    } else if (sb > smax) smax = sb;
+  }
+  // compaction of the gate survivors into the two work lists (one shared counter bump per warp and list)
+  {
+    const int cx = __popc(nx_mask), cz = __popc(nz_mask);
+    int px = cx, pz = cz;                                 // inclusive warp scans of the per-thread counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ax = __shfl_up_sync(0xffffffffu, px, o), az = __shfl_up_sync(0xffffffffu, pz, o);
+      if (lane_id() >= o) { px += ax; pz += az; }
+    }
+    int wx = 0, wz = 0;
+    if (lane_id() == 31) { if (px) wx = atomicAdd(&s_nx, px); if (pz) wz = atomicAdd(&s_nz, pz); }
+    wx = __shfl_sync(0xffffffffu, wx, 31); wz = __shfl_sync(0xffffffffu, wz, 31);
+    int ox = wx + px - cx, oz = wz + pz - cz;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (nx_mask & (1u << j)) s_itx[ox++] = (unsigned short)(t0 + j);
+      if (nz_mask & (1u << j)) s_itz[oz++] = (unsigned short)(t0 + j);
+    }
+  }
+  // warp-level maximum of the planar sums when the whole warp ended in one ring, else one atomic per thread
+  {
+    const int r0 = __shfl_sync(0xffffffffu, rmax, 0);
+    if (__all_sync(0xffffffffu, rmax == r0)) {
+      if (r0 >= 0) {
+        const unsigned hi = (unsigned)(smax >> 32), mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? (unsigned)smax : 0u);
+        if (lane_id() == 0) atomicMax(&buf.tab[b].maxs[kbase + r0], ((unsigned long long)mh << 32) | ml);
+      }
+    } else if (rmax >= 0) atomicMax(&buf.tab[b].maxs[kbase + rmax], smax);
+  }
+  __syncthreads();
+  const int nx = s_nx, nz = s_nz;
+  auto ring_base = [&](int t) {                           // ring start of tile position t (a tile spans few rings)
+    const int p = p0 + t;
+    int a = 0;
+    while (p >= s_rs[a + 1]) a++;
+    return s_rs[a];
+  };
+  for (int it = tid; it < nx; it += 256) {                              // x-zero angle tests, x_zero_method.cpp:35-61
+    const int t = s_itx[it];
+    const int base = ring_base(t), off = base - (p0 - kHalo);
+    const RingSoA ring{s_x + off, s_y + off, s_z + off};
+    if (xzero_post(prm, ring, p0 + t - base, buf.newY)) s_hit[t] = 1;
+  }
+  for (int it = tid; it < nz; it += 256) {                              // z-zero angle tests, z_zero_method.cpp:23-66
+    const int t = s_itz[it];
+    const int base = ring_base(t), off = base - (p0 - kHalo);
+    const RingSoA ring{s_x + off, s_y + off, s_z + off};
+    if (zzero_post_t<CP>(prm, ring, p0 + t - base)) s_hit[t] = 1;
+  }
+  __syncthreads();
+  const unsigned hits = *reinterpret_cast<const unsigned*>(&s_hit[t0]);  // x_zero_method.cpp:66, z_zero_method.cpp:71
+  if (hits) {
+    int rr = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int p = p0 + t0 + j;
+      if (p >= N) break;
+      while (p >= s_rs[rr + 1]) rr++;
+      if ((hits >> (8 * j)) & 0xffu) curb_hit(buf, prm, b, gb, __float_as_int(bucket[p].w), kbase + rr);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
-// blindSpots as tables (urf_logic.cuh: CurbView, window_blocked, build_T_row, covered_T): one thread-block CLUSTER of
-// kTabCtas CTAs per scan runs the three dependent phases back to back, separated by cluster barriers instead of kernel
-// boundaries (the hardware co-schedules the CTAs of a cluster, so the barrier cannot deadlock):
-//   phase 1  per ring: prefix counts of non-empty curb bins; maxDistance / arc widths; q1..q4; reach := n_rings
-//   phase 2  one warp per (direction, window start i): lanes test 32 rings at a time whether ring k holds a curb point
-//            inside window i and stop at the first blocked ring — reach[dir][i] (blind_spots.cpp:107-171 / :216-280)
-//   phase 3  one warp per (ring, direction): a row of a threshold table by a warp max/min scan over the 361 window
-//            starts (same result as the sequential build_T_row of urf_logic.cuh)
-constexpr int kTabCtas = 8, kTabThreads = 512;
-__global__ void __cluster_dims__(kTabCtas, 1, 1) __launch_bounds__(kTabThreads) k_tabs(DevBuffers buf, DevParams prm) {
-  cg::cluster_group cluster = cg::this_cluster();
+// blindSpots as tables (urf_logic.cuh: CurbView, window_blocked, build_T_row, covered_T). Three short kernels — a cluster
+// of eight CTAs per scan running the three phases behind cluster barriers was measured at 111 us against 71 us for the
+// three launches (C2 x 128: the 722 window tests of a scan want more than eight CTAs' worth of warps at once).
+// k_tab1: per scan — prefix counts of non-empty curb bins per ring, maxDistance / arc widths, q1..q4, reach := n_rings.
+__global__ void __launch_bounds__(256) k_tab1(DevBuffers buf, DevParams prm) {
   const int b = blockIdx.y;
   const ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
   const int R = out.n_rings;
-  const int lane = lane_id();
-  const int gw = blockIdx.x * (kTabThreads / 32) + (threadIdx.x >> 5);     // warp index inside the cluster
-  constexpr int NW = kTabCtas * (kTabThreads / 32);
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  if (blockIdx.x == 0) for (int t = threadIdx.x; t < 2 * kDegBins; t += blockDim.x) tab.reach[t / kDegBins][t % kDegBins] = R;
+  if (R <= 0) return;
   const size_t nb = (size_t)prm.channels * kDegBins;
   const unsigned* cmin = buf.cmin + (size_t)b * nb;
   unsigned short* ne = buf.ne + (size_t)b * prm.channels * (kDegBins + 1);
-  const CurbView cv{cmin, buf.cmax + (size_t)b * nb, ne};
-  // ---- phase 1
-  if (blockIdx.x == 0) for (int t = threadIdx.x; t < 2 * kDegBins; t += kTabThreads) tab.reach[t / kDegBins][t % kDegBins] = R;
-  for (int k = gw; k < R; k += NW) {                                      // one warp per ring: 12 x 32 bins with a running carry
+  for (int k = blockIdx.x * 8 + warp; k < R; k += gridDim.x * 8) {        // one warp per ring: 12 x 32 bins with a running carry
     unsigned carry = 0;
     for (int c = 0; c < (kDegBins + 31) / 32; c++) {
       const int bin = c * 32 + lane;
@@ -1024,40 +1276,61 @@ __global__ void __cluster_dims__(kTabCtas, 1, 1) __launch_bounds__(kTabThreads) 
     }
     if (lane == 0) ne[(size_t)k * (kDegBins + 1) + kDegBins] = (unsigned short)carry;
   }
-  if (blockIdx.x == kTabCtas - 1 && R > 0) {
-    const float arc = arc_distance(prm, maxdist_from_bits(tab.maxs[0]));   // blind_spots.cpp:65
-    for (int k = threadIdx.x; k < R; k += kTabThreads) {
-      const float md = maxdist_from_bits(tab.maxs[k]);                     // lidar_segmentation.cpp:271-274
-      tab.maxdist[k] = fbits(md);
-      tab.A[k] = ring_width(arc, md);                                      // :142
-    }
-    if (threadIdx.x < 4) tab.q[threadIdx.x] = blind_quarter(prm, cv, R, threadIdx.x);   // :13-57 (reads the curb bins only)
+  if (blockIdx.x != 0) return;
+  const float arc = arc_distance(prm, maxdist_from_bits(tab.maxs[0]));   // blind_spots.cpp:65
+  for (int k = threadIdx.x; k < R; k += blockDim.x) {
+    const float md = maxdist_from_bits(tab.maxs[k]);                     // lidar_segmentation.cpp:271-274
+    tab.maxdist[k] = fbits(md);
+    tab.A[k] = ring_width(arc, md);                                      // :142
   }
-  __threadfence();
-  cluster.sync();
-  // ---- phase 2
-  for (int w = gw; w < 2 * kDegBins && R > 0; w += NW) {
-    const int dir = w / kDegBins, i = w % kDegBins;
-    if (dir == 0 ? i > prm.fwd_last : i < prm.bwd_first) continue;        // outside the loop range: never accepted anyway
-    int reach = R;
-    for (int k0 = 0; k0 < R; k0 += 32) {
-      const int k = k0 + lane;
-      const bool blocked = k < R && window_blocked(prm, cv, tab.A[k], dir, i, k);
-      const unsigned bal = __ballot_sync(0xffffffffu, blocked);
-      if (bal) { reach = k0 + __ffs(bal) - 1; break; }
-    }
-    if (lane == 0) tab.reach[dir][i] = reach;
+  if (threadIdx.x < 4) {
+    CurbView cv{cmin, buf.cmax + (size_t)b * nb, ne};
+    tab.q[threadIdx.x] = blind_quarter(prm, cv, R, threadIdx.x);         // :13-57 (reads the curb bins only)
   }
-  __threadfence();
-  cluster.sync();
-  // ---- phase 3: degree-major tables, entry (j, k) at (j * channels + k) — a warp of k_label reads one or a few
-  // contiguous runs whether the sensor emits column-major (32 rings at one azimuth) or ring-major (one ring, a few degrees)
-  const size_t ch = prm.channels;
+}
+
+// k_reach: one warp per (direction, window start i): lanes test 32 rings at a time whether ring k holds a curb point
+// inside window i and stop at the first blocked ring — reach[dir][i] (blind_spots.cpp:107-171 / :216-280 stop there too).
+__global__ void __launch_bounds__(256) k_reach(DevBuffers buf, DevParams prm) {
+  const int b = blockIdx.y;
+  const ScanOut& out = buf.out[b];
+  ScanTab& tab = buf.tab[b];
+  const int R = out.n_rings;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id();
+  if (w >= 2 * kDegBins || R <= 0) return;
+  const int dir = w / kDegBins, i = w % kDegBins;
+  if (dir == 0 ? i > prm.fwd_last : i < prm.bwd_first) return;          // outside the loop range: never accepted anyway
+  const size_t nb = (size_t)prm.channels * kDegBins;
+  CurbView cv{buf.cmin + (size_t)b * nb, buf.cmax + (size_t)b * nb, buf.ne + (size_t)b * prm.channels * (kDegBins + 1)};
+  int reach = R;
+  for (int k0 = 0; k0 < R; k0 += 32) {
+    const int k = k0 + lane;
+    const bool blocked = k < R && window_blocked(prm, cv, tab.A[k], dir, i, k);
+    const unsigned bal = __ballot_sync(0xffffffffu, blocked);
+    if (bal) { reach = k0 + __ffs(bal) - 1; break; }
+  }
+  if (lane == 0) tab.reach[dir][i] = reach;
+}
+
+// k_tab2: one warp per (ring, direction) builds a row of a threshold table with a warp max/min scan over the 361
+// window starts (same result as the sequential build_T_row of urf_logic.cuh). Degree-major layout in memory: entry (j, k)
+// at (j * channels + k) — a warp of k_label reads one or a few contiguous runs whether the sensor emits column-major (32
+// rings at one azimuth) or ring-major (one ring, a few degrees). A CTA builds the rows of kTab2Rings consecutive rings in
+// shared memory and writes them out transposed, kTab2Rings consecutive floats per degree.
+constexpr int kTab2Rings = 16;
+__global__ void __launch_bounds__(kTab2Rings * 64) k_tab2(DevBuffers buf, DevParams prm) {
+  const int b = blockIdx.y;
+  const ScanOut& out = buf.out[b];
+  const ScanTab& tab = buf.tab[b];
+  __shared__ float s_T[2][kDegBins][kTab2Rings + 1];     // +1: the row writes of a warp (stride kTab2Rings + 1) avoid bank conflicts
+  const int w = threadIdx.x >> 5, lane = lane_id();
+  const int kl = w >> 1, dir = w & 1;
+  const int k0 = blockIdx.x * kTab2Rings, k = k0 + kl;
+  const int R = out.n_rings;
+  if (k0 >= R) return;
   constexpr int NCH = (kDegBins + 31) / 32;
-  for (int w = gw; w < 2 * R; w += NW) {
-    const int k = w >> 1, dir = w & 1;
+  if (k < R) {
     const double A = tab.A[k];
-    const size_t o = (size_t)b * ch * kTStride + k;
     if (dir == 0) {
       int carry = -1;
       for (int c = 0; c < NCH; c++) {
@@ -1065,7 +1338,7 @@ __global__ void __cluster_dims__(kTabCtas, 1, 1) __launch_bounds__(kTabThreads) 
         int m = (j < kDegBins && accepted_fwd(prm, tab.reach[0], tab.q, k, j)) ? j : -1;
         for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, m, d); if (lane >= d) m = max(m, v); }
         m = max(m, carry);
-        if (j < kDegBins) buf.Tf[o + j * ch] = T_fwd_value(prm, k, m, A);
+        if (j < kDegBins) s_T[0][j][kl] = T_fwd_value(prm, k, m, A);
         carry = __shfl_sync(0xffffffffu, m, 31);
       }
     } else {
@@ -1075,28 +1348,38 @@ __global__ void __cluster_dims__(kTabCtas, 1, 1) __launch_bounds__(kTabThreads) 
         int m = (j < kDegBins && accepted_bwd(prm, tab.reach[1], tab.q, k, j)) ? j : 361;
         for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_down_sync(0xffffffffu, m, d); if (lane + d < 32) m = min(m, v); }
         m = min(m, carry);
-        if (j < kDegBins) buf.Tb[o + j * ch] = T_bwd_value(prm, k, m, A);
+        if (j < kDegBins) s_T[1][j][kl] = T_bwd_value(prm, k, m, A);
         carry = __shfl_sync(0xffffffffu, m, 0);
       }
     }
+  }
+  __syncthreads();
+  const size_t ch = prm.channels;
+  const size_t o = (size_t)b * ch * kTStride + k0;
+  const int nk = min(kTab2Rings, R - k0);
+  for (int t = threadIdx.x; t < 2 * kDegBins * kTab2Rings; t += blockDim.x) {
+    const int kk = t % kTab2Rings, j = (t / kTab2Rings) % kDegBins, d = t / (kTab2Rings * kDegBins);
+    if (kk < nk) (d == 0 ? buf.Tf : buf.Tb)[o + (size_t)j * ch + kk] = s_T[d][j][kk];
   }
 }
 
 // k_label: final label per input point, in input order (coalesced): -1 outside the ROI cloud, 2 where a detector marked
 // the point, 1 where a blindSpots window covers it (two threshold look-ups, covered_from), else 0. Also the counts, per
 // degree bin the first non-road point in the reference's scan order (ring, azimuth; equal azimuths in input order), and
-// the compact list of road points for the marker search.
+// the road points for the marker search: every warp owns the 32 list slots at its own position (roadlist[warp * 32 ..],
+// count in roadcnt[warp]) — no running counter, so no atomic with a return value and no barrier in this kernel: a warp's
+// life is two memory round trips (its point's ring / azimuth / mark, then the two threshold entries and the bin's key).
 __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.y;
   ScanOut& out = buf.out[b];
   ScanTab& tab = buf.tab[b];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = buf.n[b];
-  if ((int)(blockIdx.x * blockDim.x) >= n) return;
-  __shared__ int s_road[8], s_curb[8], s_base;
+  if ((i & ~31) >= n) return;                           // whole warp past the end of the scan
   const unsigned gb = scan_base(b, S), g = gb + (unsigned)i;
-  int lab = -2, k = -2, bin = 0;                        // -2: past the end of the scan
+  int lab = -2, k = -2, bin = -1;                       // -2: past the end of the scan
   float a = 0.f, d = 0.f;
+  unsigned long long key = ~0ull, cb = 0ull;            // first-non-road key of this point (~0 = none), current key of its bin
   if (i < n) {
     k = buf.ringid[g];
     lab = k == -2 ? URF_LABEL_OUTSIDE : URF_LABEL_NONE;
@@ -1105,92 +1388,216 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
       d = buf.d2[g];
       const int m = buf.mark[g];
       // everything the decision needs is loaded up front (independent loads, one round trip): the two threshold entries
-      // (degree-major table, see k_tab2) and the bin's current first-non-road key (from L2: L1 would keep serving the
-      // value of the first look, and every later non-road point of the CTA would fire an atomic)
+      // (degree-major table, see k_tab2) and, further down, the bin's current first-non-road key
       const unsigned o = (unsigned)b * (unsigned)prm.channels * kTStride + (unsigned)k;
       const bool valid = a >= 0.0f;
       int j = 0, jc = 0;
       if (valid) T_indices(a, &j, &jc);
       const float tf = buf.Tf[o + (unsigned)j * prm.channels], tb = buf.Tb[o + (unsigned)jc * prm.channels];
-      bin = j;                                          // == deg_bin(a)
-      const unsigned long long cb = __ldcg(&tab.cutbest[bin]);
+      if (valid) cb = __ldcg(&tab.cutbest[j]);          // from L2: L1 would keep serving the value of the first look
       lab = m == 2 ? 2 : (valid && covered_from(a, tf, tb)) ? 1 : 0;   // covered_T of urf_logic.cuh with the loads hoisted
-      if (valid && lab != 1) {                          // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
-        const unsigned long long key = best_key(k, fbits(a), i);
-        if (cb > key) atomicMin(&tab.cutbest[bin], key);
-      }
+      if (valid) bin = j;                               // == deg_bin(a)
+      if (valid && lab != 1) key = best_key(k, fbits(a), i);          // lidar_segmentation.cpp:318: non-road point in bin [i, i+1)
     }
     buf.label[g] = lab;
     if (buf.label8) buf.label8[g] = (signed char)lab;
   }
-  // one list slot per road point: counts per warp, ONE atomic per CTA on the scan's running road count
+  // first non-road point per bin: atomicMin of the keys. A column-major scan puts the 32 rings of one azimuth — one bin —
+  // into a warp, a ring-major one a few neighbouring bins: when all keys of the warp belong to one bin only their minimum
+  // goes out (one atomic per warp instead of one per point).
+  const bool has_key = key != ~0ull;
+  const unsigned hk = __ballot_sync(0xffffffffu, has_key);
+  if (hk) {
+    const int bin0 = __shfl_sync(0xffffffffu, bin, __ffs(hk) - 1);
+    if (__all_sync(0xffffffffu, !has_key || bin == bin0)) {
+      const unsigned hi = (unsigned)(key >> 32), mh = __reduce_min_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? (unsigned)key : 0xffffffffu);
+      const unsigned long long cb0 = __shfl_sync(0xffffffffu, cb, __ffs(hk) - 1);
+      if (lane_id() == 0) {
+        const unsigned long long mk = ((unsigned long long)mh << 32) | ml;
+        if (cb0 > mk) atomicMin(&tab.cutbest[bin0], mk);
+      }
+    } else if (has_key && cb > key) atomicMin(&tab.cutbest[bin], key);
+  }
   const unsigned br = __ballot_sync(0xffffffffu, lab == 1), bc = __ballot_sync(0xffffffffu, lab == 2);
-  const int warp = threadIdx.x >> 5;
-  if (lane_id() == 0) { s_road[warp] = __popc(br); s_curb[warp] = __popc(bc); }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tr = 0, tc = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) { tr += s_road[w]; tc += s_curb[w]; }
-    s_base = tr ? atomicAdd(&out.n_road, tr) : 0;
-    if (tc) atomicAdd(&out.n_curb, tc);
+  if (lane_id() == 0) {
+    buf.roadcnt[(size_t)b * ((S + 31) >> 5) + (unsigned)(i >> 5)] = (unsigned char)__popc(br);
+    if (br) atomicAdd(&out.n_road, __popc(br));         // results unused: fire-and-forget
+    if (bc) atomicAdd(&out.n_curb, __popc(bc));
   }
-  __syncthreads();
-  if (lab == 1) {
-    int slot = s_base + __popc(br & ((1u << lane_id()) - 1u));
-    for (int w = 0; w < warp; w++) slot += s_road[w];
-    buf.roadlist[gb + (unsigned)slot] = make_uint4((unsigned)bin | ((unsigned)k << 16), fbits(a), fbits(d), (unsigned)i);
-  }
+  if (lab == 1)
+    buf.roadlist[gb + (unsigned)(i & ~31) + (unsigned)__popc(br & ((1u << lane_id()) - 1u))] =
+        make_uint4((unsigned)bin | ((unsigned)k << 16), fbits(a), fbits(d), (unsigned)i);
 }
 
-// k_markers: marker candidate vertices, lidar_segmentation.cpp:305-351, over the compact road list — one thread-block
-// CLUSTER of kMarkCtas CTAs per scan, the per-bin aggregates in the shared memory of the cluster's first CTA (distributed
-// shared memory, reached by the other CTAs through cluster.map_shared_rank), the passes separated by cluster barriers:
+// k_markers: marker candidate vertices, lidar_segmentation.cpp:305-351, over the road points k_label listed (32 slots per
+// warp of input points, count in roadcnt) — one thread-block CLUSTER of kMarkCtas CTAs per scan. Every CTA aggregates its
+// share of the list per degree bin in its own shared memory, then merges into the arrays of the cluster's first CTA
+// through distributed shared memory (cluster.map_shared_rank); the passes are separated by cluster barriers:
 //   pass 1  farthest candidate road point per bin (candidates: road points scanned before the bin's first non-road point)
 //   pass 2  first candidate in scan order that reaches that distance (`d > maxDistanceRoad` is strict, :329)
 //   then    the first CTA compacts the per-bin winners in bin order into markerPointsArray (:343-350)
-constexpr int kMarkCtas = 8, kMarkThreads = 512;
+constexpr int kMarkCtas = 8, kMarkThreads = 256;
 __global__ void __cluster_dims__(kMarkCtas, 1, 1) __launch_bounds__(kMarkThreads) k_markers(DevBuffers buf, int S) {
   cg::cluster_group cluster = cg::this_cluster();
   const int b = blockIdx.y;
   ScanOut& out = buf.out[b];
   const ScanTab& tab = buf.tab[b];
-  __shared__ unsigned long long s_cut[kDegBins];       // every CTA's own copy of the first-non-road keys (read only here)
-  __shared__ unsigned s_dmax[kDegBins];                // used in CTA 0 only
-  __shared__ unsigned long long s_best[kDegBins];      // used in CTA 0 only
+  __shared__ unsigned long long s_cut[kDegBins];       // first-non-road keys of the scan (read only here)
+  __shared__ unsigned s_dmax[kDegBins];                // this CTA's share; in CTA 0 also the merged result
+  __shared__ unsigned s_far[kDegBins];                 // copy of the merged result for pass 2
+  __shared__ unsigned long long s_best[kDegBins];      // this CTA's share; in CTA 0 also the merged result
   __shared__ int s_wsum[kMarkThreads / 32];
   unsigned* dmax0 = cluster.map_shared_rank(s_dmax, 0);
   unsigned long long* best0 = cluster.map_shared_rank(s_best, 0);
-  for (int t = threadIdx.x; t < kDegBins; t += kMarkThreads) { s_cut[t] = tab.cutbest[t]; s_dmax[t] = 0u; s_best[t] = ~0ull; }
-  cluster.sync();
-  const int nroad = out.n_road;
-  const uint4* list = buf.roadlist + scan_base(b, S);
-  const int t0 = blockIdx.x * kMarkThreads + threadIdx.x;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < kDegBins; t += kMarkThreads) { s_cut[t] = tab.cutbest[t]; s_dmax[t] = 0u; s_best[t] = ~0ull; }
+  cluster.sync();                                      // every CTA's arrays are initialised before anybody merges into CTA 0's
+  const int n = buf.n[b];
+  const int nseg = (n + 31) >> 5;                      // one list segment per warp of input points
+  const unsigned gb = scan_base(b, S);
+  const unsigned char* cnt = buf.roadcnt + (size_t)b * ((S + 31) >> 5);
+  const uint4* list = buf.roadlist + gb;
   constexpr int STEP = kMarkCtas * kMarkThreads;
-  for (int t = t0; t < nroad; t += STEP) {
-    const uint4 e = list[t];
-    const int bin = e.x & 0xffff, k = e.x >> 16;
-    if (marker_candidate(s_cut[bin], k, e.y, (int)e.w) && dmax0[bin] < e.z) atomicMax(&dmax0[bin], e.z);
-  }
-  cluster.sync();
-  for (int t = t0; t < nroad; t += STEP) {
-    const uint4 e = list[t];
-    const int bin = e.x & 0xffff, k = e.x >> 16;
-    if (e.z != 0u && e.z == dmax0[bin] && marker_candidate(s_cut[bin], k, e.y, (int)e.w)) {
-      const unsigned long long key = best_key(k, e.y, (int)e.w);
-      if (best0[bin] > key) atomicMin(&best0[bin], key);
+  const int t0 = blockIdx.x * kMarkThreads + tid;
+  for (int seg = t0; seg < nseg; seg += STEP) {        // a thread walks the segments it owns, four entries in flight
+    const int c = cnt[seg];
+    for (int r0 = 0; r0 < c; r0 += 4) {
+      uint4 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) e[u] = list[seg * 32 + min(r0 + u, c - 1)];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (r0 + u >= c) break;
+        const int bin = e[u].x & 0xffff, k = e[u].x >> 16;
+        if (marker_candidate(s_cut[bin], k, e[u].y, (int)e[u].w) && s_dmax[bin] < e[u].z) atomicMax(&s_dmax[bin], e[u].z);
+      }
     }
   }
+  __syncthreads();
+  if (blockIdx.x != 0)
+    for (int t = tid; t < kDegBins; t += kMarkThreads) { const unsigned v = s_dmax[t]; if (v) atomicMax(&dmax0[t], v); }
+  cluster.sync();
+  for (int t = tid; t < kDegBins; t += kMarkThreads) s_far[t] = dmax0[t];
+  __syncthreads();
+  for (int seg = t0; seg < nseg; seg += STEP) {
+    const int c = cnt[seg];
+    for (int r0 = 0; r0 < c; r0 += 4) {
+      uint4 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) e[u] = list[seg * 32 + min(r0 + u, c - 1)];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (r0 + u >= c) break;
+        const int bin = e[u].x & 0xffff, k = e[u].x >> 16;
+        if (e[u].z != 0u && e[u].z == s_far[bin] && marker_candidate(s_cut[bin], k, e[u].y, (int)e[u].w)) {
+          const unsigned long long key = best_key(k, e[u].y, (int)e[u].w);
+          if (s_best[bin] > key) atomicMin(&s_best[bin], key);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x != 0)
+    for (int t = tid; t < kDegBins; t += kMarkThreads) { const unsigned long long v = s_best[t]; if (v != ~0ull) atomicMin(&best0[t], v); }
   cluster.sync();                                      // the other CTAs are done with CTA 0's shared memory
   if (blockIdx.x != 0) return;
-  const int i = threadIdx.x;
+  int run = 0;                                         // vertices written so far (bins are compacted in bin order)
+  for (int c0 = 0; c0 < kDegBins; c0 += kMarkThreads) {
+    const int i = c0 + tid;
+    const bool has = i < kDegBins && s_best[i] != ~0ull;
+    const unsigned bal = __ballot_sync(0xffffffffu, has);
+    const int warp = tid >> 5, lane = lane_id();
+    if (lane == 0) s_wsum[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < kMarkThreads / 32; w++) { if (w < warp) off += s_wsum[w]; total += s_wsum[w]; }
+    if (has) {
+      const int slot = run + off + __popc(bal & ((1u << lane) - 1u));
+      const int p = (int)(s_best[i] & 0xffffffull);    // input index of the winner
+      const float4 q = buf.in[(size_t)b * S + p];
+      out.vert[slot][0] = q.x; out.vert[slot][1] = q.y; out.vert[slot][2] = q.z;
+      out.vert[slot][3] = s_cut[i] != ~0ull ? 1.0f : 0.0f;              // redPoints, :320,348
+    }
+    run += total;
+    __syncthreads();
+  }
+  if (tid == 0) out.n_vert = run;
+  for (int i = run + tid; i < URF_MAX_VERTS; i += kMarkThreads) { out.vert[i][0] = 0.f; out.vert[i][1] = 0.f; out.vert[i][2] = 0.f; out.vert[i][3] = 0.f; }   // defined tail
+}
+
+// k_markers1: the same search by ONE CTA of 1024 threads per scan, everything in its own shared memory (no cluster, no
+// distributed shared memory): a warp takes 32 list segments at a time, scans their counts and spreads the entries evenly
+// over its lanes (entry e of the 32 segments belongs to the segment whose exclusive count prefix is the last one <= e), four
+// entries in flight per lane. Selected with option 9; bench.py's tuning sweep compares the two.
+constexpr int kMark1Threads = 1024;
+template <int PASS>
+__device__ __forceinline__ void markers_pass(const uint4* __restrict__ list, const unsigned char* __restrict__ cnt, int nseg,
+                                             const unsigned long long* s_cut, unsigned* s_dmax, unsigned long long* s_best) {
+  const int warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
+  for (int seg0 = warp * 32; seg0 < nseg; seg0 += nwarps * 32) {
+    const int c = seg0 + lane < nseg ? cnt[seg0 + lane] : 0;
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const int excl = inc - c, total = __shfl_sync(0xffffffffu, inc, 31);
+    for (int e0 = 0; e0 < total; e0 += 128) {
+      uint4 ent[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = e0 + u * 32 + lane;
+        int lo = 0;                                      // last segment whose exclusive prefix is <= e (skips empty segments)
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int ex = __shfl_sync(0xffffffffu, excl, lo + step < 32 ? lo + step : 31);
+          if (lo + step < 32 && ex <= e) lo += step;
+        }
+        const int r = e - __shfl_sync(0xffffffffu, excl, lo);
+        ok[u] = e < total;
+        ent[u] = ok[u] ? list[(seg0 + lo) * 32 + r] : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (!ok[u]) continue;
+        const uint4 q = ent[u];
+        const int bin = q.x & 0xffff, k = q.x >> 16;
+        if (PASS == 1) {
+          if (marker_candidate(s_cut[bin], k, q.y, (int)q.w) && s_dmax[bin] < q.z) atomicMax(&s_dmax[bin], q.z);
+        } else if (q.z != 0u && q.z == s_dmax[bin] && marker_candidate(s_cut[bin], k, q.y, (int)q.w)) {
+          const unsigned long long key = best_key(k, q.y, (int)q.w);
+          if (s_best[bin] > key) atomicMin(&s_best[bin], key);
+        }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(kMark1Threads) k_markers1(DevBuffers buf, int S) {
+  const int b = blockIdx.x;
+  ScanOut& out = buf.out[b];
+  const ScanTab& tab = buf.tab[b];
+  __shared__ unsigned long long s_cut[kDegBins], s_best[kDegBins];
+  __shared__ unsigned s_dmax[kDegBins];
+  __shared__ int s_wsum[kMark1Threads / 32];
+  const int tid = threadIdx.x;
+  for (int t = tid; t < kDegBins; t += kMark1Threads) { s_cut[t] = tab.cutbest[t]; s_dmax[t] = 0u; s_best[t] = ~0ull; }
+  __syncthreads();
+  const int n = buf.n[b];
+  const int nseg = (n + 31) >> 5;
+  const unsigned char* cnt = buf.roadcnt + (size_t)b * ((S + 31) >> 5);
+  const uint4* list = buf.roadlist + scan_base(b, S);
+  markers_pass<1>(list, cnt, nseg, s_cut, s_dmax, s_best);
+  __syncthreads();
+  markers_pass<2>(list, cnt, nseg, s_cut, s_dmax, s_best);
+  __syncthreads();
+  const int i = tid;                                   // kMark1Threads >= kDegBins: one bin per thread
   const bool has = i < kDegBins && s_best[i] != ~0ull;
   const unsigned bal = __ballot_sync(0xffffffffu, has);
   const int warp = i >> 5, lane = lane_id();
   if (lane == 0) s_wsum[warp] = __popc(bal);
   __syncthreads();
   int off = 0, total = 0;
-  for (int w = 0; w < kMarkThreads / 32; w++) { if (w < warp) off += s_wsum[w]; total += s_wsum[w]; }
+  for (int w = 0; w < kMark1Threads / 32; w++) { if (w < warp) off += s_wsum[w]; total += s_wsum[w]; }
   if (has) {
     const int slot = off + __popc(bal & ((1u << lane) - 1u));
     const int p = (int)(s_best[i] & 0xffffffull);      // input index of the winner
