@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn the raw `ncu --csv` log of scripts/gpu_pipeline_table.sh into one row per kernel launch of the captured step.
 usage: pipeline_table.py gpurun_out/pipeline_<tag>.csv profiles/<out>.csv [points_per_launch]"""
-import csv, sys, collections
+import csv, os, sys, collections
 src, dst = sys.argv[1], sys.argv[2]
 pts = float(sys.argv[3]) if len(sys.argv) > 3 else 131072 * 128
 lines = open(src).read().splitlines()
@@ -48,4 +48,12 @@ w.writerow({"kernel": "TOTAL", "time_us": round(tot["time_us"], 1), "dram_read_M
             "dram_write_MB": round(tot["dram_write_MB"], 1), "dram_B_per_pt": round((tot["dram_read_MB"] + tot["dram_write_MB"]) * 1e6 / pts, 1),
             "warp_inst": tot["warp_inst"], "warp_inst_per_32pts": round(tot["warp_inst"] / (pts / 32), 1)})
 for r in out: print(f'{r["kernel"]:22s} {r["time_us"]:8.1f}us dram {r["dram_B_per_pt"]:6.1f} B/pt  l2 {r["l2_B_per_pt"]:6.1f} B/pt  inst/warp {r["warp_inst_per_32pts"]:7.1f}  issue {r["issue_pct"]:5.1f}%  occ {r["occupancy_pct"]:5.1f}%  regs {r["regs"]}  long_sb {r["stall_long_sb"]}')
+if len(sys.argv) > 4:            # per-kernel DRAM bytes of this capture -> the file bench.py reads for roofline.traffic
+    import json
+    tj = {}
+    for r in out:
+        name = r["kernel"].replace("void ", "").split("<")[0]
+        tj[name] = tj.get(name, 0.0) + (r["dram_read_MB"] + r["dram_write_MB"]) * 1e6
+    tj["_source"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, {os.path.basename(src)} (scripts/gpu_pipeline_table.sh, batch of {int(pts) // 131072} C2 scans)"
+    json.dump(tj, open(sys.argv[4], "w"), indent=1)
 print("TOTAL", round(tot["time_us"], 1), "us; dram", round((tot["dram_read_MB"] + tot["dram_write_MB"]) * 1e6 / pts, 1), "B/pt; warp inst per 32 pts", round(tot["warp_inst"] / (pts / 32), 1))

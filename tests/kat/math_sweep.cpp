@@ -76,6 +76,10 @@ int main(int argc, char** argv) {
           if (!std::isfinite(f)) continue;
           const double mine = urfm::div_pi((double)f), ref = (double)f / URF_PI_D;
           if (memcmp(&mine, &ref, 8)) { if (bb < 3) fprintf(stderr, "div_pi(%a) = %a, IEEE %a\n", (double)f, mine, ref); bb++; }
+          if (!(u & 0x80000000ull)) {                       // the variant without the sign-of-zero test, on +0 and above
+            const double nn = urfm::div_pi_nonneg((double)f);
+            if (memcmp(&nn, &ref, 8)) { if (bb < 3) fprintf(stderr, "div_pi_nonneg(%a) = %a, IEEE %a\n", (double)f, nn, ref); bb++; }
+          }
           cc++;
         }
         bad += bb; cnt += cc;

@@ -160,7 +160,7 @@ def test_gpu_profile_option_after_graphed_call(port):
         d.set_option(1, 2)
         assert np.array_equal(d.filtered(pts).label, o.label)          # per-kernel events, no graph
         names = [k for k, _ in d.kernel_times(0)]
-        assert "k_ring_detect" in names and "k_label" in names
+        assert any(k.startswith("k_ring_detect") for k in names) and "k_label" in names
         d.set_option(1, 0)
         d.set_option(1, 0)
         assert np.array_equal(d.filtered(pts).label, o.label)          # graph captured again

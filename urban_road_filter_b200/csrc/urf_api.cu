@@ -24,13 +24,13 @@ struct urf_ctx {
   static constexpr int kGroups = 16;               // sub-batches of a device-resident call run on separate streams: scans are
   cudaStream_t s_grp[kGroups] = {};               // independent, so their (short, partly latency-bound) kernels overlap
   cudaEvent_t ev_fork = nullptr, ev_join[kGroups] = {};
-  int groups = 4;
+  int groups = 2;                                 // measured at C2 x 128: 1 stream 1.37 ms, 2 streams 1.31, 4 streams 1.34, 8 streams 1.40
   // device-resident batches as many small sub-batches: `sub` scans per sub-batch (0 = one sub-batch per stream), dealt
   // round-robin to the `groups` streams, the whole fork/join captured once as a CUDA graph (bgraph) and replayed; with
   // `slot_reuse` the sub-batches of a stream share one workspace slot (working set = groups * sub scans, L2-resident)
   int sub = 0;
-  int markers_variant = 0;             // 0: cluster of eight CTAs per scan (k_markers), 1: one CTA per scan (k_markers1) (tuning option 9)
-  int rd_variant = 4;                  // 4 / 45 / 46: k_ring_detect4 (four positions per thread; default curb_points only) at 4 / 5 / 6 CTAs per SM;
+  int markers_variant = 1;             // 0: cluster of eight CTAs per scan (k_markers), 1: one CTA per scan (k_markers1) (tuning option 9)
+  int rd_variant = 46;                 // 4 / 45 / 46: k_ring_detect4 (four positions per thread; default curb_points only) at 4 / 5 / 6 CTAs per SM;
                                        // 8 / 6 / 5: k_ring_detect (one position per thread) (tuning option 8)
   bool slot_reuse = false, batch_graph = false;
   cudaGraphExec_t bexec = nullptr;
@@ -112,7 +112,7 @@ DevBuffers slot_view(const DevBuffers& a, int b0, int w0, int S, int T, int chan
   v.in += o; v.label += o; v.order += o; v.n += b0; v.out += b0;
   if (v.label8) v.label8 += o;
   v.alpha_v += w; v.mark += w; v.ringid += w; v.sect += w; v.bpt += w; v.spt += w; v.ssorted += w;
-  v.az += w; v.d2 += w; v.roadlist += w; v.roadcnt += (size_t)w0 * ((S + 31) >> 5); v.sortbuf += 2 * w;
+  v.az += w; v.d2 += w; v.baz += w; v.roadlist += w; v.roadcnt += (size_t)w0 * ((S + 31) >> 5); v.sortbuf += 2 * w;
   v.Tf += (size_t)w0 * channels * kTStride; v.Tb += (size_t)w0 * channels * kTStride;
   v.lut += (size_t)w0 * (kElevBins + 1); v.firstidx += (size_t)w0 * (kElevBins + 1);
   v.hist += (size_t)w0 * T * kRingKeys;
@@ -124,11 +124,13 @@ DevBuffers slot_view(const DevBuffers& a, int b0, int w0, int S, int T, int chan
 DevBuffers offset_view(const DevBuffers& a, int b0, int S, int T, int channels) { return slot_view(a, b0, b0, S, T, channels); }
 
 constexpr int kMaxKernels = 32;
+constexpr int kMarkSingleMax = 300000;   // scans above this many points take the multi-CTA marker search
 thread_local std::string g_create_err;
 
 int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want_order, bool first = true, bool last = true,
                     cudaStream_t st_override = nullptr) {
-  const DevParams dp = ctx->dp;
+  DevParams dp = ctx->dp;
+  dp.want_order = want_order ? 1 : 0;
   cudaStream_t st = st_override ? st_override : ctx->stream;
   const int T = (S + kChunk - 1) / kChunk;
   if (T > ctx->Tmax) return URF_ERR_CAPACITY;
@@ -160,7 +162,7 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
     K("k_star_sort_big", k_star_sort_big<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, dp, S));
     K("k_star_scan", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S));
     if (dp.star_prefix)            // sectors whose edge search ran off the near-first prefix: full sort, search resumed
-      K("k_star_refine", k_star_refine<<<dim3(std::max(8, std::min(kSectKeys, 4096 / B)), B), 256, kStarCtaSmem, st>>>(buf, dp, S));
+      K("k_star_refine", k_star_refine<<<dim3(std::max(8, std::min(kSectKeys / 8, 8192 / B)), B), 256, kStarCtaSmem, st>>>(buf, dp, S));
   }
   const dim3 gtile((S + kTile4 - 1) / kTile4, B);
   if (ctx->rd_variant == 4 && dp.curbPoints == 5)        // four positions per thread (default curb_points only)
@@ -174,9 +176,14 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   K("k_reach", k_reach<<<dim3((2 * kDegBins + 7) / 8, B), 256, 0, st>>>(buf, dp));
   K("k_tab2", k_tab2<<<dim3((dp.channels + kTab2Rings - 1) / kTab2Rings, B), kTab2Rings * 64, 0, st>>>(buf, dp));
   K("k_label", k_label<<<gpts, 256, 0, st>>>(buf, dp, S));
-  if (ctx->markers_variant == 1) K("k_markers1", k_markers1<<<B, kMark1Threads, 0, st>>>(buf, S));   // one CTA per scan
+  if (ctx->markers_variant == 2 || (ctx->markers_variant == 1 && S > kMarkSingleMax)) {   // large scans: a grid of CTAs per scan, three launches
+    const dim3 gm(std::max(1, std::min(64, S / 16384)), B);
+    K("k_markers_grid1", k_markers_grid<1><<<gm, kMarkGridThreads, 0, st>>>(buf, S));
+    K("k_markers_grid2", k_markers_grid<2><<<gm, kMarkGridThreads, 0, st>>>(buf, S));
+    K("k_verts", k_verts<<<B, 384, 0, st>>>(buf, S));
+  } else if (ctx->markers_variant == 1) K("k_markers1", k_markers1<<<dim3(1, B), kMark1Threads, 0, st>>>(buf, S));   // one CTA per scan
   else K("k_markers", k_markers<<<dim3(kMarkCtas, B), kMarkThreads, 0, st>>>(buf, S));              // cluster of kMarkCtas CTAs per scan
-  if (want_order) K("k_sort_rings", k_sort_rings<<<dim3(dp.channels, B), 256, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S));
+  if (want_order) K("k_sort_rings", k_sort_rings<<<dim3(dp.channels, B), kSortThreads, kRingSmemKeys * sizeof(unsigned long long), st>>>(buf, S));
 #undef K
   if (last) CK(cudaEventRecord(ctx->ev1, st));
   if (ctx->profile) {
@@ -312,6 +319,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   TRY(dalloc(ctx, &b.ssorted, P));
   TRY(dalloc(ctx, &b.az, P));
   TRY(dalloc(ctx, &b.d2, P));
+  TRY(dalloc(ctx, &b.baz, P));
   TRY(dalloc(ctx, &b.roadlist, P));
   TRY(dalloc(ctx, &b.roadcnt, P / 32 + (size_t)max_batch + 1));
   TRY(dalloc(ctx, &b.Tf, (size_t)max_batch * kTStride * URF_MAX_CHANNELS));
@@ -354,6 +362,7 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
   narrow_params(&ctx->params, &ctx->dp, ctx->dp.Kfi, fe && fe[0] == '1', 0);
   const char* sp = std::getenv("URF_STAR_PREFIX");          // near-first star sort, on unless URF_STAR_PREFIX=0 (A/B measurements)
   ctx->dp.star_prefix = !(sp && sp[0] == '0');
+  ctx->dp.star_pivot = 17;
 #undef TRY
 #undef CKF
   *out = ctx;
@@ -426,6 +435,7 @@ int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (option == 7) { ctx->slot_reuse = value != 0; return URF_OK; }
   if (option == 8) { ctx->rd_variant = value; return URF_OK; }
   if (option == 9) { ctx->markers_variant = value; return URF_OK; }
+  if (option == 10) { ctx->dp.star_pivot = value < 3 ? 3 : (value > 28 ? 28 : value); return URF_OK; }
   if (option == 1) {                   // value = number of event slots (0 = off)
     CK(cudaStreamSynchronize(ctx->stream));               // events of the previous setting may still be pending
     if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; ctx->g_B = -1; }
@@ -627,8 +637,24 @@ int process_batch_impl(urf_ctx* ctx, const void* const* data, const int* n, int 
   bufv.label8 = want_l8 ? ctx->label8 : nullptr;
   // Software pipeline over chunks of scans: H2D of chunk c+1 (s_in), kernels of chunk c (stream) and D2H of chunk c-1
   // (s_out) overlap; scans are independent, every chunk owns its slice of every buffer.
-  const int chunk = batch >= 16 ? std::max(4, (batch + 15) / 16) : batch;     // short fill / drain of the pipeline
-  const int nchunks = (batch + chunk - 1) / chunk;
+  // Chunk schedule: chunks of batch / 16 scans in the middle, ramping up from and down to batch / 64 at the two ends — the
+  // call is synchronous, so the first chunk's copy (before any kernel can run) and the last chunk's kernels and result copy
+  // (after the last input has landed) are the part of a call nothing overlaps with.
+  std::vector<int> cb;                                        // chunk c = scans [cb[c], cb[c + 1])
+  cb.push_back(0);
+  if (batch < 16) cb.push_back(batch);
+  else {
+    const int mid = std::max(4, (batch + 15) / 16), small = std::max(1, mid / 4);
+    const int ramp[3] = {small, small, std::max(small, mid / 2)};
+    int head = 0;
+    for (int r = 0; r < 3 && head + ramp[r] < batch; r++) { head += ramp[r]; cb.push_back(head); }
+    int tail = 0;
+    std::vector<int> tails;
+    for (int r = 0; r < 3 && head + tail + ramp[r] < batch; r++) { tail += ramp[r]; tails.push_back(ramp[r]); }
+    for (int b0 = head; b0 < batch - tail; b0 += mid) cb.push_back(std::min(b0 + mid, batch - tail));
+    for (int r = (int)tails.size() - 1; r >= 0; r--) cb.push_back(cb.back() + tails[r]);
+  }
+  const int nchunks = (int)cb.size() - 1;
   while ((int)ctx->ev_in.size() < nchunks) {
     cudaEvent_t a, c;
     CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -637,8 +663,12 @@ int process_batch_impl(urf_ctx* ctx, const void* const* data, const int* n, int 
   }
   int* ring32 = reinterpret_cast<int*>(ctx->buf.sortbuf);     // free once the sorts of a chunk are done (chunk-private slice)
   const bool graphed = nchunks == 1 && batch <= 8 && !want_l8;
-  for (int c = 0; c < nchunks; c++) {
-    const int b0 = c * chunk, nb = std::min(chunk, batch - b0);
+  // host-to-device copies run kAhead chunks ahead of the kernel launches (the copies depend on nothing): the copy engine
+  // never waits for this thread to get through a chunk's launches and result copies, and the first kernels are not held
+  // back behind the enqueueing of the whole call's copies
+  constexpr int kAhead = 3;
+  auto enqueue_h2d = [&](int c) -> int {
+    const int b0 = cb[c], nb = cb[c + 1] - b0;
     CK(cudaMemcpyAsync(ctx->buf.n + b0, ctx->h_n + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->s_in));
     for (int b = b0; b < b0 + nb; b++) {
       if (n[b] <= 0) continue;
@@ -646,6 +676,12 @@ int process_batch_impl(urf_ctx* ctx, const void* const* data, const int* n, int 
       else CK(cudaMemcpyAsync(ctx->rawb + (size_t)b * S * step, data[b], (size_t)step * (size_t)n[b], cudaMemcpyHostToDevice, ctx->s_in));
     }
     CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    return URF_OK;
+  };
+  for (int c = 0; c < std::min(kAhead, nchunks); c++) { const int rc = enqueue_h2d(c); if (rc != URF_OK) return rc; }
+  for (int c = 0; c < nchunks; c++) {
+    const int b0 = cb[c], nb = cb[c + 1] - b0;
+    if (c + kAhead < nchunks) { const int rc = enqueue_h2d(c + kAhead); if (rc != URF_OK) return rc; }
     CK(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
     if (step != 0)
       k_unpack_cloud2_batch<<<dim3((S + 255) / 256, nb), 256, 0, st>>>(ctx->rawb + (size_t)b0 * S * step, ctx->own_in + (size_t)b0 * S, ctx->buf.n + b0, S,

@@ -44,6 +44,7 @@ struct DevParams {
   int force_exact;   // test hook: always use the exact registration path
   int want_order;    // produce emission order (per-ring azimuth sort)
   int star_prefix;   // near-first star sort on (default); 0 = always sort whole sectors (test hook)
+  int star_pivot;    // near-first pivot: rank (0..31) of the pivot among 32 evenly spaced radius samples (default 17: the 18th smallest)
 };
 
 // Small per-scan outputs copied back to the host after every call.
@@ -69,6 +70,8 @@ struct ScanTab {
   float q[4];                      // q1..q4 (blind_spots.cpp:13-57)
   int reach[2][kDegBins];          // rings accepted by window start i, forward / backward (atomicMin over cells)
   unsigned long long cutbest[kDegBins];              // min (ring, azimuth bits, input index) over the bin's non-road points
+  unsigned dmax[kDegBins];         // large scans (k_markers_grid): float bits of the farthest candidate road point
+  unsigned long long best[kDegBins];                 // large scans: (ring, azimuth bits, input index) of the first candidate reaching dmax
   // near-first star sort (k_star_sort_warp): only the points below a sampled pivot radius are sorted at first
   int sorted_len[kSectKeys];       // length of the radius-sorted prefix of the sector in `ssorted` (== size when fully sorted)
   int nrefine, pad_;               // sectors whose edge search ran off the sorted prefix
@@ -90,6 +93,7 @@ struct DevBuffers {
   float4* ssorted;       // [P]   sector buckets sorted by r
   float* az;             // [P]   azimuth per input point (ROI points only)
   float* d2;             // [P]   planar range per input point (ROI points only)
+  float* baz;            // [P]   azimuth per bucket position (written by k_scatter only when the emission order is wanted)
   uint4* roadlist;       // [P]   road points, 32 slots per warp of input points: (bin | ring << 16, azimuth bits, range bits, input index)
   unsigned char* roadcnt; // [B][ceil(S / 32)] road points of each input warp (entries used in its 32 list slots)
   float* Tf;             // [B][channels][kTStride] forward threshold table (urf_logic.cuh build_T_row)

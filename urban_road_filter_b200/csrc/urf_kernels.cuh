@@ -85,7 +85,7 @@ __global__ void k_reset(DevBuffers buf, DevParams prm) {
   }
   for (int i = tid; i <= kRingKeys; i += nth) o.ring_start[i] = 0;
   for (int i = tid; i < kRingKeys; i += nth) { t.maxs[i] = 0ull; t.maxdist[i] = 0u; t.angle[i] = 0.f; t.regidx[i] = 0x7fffffff; t.regorder[i] = 0x7fffffff; }
-  for (int i = tid; i < kDegBins; i += nth) t.cutbest[i] = ~0ull;
+  for (int i = tid; i < kDegBins; i += nth) { t.cutbest[i] = ~0ull; t.dmax[i] = 0u; t.best[i] = ~0ull; }
   for (int i = tid; i < kSectKeys; i += nth) t.sect_cnt[i] = 0;
   if (tid == 0) { t.nbig = 0; t.nslow = 0; t.nrefine = 0; }
   unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1);
@@ -430,11 +430,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int chunk = blockIdx.x * kWarpsPerBlock + warp;
   __shared__ unsigned s_delta[kWarpsPerBlock][kChunk];            // bucket slot of ring-ordered slot t, minus t
-  __shared__ unsigned short s_lcnt[kWarpsPerBlock][kRingKeys];    // per-ring count, then exclusive local start
+  __shared__ unsigned s_lcnt[kWarpsPerBlock][kRingKeys];          // per-ring count, then exclusive local start
   __shared__ unsigned short s_perm[kWarpsPerBlock][kChunk];       // chunk-local point index in ring order
   __shared__ int s_scnt[kSectKeys], s_sbase[kSectKeys];           // sector: points of this CTA, first slot reserved for them
   unsigned* delta = s_delta[warp];
-  unsigned short* lcnt = s_lcnt[warp];
+  unsigned* lcnt = s_lcnt[warp];
   unsigned short* perm = s_perm[warp];
   ScanTab& tab = buf.tab[b];
   const bool live = chunk * kChunk < n;                           // a warp past the end only takes part in the barriers
@@ -473,14 +473,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
           srank = __shfl_sync(0xffffffffu, sb, 0) + lane;
         } else if (sec >= 0) srank = atomicAdd(&s_scnt[sec], 1);
         spack[it] = sec >= 0 ? (((unsigned)(sec + 1) << 16) | (unsigned)srank) : 0u;
+        // stable rank inside the ring: the group's first lane takes the group's slots from the warp's ring counter with a
+        // shared atomic (same-address atomics of one warp apply in program order, so iteration order = input order; nothing
+        // else orders the iterations, the sixteen of them pipeline), lanes add their position inside the group
+        // groups of equal rings in the warp. The two sensor layouts need no MATCH (its latency was the kernel's largest
+        // stall): ring-major input puts ONE ring into a warp, column-major input 32 DIFFERENT rings in ascending or
+        // descending order (all distinct: every lane is its own group); anything else takes __match_any_sync
         const int ring = rr[u];
-        const unsigned peers = __match_any_sync(0xffffffffu, ring);
-        unsigned pk = 0;
-        if (ring >= 0) pk = ((unsigned)(ring + 1) << 16) | (lcnt[ring] + __popc(peers & lt));
-        __syncwarp();
-        if (ring >= 0 && lane == __ffs(peers) - 1) lcnt[ring] += (unsigned short)__popc(peers);
-        packed[it] = pk;
-        __syncwarp();
+        const int rprev = __shfl_up_sync(0xffffffffu, ring, 1), ring0 = __shfl_sync(0xffffffffu, ring, 0);
+        unsigned peers;
+        if (__all_sync(0xffffffffu, ring == ring0)) peers = 0xffffffffu;
+        else if (__all_sync(0xffffffffu, lane == 0 || ring > rprev) || __all_sync(0xffffffffu, lane == 0 || ring < rprev)) peers = 1u << lane;
+        else peers = __match_any_sync(0xffffffffu, ring);
+        const int leader = __ffs(peers) - 1;
+        unsigned rb = 0;
+        if (ring >= 0 && lane == leader) rb = atomicAdd(&lcnt[ring], (unsigned)__popc(peers));
+        rb = __shfl_sync(0xffffffffu, rb, leader);
+        packed[it] = ring >= 0 ? (((unsigned)(ring + 1) << 16) | (rb + __popc(peers & lt))) : 0u;
       }
     }
   }
@@ -501,7 +510,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
       unsigned run = inc - sum;
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < kRingKeys / 32; j++) { lcnt[lane * (kRingKeys / 32) + j] = (unsigned short)run; run += v[j]; }
+      for (int j = 0; j < kRingKeys / 32; j++) { lcnt[lane * (kRingKeys / 32) + j] = run; run += v[j]; }
     }
     __syncwarp();
 #pragma unroll
@@ -536,6 +545,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
         if (t < total) {
           const unsigned dst = gb + dl[j] + (unsigned)t;
           buf.bpt[dst] = make_float4(p[j].x, p[j].y, p[j].z, __int_as_float(chunk * kChunk + li[j]));
+          if (prm.want_order) buf.baz[dst] = buf.az[g0 + li[j]];       // azimuth in bucket order: what k_sort_rings sorts by
         }
       }
     }
@@ -680,7 +690,7 @@ __device__ __forceinline__ bool sort_sector_warp(const float4* __restrict__ src,
 // smallest of 32 evenly spaced samples, and the (radius bits, slot) pairs below the pivot are appended to the shared
 // lists in any order. Returns their number.
 template <int EPL>
-__device__ __forceinline__ int select_near(const float4* __restrict__ src, int n, int lane, unsigned* s_pk, unsigned* s_pe) {
+__device__ __forceinline__ int select_near(const float4* __restrict__ src, int n, int lane, unsigned* s_pk, unsigned* s_pe, int pivot_rank) {
   const unsigned mine = fbits(src[(int)(((unsigned)lane * (unsigned)n) >> 5)].x);
   unsigned key[EPL];
 #pragma unroll
@@ -691,7 +701,7 @@ __device__ __forceinline__ int select_near(const float4* __restrict__ src, int n
   int rank = 0;                                        // ranks of the samples are a permutation (ties broken by lane)
 #pragma unroll
   for (int j = 0; j < 32; j++) { const unsigned o = __shfl_sync(0xffffffffu, mine, j); rank += (o < mine) || (o == mine && j < lane); }
-  const unsigned pivot = __shfl_sync(0xffffffffu, mine, __ffs(__ballot_sync(0xffffffffu, rank == 17)) - 1);
+  const unsigned pivot = __shfl_sync(0xffffffffu, mine, __ffs(__ballot_sync(0xffffffffu, rank == pivot_rank)) - 1);
   const unsigned lt = (1u << lane) - 1u;
   int m = 0;
 #pragma unroll
@@ -736,9 +746,9 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, DevParams
   bool tie;
   int m = 0;
   if (prm.star_prefix && n > kPrefixMin) {
-    if (n <= 256) m = select_near<8>(src, n, lane, s_pk, s_pe);
-    else if (n <= 512) m = select_near<16>(src, n, lane, s_pk, s_pe);
-    else m = select_near<32>(src, n, lane, s_pk, s_pe);
+    if (n <= 256) m = select_near<8>(src, n, lane, s_pk, s_pe, prm.star_pivot);
+    else if (n <= 512) m = select_near<16>(src, n, lane, s_pk, s_pe, prm.star_pivot);
+    else m = select_near<32>(src, n, lane, s_pk, s_pe, prm.star_pivot);
   }
   if (m >= 32 && 4 * m <= 3 * n) {                                      // worth it: sort the near part only
     if (m <= 128) tie = bitonic_sector<4, 1, true>(src, dst, m, lane, s_pk, s_pe);
@@ -780,7 +790,7 @@ __device__ void slow_sort_sector(const DevBuffers& buf, int b, int S, int base, 
 // Near-first selection for the eight-warp sort (see k_star_sort_warp): pivot = the 144th smallest of 256 evenly spaced
 // samples (56 %), the (radius bits, slot) pairs below it appended to the shared lists in any order. Returns their number.
 template <int EPL>
-__device__ __forceinline__ int select_near_cta(const float4* __restrict__ src, int n, int tid, unsigned* s_pk, unsigned* s_pe, unsigned* s_misc) {
+__device__ __forceinline__ int select_near_cta(const float4* __restrict__ src, int n, int tid, unsigned* s_pk, unsigned* s_pe, unsigned* s_misc, int pivot_rank) {
   const unsigned mine = fbits(src[(int)(((unsigned)tid * (unsigned)n) >> 8)].x);
   unsigned key[EPL];
 #pragma unroll
@@ -794,7 +804,7 @@ __device__ __forceinline__ int select_near_cta(const float4* __restrict__ src, i
   __syncthreads();
   int rank = 0;                                        // ranks of the samples are a permutation (ties broken by thread)
   for (int j = 0; j < 256; j++) { const unsigned o = s_pk[j]; rank += (o < mine) || (o == mine && j < tid); }
-  if (rank == 143) s_misc[0] = mine;
+  if (rank == pivot_rank) s_misc[0] = mine;
   __syncthreads();
   const unsigned pivot = s_misc[0];
   __syncthreads();                                     // everybody has read the samples: the lists may be overwritten
@@ -843,9 +853,9 @@ __global__ void __launch_bounds__(256) k_star_sort_big(DevBuffers buf, DevParams
     if (threadIdx.x == 0) s_tie = 0;
     int m = 0;
     if (prm.star_prefix) {
-      if (n <= 2048) m = select_near_cta<8>(src, n, threadIdx.x, s_xk, s_xe, s_misc);
-      else if (n <= 4096) m = select_near_cta<16>(src, n, threadIdx.x, s_xk, s_xe, s_misc);
-      else m = select_near_cta<32>(src, n, threadIdx.x, s_xk, s_xe, s_misc);
+      if (n <= 2048) m = select_near_cta<8>(src, n, threadIdx.x, s_xk, s_xe, s_misc, 8 * prm.star_pivot + 7);
+      else if (n <= 4096) m = select_near_cta<16>(src, n, threadIdx.x, s_xk, s_xe, s_misc, 8 * prm.star_pivot + 7);
+      else m = select_near_cta<32>(src, n, threadIdx.x, s_xk, s_xe, s_misc, 8 * prm.star_pivot + 7);
     }
     const bool near = m >= 256 && 4 * m <= 3 * n;                          // uniform: m comes from shared memory
     const bool tie = near ? sort_sector_cta<true>(src, dst, m, threadIdx.x, s_xk, s_xe) : sort_sector_cta<false>(src, dst, n, threadIdx.x, s_xk, s_xe);
@@ -868,52 +878,99 @@ __global__ void __launch_bounds__(256) k_star_sort_big(DevBuffers buf, DevParams
   }
 }
 
+// the exact fallback sort (see slow_sort_sector) by ONE warp, for a sector of up to kWarpCap points: keys in the warp's own
+// shared memory, warp barriers only
+__device__ void slow_sort_sector_warp(const DevBuffers& buf, int b, int S, int base, int n, unsigned long long* keys, int lane) {
+  const float4* src = buf.spt + (size_t)b * S + base;
+  float4* dst = buf.ssorted + (size_t)b * S + base;
+  const int npad = next_pow2(n < 2 ? 2 : n);
+  for (int t = lane; t < npad; t += 32)
+    keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
+  __syncwarp();
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (npad >> 1); t += 32) {
+        const int i = 2 * t - (t & (j - 1)), l = i + j;
+        const bool up = (i & k) == 0;
+        const unsigned long long x = keys[i], y = keys[l];
+        if ((x > y) == up) { keys[i] = y; keys[l] = x; }
+      }
+      __syncwarp();
+    }
+  }
+  bool tie = false;
+  for (int t = lane; t < n; t += 32) {
+    const unsigned long long k = keys[t];
+    if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
+    const int idx = (int)(unsigned)k;
+    dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
+  }
+  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
+  __syncwarp();
+}
+
+// resumed walk of a refined sector (entry w of tab.refine) over its completely sorted points, by one thread
+__device__ void star_resume_walk(const DevBuffers& buf, const DevParams& prm, ScanTab& tab, int b, int S, int w, int s, const float4* dst, int n) {
+  tab.sorted_len[s] = n;
+  StarState st;
+  st.avg = tab.resume[w][0]; st.dev = tab.resume[w][1]; st.nan = tab.resume[w][2];
+  int i = __float_as_int(tab.resume[w][3]);            // >= 32: a prefix is never shorter
+  const float4 last = dst[i - 1];
+  st.bx = last.x; st.by = last.y;
+  int hit = -1;
+  while (i < n && hit < 0) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) p[u] = dst[min(i + u, n - 1)];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (hit < 0 && i + u < n && star_step(prm, st, i + u, p[u].x, p[u].y)) hit = i + u;
+    i += 4;
+  }
+  if (hit >= 0) curb_hit(buf, prm, b, scan_base(b, S), __float_as_int(dst[hit].z), -1);     // star_shaped_search.cpp:146
+}
+
 // k_star_refine: second pass for the sectors whose edge search ran off their sorted prefix (tab.refine, filled by
-// k_star_scan): the sector is sorted completely (one warp up to kWarpCap points, eight warps beyond; exact fallback on
-// equal radii), then thread 0 resumes the walk at point n0 with the saved running mean / deviation — the first n0 points
-// of the full order are the prefix already walked (all of them are closer than the rest).
+// k_star_scan): the sector is sorted completely, then one thread resumes the walk at point n0 with the saved running
+// mean / deviation — the first n0 points of the full order are the prefix already walked (all of them are closer than the
+// rest). Sectors of up to kWarpCap points: one WARP per sector (register network, exact fallback on equal radii in the
+// warp's shared memory), the eight warps of a CTA working on eight sectors; larger sectors: the whole CTA, one at a time.
 __global__ void __launch_bounds__(256) k_star_refine(DevBuffers buf, DevParams prm, int S) {
   extern __shared__ unsigned s_dyn[];
-  const int b = blockIdx.y, tid = threadIdx.x;
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   ScanTab& tab = buf.tab[b];
-  unsigned* s_xk = s_dyn;
-  unsigned* s_xe = s_dyn + kCtaCap;
   __shared__ int s_tie;
   const int nref = tab.nrefine;
+  unsigned long long* wkeys = reinterpret_cast<unsigned long long*>(s_dyn) + (size_t)warp * kWarpCap;   // 8 x 8 KB
+  for (int w = blockIdx.x * 8 + warp; w < nref; w += gridDim.x * 8) {
+    const int s = tab.refine[w];
+    const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+    if (n > kWarpCap) continue;                                            // second loop
+    const float4* src = buf.spt + (size_t)b * S + base;
+    float4* dst = buf.ssorted + (size_t)b * S + base;
+    const bool tie = sort_sector_warp(src, dst, n, lane);
+    if (__any_sync(0xffffffffu, tie)) slow_sort_sector_warp(buf, b, S, base, n, wkeys, lane);
+    __syncwarp();
+    if (lane == 0) star_resume_walk(buf, prm, tab, b, S, w, s, dst, n);
+    __syncwarp();
+  }
+  __syncthreads();
+  unsigned* s_xk = s_dyn;
+  unsigned* s_xe = s_dyn + kCtaCap;
   for (int w = blockIdx.x; w < nref; w += gridDim.x) {
     const int s = tab.refine[w];
     const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
+    if (n <= kWarpCap) continue;                                           // done above
     const float4* src = buf.spt + (size_t)b * S + base;
     float4* dst = buf.ssorted + (size_t)b * S + base;
     if (tid == 0) s_tie = 0;
     __syncthreads();
-    bool tie = false;
-    if (n <= kWarpCap) { if (tid < 32) tie = sort_sector_warp(src, dst, n, tid); }
-    else if (n <= kCtaCap) tie = sort_sector_cta<false>(src, dst, n, tid, s_xk, s_xe);
-    else tie = true;                                                       // beyond the register networks: exact fallback
+    bool tie = n <= kCtaCap ? sort_sector_cta<false>(src, dst, n, tid, s_xk, s_xe) : true;   // beyond the register networks: exact fallback
     if (tie) s_tie = 1;
     __syncthreads();
     if (s_tie) slow_sort_sector(buf, b, S, base, n, reinterpret_cast<unsigned long long*>(s_dyn), kCtaCap);
     __syncthreads();
-    if (tid == 0) {
-      tab.sorted_len[s] = n;
-      StarState st;
-      st.avg = tab.resume[w][0]; st.dev = tab.resume[w][1]; st.nan = tab.resume[w][2];
-      int i = __float_as_int(tab.resume[w][3]);            // >= 32: a prefix is never shorter
-      const float4 last = dst[i - 1];
-      st.bx = last.x; st.by = last.y;
-      int hit = -1;
-      while (i < n && hit < 0) {
-        float4 p[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) p[u] = dst[min(i + u, n - 1)];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (hit < 0 && i + u < n && star_step(prm, st, i + u, p[u].x, p[u].y)) hit = i + u;
-        i += 4;
-      }
-      if (hit >= 0) curb_hit(buf, prm, b, scan_base(b, S), __float_as_int(dst[hit].z), -1);     // star_shaped_search.cpp:146
-    }
+    if (tid == 0) star_resume_walk(buf, prm, tab, b, S, w, s, dst, n);
     __syncthreads();
   }
 }
@@ -1534,9 +1591,15 @@ constexpr int kMark1Threads = 1024;
 template <int PASS>
 __device__ __forceinline__ void markers_pass(const uint4* __restrict__ list, const unsigned char* __restrict__ cnt, int nseg,
                                              const unsigned long long* s_cut, unsigned* s_dmax, unsigned long long* s_best) {
-  const int warp = threadIdx.x >> 5, lane = lane_id(), nwarps = blockDim.x >> 5;
-  for (int seg0 = warp * 32; seg0 < nseg; seg0 += nwarps * 32) {
-    const int c = seg0 + lane < nseg ? cnt[seg0 + lane] : 0;
+  const int lane = lane_id(), nwarps = (blockDim.x >> 5) * gridDim.x;       // warps of all CTAs that share this scan
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int cpre[4];                                          // counts of the warp's next four sweeps, loaded together
+  for (int seg0 = warp * 32, sw = 0; seg0 < nseg; seg0 += nwarps * 32, sw++) {
+    if ((sw & 3) == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int sg = seg0 + u * nwarps * 32 + lane; cpre[u] = sg < nseg ? cnt[sg] : 0; }
+    }
+    const int c = (sw & 3) == 0 ? cpre[0] : (sw & 3) == 1 ? cpre[1] : (sw & 3) == 2 ? cpre[2] : cpre[3];
     int inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
@@ -1573,7 +1636,7 @@ __device__ __forceinline__ void markers_pass(const uint4* __restrict__ list, con
   }
 }
 __global__ void __launch_bounds__(kMark1Threads) k_markers1(DevBuffers buf, int S) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;                            // grid (1, B)
   ScanOut& out = buf.out[b];
   const ScanTab& tab = buf.tab[b];
   __shared__ unsigned long long s_cut[kDegBins], s_best[kDegBins];
@@ -1609,6 +1672,58 @@ __global__ void __launch_bounds__(kMark1Threads) k_markers1(DevBuffers buf, int 
   if (i >= total && i < URF_MAX_VERTS) { out.vert[i][0] = 0.f; out.vert[i][1] = 0.f; out.vert[i][2] = 0.f; out.vert[i][3] = 0.f; }   // defined tail
 }
 
+// The same search for LARGE scans (hundreds of thousands of road points want more than one CTA): a grid of CTAs per scan,
+// every CTA aggregates its share per degree bin in shared memory and merges into the scan's global arrays with atomics;
+// pass 1, pass 2 and the vertex compaction are three launches.
+constexpr int kMarkGridThreads = 256;
+template <int PASS>
+__global__ void __launch_bounds__(kMarkGridThreads) k_markers_grid(DevBuffers buf, int S) {
+  const int b = blockIdx.y;
+  ScanTab& tab = buf.tab[b];
+  __shared__ unsigned long long s_cut[kDegBins], s_best[kDegBins];
+  __shared__ unsigned s_dmax[kDegBins];
+  const int tid = threadIdx.x;
+  for (int t = tid; t < kDegBins; t += kMarkGridThreads) {
+    s_cut[t] = tab.cutbest[t]; s_best[t] = ~0ull;
+    s_dmax[t] = PASS == 1 ? 0u : tab.dmax[t];          // pass 2 compares with the merged maxima of pass 1
+  }
+  __syncthreads();
+  const int n = buf.n[b];
+  const int nseg = (n + 31) >> 5;
+  const unsigned char* cnt = buf.roadcnt + (size_t)b * ((S + 31) >> 5);
+  const uint4* list = buf.roadlist + scan_base(b, S);
+  markers_pass<PASS>(list, cnt, nseg, s_cut, s_dmax, s_best);
+  __syncthreads();
+  for (int t = tid; t < kDegBins; t += kMarkGridThreads) {
+    if (PASS == 1) { const unsigned v = s_dmax[t]; if (v) atomicMax(&tab.dmax[t], v); }
+    else { const unsigned long long v = s_best[t]; if (v != ~0ull) atomicMin(&tab.best[t], v); }
+  }
+}
+// k_verts: compact the per-bin winners (tab.best) in bin order into markerPointsArray (lidar_segmentation.cpp:343-350)
+__global__ void __launch_bounds__(384) k_verts(DevBuffers buf, int S) {
+  const int b = blockIdx.x;
+  ScanOut& out = buf.out[b];
+  const ScanTab& tab = buf.tab[b];
+  __shared__ int s_wsum[12];
+  const int i = threadIdx.x;
+  const bool has = i < kDegBins && tab.best[i] != ~0ull;
+  const unsigned bal = __ballot_sync(0xffffffffu, has);
+  const int warp = i >> 5, lane = lane_id();
+  if (lane == 0) s_wsum[warp] = __popc(bal);
+  __syncthreads();
+  int off = 0, total = 0;
+  for (int w = 0; w < 12; w++) { if (w < warp) off += s_wsum[w]; total += s_wsum[w]; }
+  if (has) {
+    const int slot = off + __popc(bal & ((1u << lane) - 1u));
+    const int p = (int)(tab.best[i] & 0xffffffull);    // input index of the winner
+    const float4 q = buf.in[(size_t)b * S + p];
+    out.vert[slot][0] = q.x; out.vert[slot][1] = q.y; out.vert[slot][2] = q.z;
+    out.vert[slot][3] = tab.cutbest[i] != ~0ull ? 1.0f : 0.0f;          // redPoints, :320,348
+  }
+  if (i == 0) out.n_vert = total;
+  if (i >= total && i < URF_MAX_VERTS) { out.vert[i][0] = 0.f; out.vert[i][1] = 0.f; out.vert[i][2] = 0.f; out.vert[i][3] = 0.f; }   // defined tail
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // k_sort_rings (only when the emission order is requested): per-ring sort by azimuth, lidar_segmentation.cpp:70-93,289-291.
 // Tie policy: (azimuth, input order) — the reference's Lomuto quicksort is unstable; ties raise F_TIE_AZIMUTH.
@@ -1620,7 +1735,8 @@ __global__ void __launch_bounds__(kMark1Threads) k_markers1(DevBuffers buf, int 
 // 64-bit (azimuth bits, position) keys. Both paths produce the same total order.
 constexpr int kRingSmemKeys = 8192;                     // 64 KB of dynamic shared memory
 constexpr int kRingFast = 4096, kRingBins = 4096, kBinCap = 48;
-__global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
+constexpr int kSortThreads = 512;
+__global__ void __launch_bounds__(kSortThreads) k_sort_rings(DevBuffers buf, int S) {
   extern __shared__ unsigned long long s_rkeys[];
   const int b = blockIdx.y, k = blockIdx.x;
   ScanOut& out = buf.out[b];
@@ -1635,16 +1751,27 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
     unsigned* s_cnt = s_idx + kRingFast;                              // [kRingBins] bin counts, then exclusive starts
     unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_cnt + kRingBins);   // [kRingFast] arrival rank inside the bin
     unsigned short* s_slot = s_rank + kRingFast;                      // [kRingFast] ring position by sorted position
-    __shared__ unsigned s_lo, s_hi, s_over, s_wsum[8];
+    __shared__ unsigned s_lo, s_hi, s_over, s_wsum[kSortThreads / 32];
     if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; s_over = 0u; }
-    for (int t = tid; t < kRingBins; t += 256) s_cnt[t] = 0u;
+    for (int t = tid; t < kRingBins; t += kSortThreads) s_cnt[t] = 0u;
     __syncthreads();
     unsigned lo = 0xffffffffu, hi = 0u;
-    for (int t = tid; t < n; t += 256) {
-      const unsigned idx = (unsigned)__float_as_int(buf.bpt[g0 + t].w);
-      const unsigned a = fbits(buf.az[gb + idx]);
-      s_az[t] = a; s_idx[t] = idx;
-      if (a <= 0x7f800000u) { lo = min(lo, a); hi = max(hi, a); }   // azimuths are >= +0: their bits order them; NaN stays out
+    for (int t0 = tid; t0 < n; t0 += 4 * kSortThreads) {             // four coalesced (azimuth, input index) pairs in flight per thread
+      unsigned av[4], iv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = t0 + u * kSortThreads;
+        av[u] = t < n ? fbits(buf.baz[g0 + t]) : 0u;                 // azimuth in bucket order, written by k_scatter
+        iv[u] = t < n ? (unsigned)__float_as_int(buf.bpt[g0 + t].w) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = t0 + u * kSortThreads;
+        if (t < n) {
+          s_az[t] = av[u]; s_idx[t] = iv[u];
+          if (av[u] <= 0x7f800000u) { lo = min(lo, av[u]); hi = max(hi, av[u]); }   // azimuths are >= +0: their bits order them; NaN stays out
+        }
+      }
     }
     lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
     if (lane_id() == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
@@ -1656,10 +1783,10 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
       const int v = __float2int_rz(__fmul_rn(__fsub_rn(bitsf(a), flo), scale));
       return v < 0 ? 0 : (v > kRingBins - 2 ? kRingBins - 2 : v);
     };
-    for (int t = tid; t < n; t += 256) s_rank[t] = (unsigned short)atomicAdd(&s_cnt[bin_of(s_az[t])], 1u);
+    for (int t = tid; t < n; t += kSortThreads) s_rank[t] = (unsigned short)atomicAdd(&s_cnt[bin_of(s_az[t])], 1u);
     __syncthreads();
-    {   // exclusive scan over the bins: 16 consecutive bins per thread, warp scan, eight warp totals
-      constexpr int PER = kRingBins / 256;
+    {   // exclusive scan over the bins: consecutive bins per thread, warp scan, warp totals
+      constexpr int PER = kRingBins / kSortThreads;
       unsigned v[PER], sum = 0, mx = 0;
 #pragma unroll
       for (int j = 0; j < PER; j++) { v[j] = s_cnt[tid * PER + j]; sum += v[j]; mx = max(mx, v[j]); }
@@ -1676,9 +1803,9 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
     }
     __syncthreads();
     if (!s_over) {
-      for (int t = tid; t < n; t += 256) s_slot[s_cnt[bin_of(s_az[t])] + s_rank[t]] = (unsigned short)t;
+      for (int t = tid; t < n; t += kSortThreads) s_slot[s_cnt[bin_of(s_az[t])] + s_rank[t]] = (unsigned short)t;
       __syncthreads();
-      constexpr int PER = kRingBins / 256;
+      constexpr int PER = kRingBins / kSortThreads;
       for (int j = 0; j < PER; j++) {                                  // order the points that share a bin
         const int bin = tid * PER + j;
         const int s0 = (int)s_cnt[bin], s1 = bin + 1 < kRingBins ? (int)s_cnt[bin + 1] : n;
@@ -1697,7 +1824,7 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
       }
       __syncthreads();
       bool tie = false;
-      for (int p = tid; p < n; p += 256) {
+      for (int p = tid; p < n; p += kSortThreads) {
         const unsigned short slot = s_slot[p];
         buf.order[g0 + p] = (int)s_idx[slot];
         if (p > 0 && s_az[s_slot[p - 1]] == s_az[slot]) tie = true;
@@ -1710,7 +1837,7 @@ __global__ void __launch_bounds__(256) k_sort_rings(DevBuffers buf, int S) {
   const int npad = next_pow2(n < 2 ? 2 : n);
   unsigned long long* keys = npad <= kRingSmemKeys ? s_rkeys : buf.sortbuf + 2 * g0;
   for (int t = tid; t < npad; t += blockDim.x)
-    keys[t] = t < n ? (((unsigned long long)fbits(buf.az[gb + (unsigned)__float_as_int(buf.bpt[g0 + t].w)]) << 32) | (unsigned)t) : ~0ull;
+    keys[t] = t < n ? (((unsigned long long)fbits(buf.baz[g0 + t]) << 32) | (unsigned)t) : ~0ull;
   __syncthreads();
   cta_bitonic(keys, npad);
   bool tie = false;

@@ -29,7 +29,8 @@ URF_HD double dsq(float a) { return URF_DMUL((double)a, (double)a); }      // po
 
 // tail of every `acos(..) * 180 / M_PI` of the reference: float multiply, then double divide (urfm::div_pi: the same
 // correctly rounded quotient from two FMAs)
-URF_HD double deg_d(float rad) { return urfm::div_pi((double)URF_FMUL(rad, 180.0f)); }
+// (every caller passes rad >= +0: acosf(.) or asinf(b) with b >= 0)
+URF_HD double deg_d(float rad) { return urfm::div_pi_nonneg((double)URF_FMUL(rad, 180.0f)); }
 
 URF_HD float clamp_unit(float b) {   // lidar_segmentation.cpp:154-157 (NaN passes through)
   if (b < -1.0f) return -1.0f;
@@ -38,9 +39,11 @@ URF_HD float clamp_unit(float b) {   // lidar_segmentation.cpp:154-157 (NaN pass
 }
 
 // ROI crop predicate, lidar_segmentation.cpp:106-113 (+ PCL ConditionalRemoval drops non-finite xyz)
+// The six bounds are finite (validate_params), so a coordinate that passes its two compares is finite itself: NaN fails
+// every compare, an infinity lies outside any finite interval — PCL's non-finite test needs no instructions of its own.
 URF_HD bool roi_keep(const DevParams& prm, float x, float y, float z) {
-  return isfinite(x) && isfinite(y) && isfinite(z) && x >= prm.min_X && x <= prm.max_X && y >= prm.min_Y &&
-         y <= prm.max_Y && z >= prm.min_Z && z <= prm.max_Z && URF_FADD(URF_FADD(x, y), z) != 0.0f;
+  return x >= prm.min_X && x <= prm.max_X && y >= prm.min_Y && y <= prm.max_Y && z >= prm.min_Z && z <= prm.max_Z &&
+         URF_FADD(URF_FADD(x, y), z) != 0.0f;
 }
 
 // elevation angle in degrees, lidar_segmentation.cpp:148-166
@@ -56,13 +59,13 @@ URF_HD void planar_az_from(float x, float y, double sxy, float* d_out, float* az
   const float d = URF_D2F(URF_DSQRT(sxy));
   const float br = clamp_unit(URF_FDIV(fabsf(x), d));
   const double t = deg_d(urfm::asinf_glibc(br));
-  float az;
-  if (x >= 0.f && y <= 0.f) az = URF_D2F(t);
-  else if (x >= 0.f && y > 0.f) az = URF_D2F(URF_DSUB(180.0, t));
-  else if (x < 0.f && y >= 0.f) az = URF_D2F(URF_DADD(180.0, t));
-  else az = URF_D2F(URF_DSUB(360.0, t));
+  // the four quadrant cases t, 180 - t, 180 + t, 360 - t (:257-268) as c + s * t: negating t is exact, and 0 + t is t
+  // itself for t >= +0, so one double addition serves all four (NaN coordinates cannot reach this point)
+  const bool xp = x >= 0.f;
+  const double c = xp ? (y <= 0.f ? 0.0 : 180.0) : (y >= 0.f ? 180.0 : 360.0);
+  const bool neg = xp ? !(y <= 0.f) : !(y >= 0.f);
   *d_out = d;
-  *az_out = az;
+  *az_out = URF_D2F(URF_DADD(c, neg ? -t : t));
 }
 URF_HD void planar_az(float x, float y, float* d_out, float* az_out) { planar_az_from(x, y, URF_DADD(dsq(x), dsq(y)), d_out, az_out); }
 
@@ -114,7 +117,13 @@ URF_HD int star_sector_exact(const DevParams& prm, float x, float y) {
 URF_HD int star_sector_fast(float x, float y) {
   const float ax = fabsf(x), ay = fabsf(y);
   const bool steep = ay > ax;
-  const float t = URF_FDIV(steep ? ax : ay, steep ? ay : ax);                // tan of the angle to the nearer axis, in [0, 1]
+  // tan of the angle to the nearer axis, in [0, 1]. The device may take the 2-ulp fast division here: it moves the angle by
+  // < 3e-7 rad, far inside the 1e-3 degree margin below, and either way a decided sector is the reference's sector
+#if defined(__CUDA_ARCH__)
+  const float t = __fdividef(steep ? ax : ay, steep ? ay : ax);
+#else
+  const float t = URF_FDIV(steep ? ax : ay, steep ? ay : ax);
+#endif
   const float s = URF_FMUL(t, t);
   float p = 0.006811792496591806f;
   p = URF_FFMA(p, s, -0.0336042195558548f);

@@ -67,6 +67,15 @@ namespace urfm {
 // v / M_PI in double, correctly rounded, without the divide: q = RN(v * RN(1/pi)), one Markstein correction step with the
 // exact remainder. Equal to the IEEE quotient for EVERY double that is a finite float (all 2^32 patterns are swept by
 // tests/kat/math_sweep.cpp); the path only ever divides float radians * 180.0f (converted to double) by M_PI.
+// the same for v >= +0 (never -0): what every call site of the path passes — float radians of acosf / asinf of a
+// non-negative argument, or acosf of anything, times 180.0f — so the sign-of-zero test can go (+0 comes out as +0)
+URF_HD double div_pi_nonneg(double v) {
+  const double inv = 0.31830988618379069122;                // RN(1 / M_PI) = 0x1.45f306dc9c883p-2
+  const double q = URF_DMUL(v, inv);
+  const double r = URF_DFMA(-URF_PI_D, q, v);
+  return URF_DFMA(r, inv, q);
+}
+
 URF_HD double div_pi(double v) {
   if (v == 0.0) return v;                                   // keeps the sign of zero
   const double inv = 0.31830988618379069122;                // RN(1 / M_PI) = 0x1.45f306dc9c883p-2
