@@ -98,8 +98,12 @@ typedef struct urf_result {
   int32_t  n_road;               /* label 1 count */
   int32_t  n_curb;               /* label 2 count */
   int32_t  n_vert;               /* `cM`, lidar_segmentation.cpp:300 */
-  int32_t  flags;                /* bit0: exact-fallback ring registration ran; bit1: sector-radius ties present;
-                                    bit2: ring-azimuth ties present (tie policy differs from the reference's unstable sorts) */
+  int32_t  flags;                /* bit0: exact-fallback ring registration ran; bit1: sector-radius ties present among the
+                                    points the star search sorted (the near-first sort leaves the far part of a sector
+                                    unsorted; ties there are neither seen nor relevant); bit2: ring-azimuth ties present
+                                    (bit1 / bit2: tie policy differs from the reference's unstable sorts); bit3: a ROI point
+                                    with x == y == 0 exists (azimuth NaN: it belongs to no window or bin here, while in the
+                                    reference it truncates the window scans of its ring) */
   int32_t  reserved;
   int32_t* label;                /* [n_in] or NULL */
   int32_t* ring;                 /* [n_in] or NULL */

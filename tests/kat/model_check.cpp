@@ -83,6 +83,7 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     const int bin = elev_bin(a);
     if (firstidx[bin] > (unsigned)i) firstidx[bin] = (unsigned)i;
     if (a == 0.0f) flags |= F_ZERO_ALPHA;
+    if (az[i] != az[i]) flags |= F_NAN_AZIMUTH;
   }
   out->n_roi = n_roi;
   if (n_roi < 30) { out->status = URF_TOO_FEW_POINTS; return 0; }

@@ -131,6 +131,20 @@ def test_gpu_zero_elevation_quirk(det, port):
     assert r.flags & 1
 
 
+def test_gpu_nan_azimuth_is_flagged(det, port):
+    """A ROI point with x == y == 0 has azimuth NaN: the documented deviation (it belongs to no blindSpots window or marker
+    bin) is reported in urf_result.flags bit3; a scan without such a point does not carry the bit."""
+    pts = make_scan("C1", 6).copy()
+    prm = make_params(**FULL_ROI)
+    det.set_params(prm)
+    assert not (det.filtered(pts).flags & 8)
+    pts[1234, :3] = (0.0, 0.0, -1.7)
+    r = det.filtered(pts)
+    assert r.flags & 8
+    o = port.run(pts, prm)                                    # the CPU restatement follows the same policy
+    assert np.array_equal(r.label, o.label)
+
+
 def test_gpu_edge_cases(det, port):
     prm = make_params(**FULL_ROI)
     det.set_params(prm)

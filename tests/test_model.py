@@ -68,7 +68,7 @@ def test_model_random_clouds_and_exact_registration(both, seed):
 def test_model_speculation_failure_is_repaired(both):
     """random cloud seed 5 defeats the 'first point per elevation bin' speculation; verification must catch it."""
     m = _check(both, random_cloud(5000, 5), make_params(**FULL_ROI))
-    assert m.flags & 16 and m.flags & 1
+    assert m.flags & 32 and m.flags & 1
 
 
 def test_model_zero_elevation_quirk(both):
@@ -78,4 +78,4 @@ def test_model_zero_elevation_quirk(both):
     pts[5] = (1e-5, 2e-5, -1.5, 1.0)       # |z| / d rounds to exactly 1.0f -> acosf -> 0.0, but r and azimuth stay regular
     pts[900] = (3e-5, -1e-5, -1.7, 1.0)
     m = _check(both, pts, make_params(**FULL_ROI))
-    assert m.flags & 8 and m.flags & 1
+    assert m.flags & 16 and m.flags & 1

@@ -637,22 +637,13 @@ int process_batch_impl(urf_ctx* ctx, const void* const* data, const int* n, int 
   bufv.label8 = want_l8 ? ctx->label8 : nullptr;
   // Software pipeline over chunks of scans: H2D of chunk c+1 (s_in), kernels of chunk c (stream) and D2H of chunk c-1
   // (s_out) overlap; scans are independent, every chunk owns its slice of every buffer.
-  // Chunk schedule: chunks of batch / 16 scans in the middle, ramping up from and down to batch / 64 at the two ends — the
-  // call is synchronous, so the first chunk's copy (before any kernel can run) and the last chunk's kernels and result copy
-  // (after the last input has landed) are the part of a call nothing overlaps with.
+  // Chunks of batch / 16 scans. (Measured and dropped: smaller chunks at both ends of the call — a shorter pipeline fill and
+  // drain on paper, 5 % slower in practice — and copies running only three chunks ahead of the launches.)
   std::vector<int> cb;                                        // chunk c = scans [cb[c], cb[c + 1])
-  cb.push_back(0);
-  if (batch < 16) cb.push_back(batch);
-  else {
-    const int mid = std::max(4, (batch + 15) / 16), small = std::max(1, mid / 4);
-    const int ramp[3] = {small, small, std::max(small, mid / 2)};
-    int head = 0;
-    for (int r = 0; r < 3 && head + ramp[r] < batch; r++) { head += ramp[r]; cb.push_back(head); }
-    int tail = 0;
-    std::vector<int> tails;
-    for (int r = 0; r < 3 && head + tail + ramp[r] < batch; r++) { tail += ramp[r]; tails.push_back(ramp[r]); }
-    for (int b0 = head; b0 < batch - tail; b0 += mid) cb.push_back(std::min(b0 + mid, batch - tail));
-    for (int r = (int)tails.size() - 1; r >= 0; r--) cb.push_back(cb.back() + tails[r]);
+  {
+    const int chunk = batch >= 16 ? std::max(4, (batch + 15) / 16) : batch;
+    for (int b0 = 0; b0 < batch; b0 += chunk) cb.push_back(b0);
+    cb.push_back(batch);
   }
   const int nchunks = (int)cb.size() - 1;
   while ((int)ctx->ev_in.size() < nchunks) {
@@ -663,11 +654,9 @@ int process_batch_impl(urf_ctx* ctx, const void* const* data, const int* n, int 
   }
   int* ring32 = reinterpret_cast<int*>(ctx->buf.sortbuf);     // free once the sorts of a chunk are done (chunk-private slice)
   const bool graphed = nchunks == 1 && batch <= 8 && !want_l8;
-  // host-to-device copies run kAhead chunks ahead of the kernel launches (the copies depend on nothing): the copy engine
-  // never waits for this thread to get through a chunk's launches and result copies, and the first kernels are not held
-  // back behind the enqueueing of the whole call's copies
-  constexpr int kAhead = 3;
-  auto enqueue_h2d = [&](int c) -> int {
+  // every host-to-device copy of the call is queued first (the copies depend on nothing): the copy engine then never waits
+  // for this thread to get through a chunk's kernel launches and result copies
+  for (int c = 0; c < nchunks; c++) {
     const int b0 = cb[c], nb = cb[c + 1] - b0;
     CK(cudaMemcpyAsync(ctx->buf.n + b0, ctx->h_n + b0, sizeof(int) * nb, cudaMemcpyHostToDevice, ctx->s_in));
     for (int b = b0; b < b0 + nb; b++) {
@@ -676,12 +665,9 @@ int process_batch_impl(urf_ctx* ctx, const void* const* data, const int* n, int 
       else CK(cudaMemcpyAsync(ctx->rawb + (size_t)b * S * step, data[b], (size_t)step * (size_t)n[b], cudaMemcpyHostToDevice, ctx->s_in));
     }
     CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
-    return URF_OK;
-  };
-  for (int c = 0; c < std::min(kAhead, nchunks); c++) { const int rc = enqueue_h2d(c); if (rc != URF_OK) return rc; }
+  }
   for (int c = 0; c < nchunks; c++) {
     const int b0 = cb[c], nb = cb[c + 1] - b0;
-    if (c + kAhead < nchunks) { const int rc = enqueue_h2d(c + kAhead); if (rc != URF_OK) return rc; }
     CK(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
     if (step != 0)
       k_unpack_cloud2_batch<<<dim3((S + 255) / 256, nb), 256, 0, st>>>(ctx->rawb + (size_t)b0 * S * step, ctx->own_in + (size_t)b0 * S, ctx->buf.n + b0, S,

@@ -16,14 +16,17 @@ constexpr int kMaxCand = 1024;        // max speculation candidates handled by t
 constexpr int kDegBins = 361;         // integer-degree bins 0..360 (marker search, lidar_segmentation.cpp:305)
 constexpr int kStLevels = 9;          // sparse-table levels over 361 window starts (CPU model cross-check only)
 
-// internal per-scan flag bits (low 3 bits are the public urf_result.flags)
+// per-scan flag bits: the low 4 bits are the public urf_result.flags, the rest is internal
 enum : int {
   F_EXACT_REG = 1,       // exact (sequential-semantics) ring registration was used
-  F_TIE_SECTOR = 2,      // a star sector holds two points with identical planar radius
+  F_TIE_SECTOR = 2,      // a star sector holds two points with identical planar radius AMONG THE POINTS THAT WERE SORTED (the
+                         // near-first sort leaves the far part of a sector unsorted: ties there are neither seen nor relevant)
   F_TIE_AZIMUTH = 4,     // a ring holds two points with identical azimuth (only detected when `order` is produced)
-  F_ZERO_ALPHA = 8,      // an elevation angle of exactly 0 exists (reference's `angle[j]==0` sentinel quirk) -> exact path
-  F_SPEC_VIOLATION = 16, // speculative registration failed verification -> exact path + re-assignment
-  F_PUBLIC_MASK = 7
+  F_NAN_AZIMUTH = 8,     // a ROI point has x == y == 0: its azimuth is NaN (DESIGN.md deviation 3: the reference's window scans
+                         // stop at such a point and its quicksort places it unpredictably; here it belongs to no window or bin)
+  F_ZERO_ALPHA = 16,     // an elevation angle of exactly 0 exists (reference's `angle[j]==0` sentinel quirk) -> exact path
+  F_SPEC_VIOLATION = 32, // speculative registration failed verification -> exact path + re-assignment
+  F_PUBLIC_MASK = 15
 };
 
 // Narrowed parameters (src/main.cpp:5-32 narrows every double to float) plus host-derived loop bounds.

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) k_points(DevBuffers buf, DevParams prm, i
       unsigned* fi = buf.firstidx + (size_t)b * (kElevBins + 1) + elev_bin(a);
       if (*fi > (unsigned)i) atomicMin(fi, (unsigned)i);      // plain (possibly stale) read: a stale value is only larger
       if (a == 0.0f) atomicOr(&buf.out[b].flags, F_ZERO_ALPHA);
+      if (az != az) atomicOr(&buf.out[b].flags, F_NAN_AZIMUTH);   // x == y == 0 inside the ROI
       if (prm.star) sec = star_sector(prm, p.x, p.y, c_beam_d, c_beam_o, c_beam_yx);   // star_shaped_search.cpp:164-173
       buf.az[g] = az;
       buf.d2[g] = d;
