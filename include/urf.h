@@ -254,6 +254,11 @@ int urf_queue_submit(urf_queue* q, const float* xyzi, int n, uint64_t tag, int t
  * ring_start are not produced by the queue. URF_ERR_TIMEOUT when nothing finished within timeout_ms (< 0: wait),
  * URF_ERR_CLOSED once the queue is closed and drained. A scan whose processing failed returns that error code. */
 int urf_queue_next(urf_queue* q, uint64_t* tag, urf_result* out, int timeout_ms);
+/* urf_queue_next without the copy of the labels: *label_view points at the n_in labels inside the queue's staging slot
+ * (NULL for a failed scan); the slot stays reserved until the consumer's next urf_queue_next / _next_view call on this queue
+ * or urf_queue_release_view. out->label is ignored. One consumer thread at a time may hold a view. */
+int urf_queue_next_view(urf_queue* q, uint64_t* tag, urf_result* out, const int32_t** label_view, int timeout_ms);
+void urf_queue_release_view(urf_queue* q);
 int urf_queue_get_stats(urf_queue* q, urf_queue_stats* st);
 /* Stop accepting scans: blocked and later urf_queue_submit calls return URF_ERR_CLOSED; the worker still finishes what
  * is pending and urf_queue_next keeps delivering until the queue is drained, then returns URF_ERR_CLOSED. */
@@ -302,6 +307,7 @@ int urf_mq_set_params(urf_mq* mq, const urf_params* p);
 int urf_mq_submit(urf_mq* mq, const float* xyzi, int n, uint64_t tag, int timeout_ms);
 int urf_mq_submit_ref(urf_mq* mq, const float* xyzi, int n, uint64_t tag, int timeout_ms);
 int urf_mq_next(urf_mq* mq, uint64_t* tag, urf_result* out, int timeout_ms);
+int urf_mq_next_view(urf_mq* mq, uint64_t* tag, urf_result* out, const int32_t** label_view, int timeout_ms);   /* see urf_queue_next_view */
 int urf_mq_get_stats(urf_mq* mq, urf_mq_stats* st);
 void urf_mq_close(urf_mq* mq);
 void urf_mq_destroy(urf_mq* mq);

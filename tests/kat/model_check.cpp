@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../urban_road_filter_b200/csrc/urf_logic.cuh"
+#include "../../urban_road_filter_b200/csrc/urf_stdsort.cuh"
 #include "../../urban_road_filter_b200/csrc/urf_host.hpp"
 
 using namespace urf;
@@ -167,14 +168,22 @@ extern "C" int urf_model_run(const float* xyzi, int n, const urf_params* up, urf
     for (int s = 0; s < kSectKeys; s++) {
       const int base = sect_start[s], m = sect_start[s + 1] - base;
       if (m <= 0) continue;
-      // the GPU's sector partition is unordered; the sort key breaks radius ties by input index (= push_back order)
-      std::vector<std::pair<unsigned long long, int>> keys(m);
-      for (int t = 0; t < m; t++) keys[t] = {((unsigned long long)fbits(spt[base + t].x) << 32) | (unsigned)URF_F2I(spt[base + t].z), t};
+      // the GPU sorts a sector by (radius bits, input index); when that meets equal radii it puts the points back into
+      // input (= push_back) order and runs the restated std::sort (urf_stdsort.cuh) — the reference's own tie order
+      std::vector<urfsort::El> keys(m);
+      for (int t = 0; t < m; t++) keys[t] = ((unsigned long long)fbits(spt[base + t].x) << 32) | (unsigned)URF_F2I(spt[base + t].z);
       std::sort(keys.begin(), keys.end());
+      bool tie = false;
+      for (int t = 1; t < m; t++) if ((unsigned)(keys[t - 1] >> 32) == (unsigned)(keys[t] >> 32)) tie = true;
+      if (tie) {
+        flags |= F_TIE_SECTOR;
+        std::sort(keys.begin(), keys.end(), [](urfsort::El a, urfsort::El b) { return (unsigned)a < (unsigned)b; });   // by input index
+        urfsort::std_sort(keys.data(), m);
+      }
       std::vector<float4> sorted(m);
       for (int t = 0; t < m; t++) {
-        sorted[t] = spt[base + keys[t].second];
-        if (t > 0 && (unsigned)(keys[t - 1].first >> 32) == (unsigned)(keys[t].first >> 32)) flags |= F_TIE_SECTOR;
+        const int idx = (int)(unsigned)keys[t];
+        sorted[t] = make_float4(bitsf((unsigned)(keys[t] >> 32)), xyzi[4 * idx + 2], URF_I2F(idx), 0.f);
       }
       const int hit = star_scan_sector(prm, sorted.data(), m);
       if (hit >= 0) mark[URF_F2I(sorted[hit].z)] = 2;

@@ -313,19 +313,34 @@ def test_gpu_ring_sort_paths(det, port):
     check(det, port, _one_ring_cloud(np.sort(rng.uniform(0.0, 359.9, 2048))[::-1], 5), prm)      # descending: the reference's O(n^2) case
 
 
-def test_gpu_radius_ties_follow_input_order(det):
-    """Exact radius ties inside a sector: the reference's order is whatever its introsort leaves; ours is (radius, input
-    index) — flagged in urf_result.flags bit1 and identical to the CPU model of the same policy."""
-    pts = make_scan("C1", 8).copy()
-    pts[1000:1400, :3] = pts[3000:3400, :3]                        # 400 exact duplicates -> same sector, same radius
+def test_gpu_radius_ties_take_the_reference_order(det, port):
+    """Exact radius ties inside a sector: the reference's order is what libstdc++'s introsort leaves (std::sort by radius
+    alone on the sector's points in push_back order); the tie path reproduces it (urf_stdsort.cuh), so labels — which do
+    depend on that order — equal the oracle's, whose star search calls the real std::sort. Flagged in urf_result.flags bit1."""
+    for seed, dup in ((8, 400), (9, 40), (10, 1500)):
+        pts = make_scan("C1", seed).copy()
+        pts[1000:1000 + dup, :3] = pts[3000:3000 + dup, :3]          # exact duplicates -> same sector, same radius
+        pts[5000:5200, 2] += 0.3                                      # and height steps among them: the tie order decides labels
+        prm = make_params(**FULL_ROI)
+        det.set_params(prm)
+        r = det.filtered(pts)
+        o = port.run(pts, prm)
+        m = _model().run(pts, prm)
+        assert r.flags & 2 and m.flags & 2 and o.flags & 2
+        assert np.array_equal(m.label, o.label), "CPU model of the tie path vs the oracle"
+        assert np.array_equal(r.label, o.label) and np.array_equal(r.ring, o.ring)
+        if not (r.flags & 4):
+            assert np.array_equal(r.order, o.order) and np.array_equal(r.vert, o.vert)
+    # quantised ranges (what a real sensor delivers): a flat ring returns the same range in neighbouring columns
+    pts = make_scan("C2", 12).copy()
+    rng = np.linalg.norm(pts[:, :3], axis=1, keepdims=True)
+    q = np.round(rng * 500.0) / 500.0                                 # 2 mm range quantisation along the beam
+    pts[:, :3] = (pts[:, :3] / np.maximum(rng, 1e-9) * q).astype(np.float32)
     prm = make_params(**FULL_ROI)
     det.set_params(prm)
     r = det.filtered(pts)
-    m = _model().run(pts, prm)
-    assert r.flags & 2 and m.flags & 2
-    assert np.array_equal(r.label, m.label) and np.array_equal(r.ring, m.ring)
-    if not (r.flags & 4):
-        assert np.array_equal(r.order, m.order) and np.array_equal(r.vert, m.vert)
+    o = port.run(pts, prm)
+    assert np.array_equal(r.label, o.label) and (r.flags & 2) == (o.flags & 2)
 
 
 def test_gpu_device_resident_multi_stream_groups(port):

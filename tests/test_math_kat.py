@@ -19,3 +19,13 @@ def test_libm_emulation_sweep():
         assert "mismatches=0" in lines[fn]
     checked, _, undecided = (int(v.split("=")[1]) for v in lines["sector"].split())
     assert undecided < 0.7 * checked          # most of the sample sits next to a boundary on purpose; uniform points: ~0.2 %
+
+
+def test_std_sort_restatement_matches_libstdcxx():
+    """urf_stdsort.cuh (what the star search's tie path runs on the device) against the real std::sort on the reference's
+    record type and comparator: tie-heavy, sorted, reversed, organ-pipe, constant and median-of-three-killer arrays (the
+    latter drive introsort into its heapsort fallback, which the binary reports having covered)."""
+    out = subprocess.run([os.path.join(ROOT, "build", "stdsort_check"), "4000"], capture_output=True, text=True, timeout=900)
+    print(out.stdout, out.stderr[-2000:])
+    assert out.returncode == 0 and "mismatches=0" in out.stdout
+    assert int(out.stdout.split("heapsort_fallbacks=")[1]) > 50

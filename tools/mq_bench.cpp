@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
   if (full_roi) { prm.min_x = prm.min_y = prm.min_z = -200; prm.max_x = prm.max_y = prm.max_z = 200; }
   std::vector<int> devs(D);
   for (int d = 0; d < D; d++) devs[d] = d;
-  for (int mode = 0; mode < 2; mode++) {                          // 0: copying submit, 1: by reference (pinned)
+  for (int mode = 0; mode < 3; mode++) {                          // 0: copying submit, 1: by reference (pinned), 2: 1 + labels viewed in place
     urf_mq* mq = nullptr;
     int rc = urf_mq_create(&mq, devs.data(), D, n, slots, mb, &prm);
     if (rc != URF_OK) { fprintf(stderr, "urf_mq_create: %s (%s)\n", urf_strerror(rc), urf_last_cuda_error(nullptr)); return 1; }
@@ -57,7 +57,8 @@ int main(int argc, char** argv) {
         for (int i = 0; i < count; i++) {
           urf_result res; memset(&res, 0, sizeof(res)); res.label = lab.data();
           uint64_t tag;
-          const int r = urf_mq_next(mq, &tag, &res, -1);
+          const int32_t* view = nullptr;
+          const int r = mode == 2 ? urf_mq_next_view(mq, &tag, &res, &view, -1) : urf_mq_next(mq, &tag, &res, -1);
           if (r != URF_OK) { fprintf(stderr, "next: %s\n", urf_strerror(r)); exit(1); }
           if (timed) road += res.n_road;
         }
@@ -74,7 +75,7 @@ int main(int argc, char** argv) {
     for (int d = 0; d < D; d++) { largest = st.largest_batch[d] > largest ? st.largest_batch[d] : largest; mn = st.submitted[d] < mn ? st.submitted[d] : mn; mx = st.submitted[d] > mx ? st.submitted[d] : mx; }
     printf("{\"mq_bench\": \"%s\", \"devices\": %d, \"producers\": %d, \"points_per_scan\": %d, \"scans\": %d, \"seconds\": %.4f, \"scans_per_sec\": %.1f, "
            "\"mpoints_per_sec\": %.1f, \"h2d_gb_per_sec\": %.2f, \"largest_batch\": %d, \"per_device_min_max\": [%llu, %llu], \"road_points\": %ld}\n",
-           mode ? "by_reference_pinned" : "copying_submit", D, P, n, total, s, total / s, total / s * n / 1e6, total / s * bytes / 1e9, largest, mn, mx,
+           mode == 2 ? "by_reference_pinned_labels_viewed_in_place" : mode ? "by_reference_pinned" : "copying_submit", D, P, n, total, s, total / s, total / s * n / 1e6, total / s * bytes / 1e9, largest, mn, mx,
            road.load());
     fflush(stdout);
     urf_mq_destroy(mq);

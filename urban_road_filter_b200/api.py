@@ -15,7 +15,7 @@ from .ctypes_abi import (UrfMqStats, QUEUE_PROCESS_FN, URF_ERR_CLOSED, URF_ERR_T
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liburf_b200.so")
 
-EXPORTS = ["urf_queue_submit_ref", "urf_queue_create_cloud2", "urf_queue_submit_cloud2", "urf_mq_create", "urf_mq_create_with",
+EXPORTS = ["urf_queue_next_view", "urf_queue_release_view", "urf_mq_next_view", "urf_queue_submit_ref", "urf_queue_create_cloud2", "urf_queue_submit_cloud2", "urf_mq_create", "urf_mq_create_with",
            "urf_mq_set_params", "urf_mq_submit", "urf_mq_submit_ref", "urf_mq_next", "urf_mq_get_stats", "urf_mq_close", "urf_mq_destroy",
            "urf_process_cloud2", "urf_process_cloud2_packed", "urf_pinned_alloc", "urf_pinned_free", "urf_queue_create",
            "urf_queue_create_with", "urf_queue_submit", "urf_queue_next", "urf_queue_get_stats", "urf_queue_close", "urf_queue_destroy",

@@ -14,7 +14,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC"]
 SOURCES = ["urf_api.cu"]
 HOST_SOURCES = ["urf_markers.cpp", "urf_queue.cpp", "urf_mq.cpp"]
-HEADERS = ["urf_kernels.cuh", "urf_logic.cuh", "urf_device.cuh", "urf_math.cuh", "urf_host.hpp"]
+HEADERS = ["urf_kernels.cuh", "urf_logic.cuh", "urf_device.cuh", "urf_math.cuh", "urf_stdsort.cuh", "urf_host.hpp"]
 
 
 def _nvcc() -> str:
@@ -73,6 +73,9 @@ def build_kat() -> None:
     if _stale(tgt, [os.path.join(kat, "model_check.cpp")] + hdrs):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
                         "-o", tgt, os.path.join(kat, "model_check.cpp")], check=True)
+    tgt = os.path.join(bdir, "stdsort_check")
+    if _stale(tgt, [os.path.join(kat, "stdsort_check.cpp")] + hdrs):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-o", tgt, os.path.join(kat, "stdsort_check.cpp")], check=True)
     tgt = os.path.join(bdir, "star_prefix_check")
     if _stale(tgt, [os.path.join(kat, "star_prefix_check.cpp")] + hdrs):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I/usr/local/cuda/include", "-o", tgt,

@@ -18,6 +18,7 @@
 
 #include "urf_device.cuh"
 #include "urf_logic.cuh"
+#include "urf_stdsort.cuh"
 
 namespace urf {
 
@@ -763,9 +764,12 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, DevParams
   if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;   // sets F_TIE_SECTOR there
 }
 
-// Exact fallback sort of one sector on (radius bits, input index) keys by all threads of the CTA (bitonic; shared memory
-// up to `cap` keys, global scratch beyond): sectors larger than kCtaCap and sectors holding equal radii, whose order must
-// follow the input index (the push_back order of star_shaped_search.cpp:173). Raises F_TIE_SECTOR for equal radii.
+// Exact fallback sort of one sector by all threads of the CTA (bitonic; shared memory up to `cap` keys, global scratch
+// beyond): sectors larger than kCtaCap and sectors holding EQUAL radii. Keys are (radius bits, input index). Without equal
+// radii any correct sort gives the reference's order. With them (F_TIE_SECTOR) the reference's order is what libstdc++'s
+// introsort leaves when it sorts the sector's points in push_back (= input) order by radius alone
+// (star_shaped_search.cpp:109): the points are put back into input order (second bitonic pass, keyed by index) and ONE
+// thread runs the restated std::sort (urf_stdsort.cuh) over them.
 __device__ void slow_sort_sector(const DevBuffers& buf, int b, int S, int base, int n, unsigned long long* s_keys, int cap) {
   const float4* src = buf.spt + (size_t)b * S + base;
   float4* dst = buf.ssorted + (size_t)b * S + base;
@@ -776,15 +780,23 @@ __device__ void slow_sort_sector(const DevBuffers& buf, int b, int S, int base, 
     keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
   __syncthreads();
   cta_bitonic(keys, npad);
-  // keys hold (radius bits, input index) ascending: rebuild the records (z comes from the input record of that index)
   bool tie = false;
+  for (int t = threadIdx.x + 1; t < n; t += blockDim.x) if ((unsigned)(keys[t - 1] >> 32) == (unsigned)(keys[t] >> 32)) tie = true;
+  if (__syncthreads_or(tie)) {                           // uniform: reproduce std::sort's order of the equal radii
+    for (int t = threadIdx.x; t < n; t += blockDim.x) { const unsigned long long k = keys[t]; keys[t] = (k << 32) | (k >> 32); }
+    __syncthreads();
+    cta_bitonic(keys, npad);                             // ascending input index = push_back order (padding keys stay last)
+    for (int t = threadIdx.x; t < n; t += blockDim.x) { const unsigned long long k = keys[t]; keys[t] = (k << 32) | (k >> 32); }
+    __syncthreads();
+    if (threadIdx.x == 0) { urfsort::std_sort(keys, n); atomicOr(&buf.out[b].flags, F_TIE_SECTOR); }
+    __syncthreads();
+  }
+  // rebuild the records in key order (z comes from the input record of that index)
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const unsigned long long k = keys[t];
-    if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
     const int idx = (int)(unsigned)k;
     dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
   }
-  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
   __syncthreads();
 }
 
@@ -881,13 +893,7 @@ __global__ void __launch_bounds__(256) k_star_sort_big(DevBuffers buf, DevParams
 
 // the exact fallback sort (see slow_sort_sector) by ONE warp, for a sector of up to kWarpCap points: keys in the warp's own
 // shared memory, warp barriers only
-__device__ void slow_sort_sector_warp(const DevBuffers& buf, int b, int S, int base, int n, unsigned long long* keys, int lane) {
-  const float4* src = buf.spt + (size_t)b * S + base;
-  float4* dst = buf.ssorted + (size_t)b * S + base;
-  const int npad = next_pow2(n < 2 ? 2 : n);
-  for (int t = lane; t < npad; t += 32)
-    keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
-  __syncwarp();
+__device__ __forceinline__ void warp_bitonic(unsigned long long* keys, int npad, int lane) {
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = lane; t < (npad >> 1); t += 32) {
@@ -899,14 +905,31 @@ __device__ void slow_sort_sector_warp(const DevBuffers& buf, int b, int S, int b
       __syncwarp();
     }
   }
+}
+__device__ void slow_sort_sector_warp(const DevBuffers& buf, int b, int S, int base, int n, unsigned long long* keys, int lane) {
+  const float4* src = buf.spt + (size_t)b * S + base;
+  float4* dst = buf.ssorted + (size_t)b * S + base;
+  const int npad = next_pow2(n < 2 ? 2 : n);
+  for (int t = lane; t < npad; t += 32)
+    keys[t] = t < n ? (((unsigned long long)fbits(src[t].x) << 32) | (unsigned)__float_as_int(src[t].z)) : ~0ull;
+  __syncwarp();
+  warp_bitonic(keys, npad, lane);
   bool tie = false;
+  for (int t = lane + 1; t < n; t += 32) if ((unsigned)(keys[t - 1] >> 32) == (unsigned)(keys[t] >> 32)) tie = true;
+  if (__any_sync(0xffffffffu, tie)) {                    // reproduce std::sort's order of the equal radii (see slow_sort_sector)
+    for (int t = lane; t < n; t += 32) { const unsigned long long k = keys[t]; keys[t] = (k << 32) | (k >> 32); }
+    __syncwarp();
+    warp_bitonic(keys, npad, lane);
+    for (int t = lane; t < n; t += 32) { const unsigned long long k = keys[t]; keys[t] = (k << 32) | (k >> 32); }
+    __syncwarp();
+    if (lane == 0) { urfsort::std_sort(keys, n); atomicOr(&buf.out[b].flags, F_TIE_SECTOR); }
+    __syncwarp();
+  }
   for (int t = lane; t < n; t += 32) {
     const unsigned long long k = keys[t];
-    if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(k >> 32)) tie = true;
     const int idx = (int)(unsigned)k;
     dst[t] = make_float4(bitsf((unsigned)(k >> 32)), buf.in[(size_t)b * S + idx].z, __int_as_float(idx), 0.f);
   }
-  if (tie) atomicOr(&buf.out[b].flags, F_TIE_SECTOR);
   __syncwarp();
 }
 

@@ -37,6 +37,7 @@ struct urf_mq {
   int rr = 0;                        // round-robin cursor for ties
   int submitting = 0;                // submit calls between device choice and order append
   bool closed = false;
+  int view_dev = -1;                 // consumer side only: device whose queue has lent out a label view
 };
 
 namespace {
@@ -130,7 +131,16 @@ int urf_mq_set_params(urf_mq* m, const urf_params* p) {
 int urf_mq_submit(urf_mq* m, const float* xyzi, int n, uint64_t tag, int timeout_ms) { return submit_common(m, xyzi, n, tag, timeout_ms, false); }
 int urf_mq_submit_ref(urf_mq* m, const float* xyzi, int n, uint64_t tag, int timeout_ms) { return submit_common(m, xyzi, n, tag, timeout_ms, true); }
 
-int urf_mq_next(urf_mq* m, uint64_t* tag, urf_result* out, int timeout_ms) {
+namespace {
+int mq_next_common(urf_mq* m, uint64_t* tag, urf_result* out, const int32_t** label_view, int timeout_ms);
+}
+int urf_mq_next(urf_mq* m, uint64_t* tag, urf_result* out, int timeout_ms) { return mq_next_common(m, tag, out, nullptr, timeout_ms); }
+int urf_mq_next_view(urf_mq* m, uint64_t* tag, urf_result* out, const int32_t** label_view, int timeout_ms) {
+  if (!label_view) return URF_ERR_INVALID;
+  return mq_next_common(m, tag, out, label_view, timeout_ms);
+}
+namespace {
+int mq_next_common(urf_mq* m, uint64_t* tag, urf_result* out, const int32_t** label_view, int timeout_ms) {
   if (!m || !out) return URF_ERR_INVALID;
   int d;
   {
@@ -141,8 +151,11 @@ int urf_mq_next(urf_mq* m, uint64_t* tag, urf_result* out, int timeout_ms) {
     if (m->order.empty()) return URF_ERR_CLOSED;          // closed and drained
     d = m->order.front();
   }
-  const int rc = urf_queue_next(m->dev[d].q, tag, out, timeout_ms);
+  // a view lent by the previous call belongs to one device's queue: give it back before another device's queue lends one
+  if (m->view_dev >= 0 && (m->view_dev != d || !label_view)) { urf_queue_release_view(m->dev[m->view_dev].q); m->view_dev = -1; }
+  const int rc = label_view ? urf_queue_next_view(m->dev[d].q, tag, out, label_view, timeout_ms) : urf_queue_next(m->dev[d].q, tag, out, timeout_ms);
   if (rc == URF_ERR_TIMEOUT) return rc;                   // still the oldest scan: the entry stays at the front
+  if (label_view) m->view_dev = d;
   {
     std::lock_guard<std::mutex> lk(m->mu);
     m->order.pop_front();
@@ -151,6 +164,7 @@ int urf_mq_next(urf_mq* m, uint64_t* tag, urf_result* out, int timeout_ms) {
   }
   return rc;
 }
+}  // namespace
 
 int urf_mq_get_stats(urf_mq* m, urf_mq_stats* st) {
   if (!m || !st) return URF_ERR_INVALID;

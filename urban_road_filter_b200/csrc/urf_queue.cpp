@@ -20,7 +20,7 @@
 #include "../../include/urf.h"
 
 namespace {
-enum SlotState { FREE = 0, FILLING, PENDING, RUNNING, DONE };
+enum SlotState { FREE = 0, FILLING, PENDING, RUNNING, DONE, VIEWED };   // VIEWED: delivered, its labels lent to the consumer
 struct Slot {
   SlotState state = FREE;
   uint64_t seq = 0, tag = 0;
@@ -45,6 +45,7 @@ struct urf_queue {
   std::mutex mu;
   std::condition_variable cv_free, cv_pending, cv_done;
   uint64_t next_seq = 1;       // sequence number of the next accepted scan
+  int viewed = -1;             // slot lent out by urf_queue_next_view, given back on the consumer's next call
   bool closed = false;
   urf_queue_stats st{};
   std::thread worker;
@@ -228,9 +229,28 @@ int urf_queue_submit_cloud2(urf_queue* q, const void* data, int n_points, uint64
   return submit_common(q, data, n_points, tag, timeout_ms, false);
 }
 
-int urf_queue_next(urf_queue* q, uint64_t* tag, urf_result* out, int timeout_ms) {
+namespace {
+int next_common(urf_queue* q, uint64_t* tag, urf_result* out, const int32_t** label_view, int timeout_ms);
+}
+
+int urf_queue_next(urf_queue* q, uint64_t* tag, urf_result* out, int timeout_ms) { return next_common(q, tag, out, nullptr, timeout_ms); }
+
+int urf_queue_next_view(urf_queue* q, uint64_t* tag, urf_result* out, const int32_t** label_view, int timeout_ms) {
+  if (!label_view) return URF_ERR_INVALID;
+  return next_common(q, tag, out, label_view, timeout_ms);
+}
+
+namespace {
+// label_view != NULL: no copy — *label_view points at the labels inside the queue's staging slot, which stays reserved
+// (not reusable by producers) until this consumer's next urf_queue_next* call on the queue.
+int next_common(urf_queue* q, uint64_t* tag, urf_result* out, const int32_t** label_view, int timeout_ms) {
   if (!q || !out) return URF_ERR_INVALID;
   std::unique_lock<std::mutex> lk(q->mu);
+  if (q->viewed >= 0) {                                   // the slot lent out by the previous view call comes back now
+    q->slots[q->viewed].state = FREE;
+    q->viewed = -1;
+    q->cv_free.notify_one();
+  }
   int slot = -1;
   bool drained = false;
   auto ready = [&] {
@@ -253,13 +273,31 @@ int urf_queue_next(urf_queue* q, uint64_t* tag, urf_result* out, int timeout_ms)
   const int rc = s.rc;
   *out = s.res;
   out->label = user_label; out->ring = nullptr; out->order = nullptr; out->ring_start = nullptr;
-  if (user_label && rc == URF_OK && s.n > 0) std::memcpy(user_label, s.label, sizeof(int32_t) * (size_t)s.n);
   if (tag) *tag = s.tag;
-  s.state = FREE;
   q->st.delivered++;
+  if (label_view) {                                       // lend the slot: DONE slots are invisible to producers and the worker
+    *label_view = rc == URF_OK ? s.label : nullptr;
+    s.state = VIEWED;
+    q->viewed = slot;
+    return rc;
+  }
+  const int n = s.n;
+  const int32_t* src = s.label;
+  s.state = VIEWED;                                       // ours: invisible to producers, the worker and other consumers
+  lk.unlock();                                            // the copy runs outside the lock
+  if (user_label && rc == URF_OK && n > 0) std::memcpy(user_label, src, sizeof(int32_t) * (size_t)n);
+  lk.lock();
+  s.state = FREE;
   lk.unlock();
   q->cv_free.notify_one();
   return rc;
+}
+}  // namespace
+
+void urf_queue_release_view(urf_queue* q) {
+  if (!q) return;
+  std::lock_guard<std::mutex> lk(q->mu);
+  if (q->viewed >= 0) { q->slots[q->viewed].state = FREE; q->viewed = -1; q->cv_free.notify_one(); }
 }
 
 int urf_queue_get_stats(urf_queue* q, urf_queue_stats* st) {
