@@ -1482,6 +1482,7 @@ __global__ void __launch_bounds__(256) k_label(DevBuffers buf, DevParams prm, in
     }
     buf.label[g] = lab;
     if (buf.label8) buf.label8[g] = (signed char)lab;
+    if (prm.want_order && i >= out.n_order) buf.order[g] = -1;   // defined tail of the emission order (k_sort_rings writes [0, n_order))
   }
   // first non-road point per bin: atomicMin of the keys. A column-major scan puts the 32 rings of one azimuth — one bin —
   // into a warp, a ring-major one a few neighbouring bins: when all keys of the warp belong to one bin only their minimum
