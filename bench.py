@@ -48,6 +48,14 @@ def bench_params(shape_key: str):
     return make_params(channels=sh.channels, interval=sh.interval, **_ABLATION, **FULL_ROI)
 
 
+def workload_config(shape_key: str) -> dict:
+    """The `config` block, identical for both arms: it names the workload, nothing that depends on who runs it."""
+    sh = SHAPES[shape_key]
+    n = sh.rings * sh.cols
+    return {"workload": f"{sh.name} {n}-pt scans, {detectors_text()}, full-ROI preset (BASELINE config {shape_key[1:]})",
+            "shape": shape_key, "points_per_scan": n, "rings": sh.rings, "channels": sh.channels, "interval": sh.interval}
+
+
 def detectors_text() -> str:
     on = [name for name, key in (("star", "star_shaped_method"), ("x_zero", "x_zero_method"), ("z_zero", "z_zero_method"))
           if _ABLATION.get(key, 1)]
@@ -238,9 +246,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": f"{SHAPES[args.shape].name} {n}-pt scans, {detectors_text()}, full-ROI preset "
-                               f"({args.shape}); one step = {cores} scans, one per host core",
-                   "points_per_scan": n, "mpoints_per_sec": value * n / 1e6},
+        "config": workload_config(args.shape),
+        "step": f"{cores} scans, one per host core (one single-threaded process each: the reference is single-threaded, src/main.cpp:54)",
+        "mpoints_per_sec": value * n / 1e6,
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": kind,
                          "sample": f"{cores} single-threaded processes x 1 scan per step, median of {args.steps} steps",
                          "single_process": {"value": single_rate, "unit": "scans/s", "ms_per_scan": single_ms, "cores": 1,
@@ -557,11 +565,11 @@ def main():
             "metric": "scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
             "data": "synthetic",
-            "config": {"workload": f"{sh.name} {n}-pt scans, {detectors_text()}, full-ROI preset (BASELINE config {args.shape[1:]}); "
-                                   f"one step = a batch of {B} distinct scans per GPU",
-                       "batch_per_gpu": B, "points_per_scan": n, "mpoints_per_sec": value * n / 1e6,
-                       "l2": f"inputs of one step are {B * n * 16 / 2**20:.0f} MiB per GPU (> 126 MB L2), no reuse between steps",
-                       "parallelism": f"scan-batch sharding x{world}, no data-path collective"},
+            "config": workload_config(args.shape),
+            "step": f"a batch of {B} distinct scans per GPU",
+            "batch_per_gpu": B, "mpoints_per_sec": value * n / 1e6,
+            "l2": f"inputs of one step are {B * n * 16 / 2**20:.0f} MiB per GPU (> 126 MB L2), no reuse between steps",
+            "parallelism": f"scan-batch sharding x{world}, no data-path collective",
             "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": B * n * 16,
                     "d2h_bytes_per_step": B * n * 4 + B * C.sizeof(UrfResult), "mpoints_per_sec": e2e * n / 1e6,
                     "pcie": {"h2d_gbs": B * n * 16 / h2d_ms / 1e6, "d2h_gbs": B * n * 4 / d2h_ms / 1e6,

@@ -1,7 +1,8 @@
 mkdir -p gpurun_out
-echo "== memcheck variants"; timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/san_variants.py > gpurun_out/san_memcheck_variants.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/san_memcheck_variants.log
-echo "== racecheck variants"; timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/san_variants.py > gpurun_out/san_racecheck_variants.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/san_racecheck_variants.log
-echo "== memcheck smoke"; timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/san_memcheck_smoke.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/san_memcheck_smoke.log
-echo "== memcheck C2 packed"; timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/san_c2_packed.py > gpurun_out/san_memcheck_c2_packed.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/san_memcheck_c2_packed.log
-echo "== racecheck C2 packed"; timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/san_c2_packed.py > gpurun_out/san_racecheck_c2_packed.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/san_racecheck_c2_packed.log
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --maxfail=8 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
 echo "== initcheck smoke"; timeout 900 compute-sanitizer --tool initcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/san_initcheck_smoke.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/san_initcheck_smoke.log
+echo "== bench (driver-style)"; timeout 1500 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02_v11k.json 2> gpurun_out/bench_r02_v11k.err; echo "bench rc=$?"; python -c "
+import json; d=json.loads(open('gpurun_out/bench_r02_v11k.json').read().strip().splitlines()[-1])
+print('value', round(d['value']), 'ms', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), 'lean', round(d['e2e_lean']['value']), 'with_order', round(d['with_order']['value']), d['config'], d['roofline']['kernel'], round(d['roofline']['frac'],4))"; tail -2 gpurun_out/bench_r02_v11k.err
+echo "== reference arm (driver-style)"; timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_ref_r02_v11k.json 2> gpurun_out/bench_ref_r02_v11k.err; echo "rc=$?"; python -c "
+import json; d=json.loads(open('gpurun_out/bench_ref_r02_v11k.json').read().strip().splitlines()[-1]); print(d['value'], d['config'], d['ms_per_step'])"

@@ -25,6 +25,7 @@ elif mode == "configs":
     for p in sys.argv[2:]:
         d = last_json(p)
         c = d["config"]; r = d["roofline"]
+        c = {**c, "batch_per_gpu": d.get("batch_per_gpu", c.get("batch_per_gpu")), "mpoints_per_sec": d.get("mpoints_per_sec", c.get("mpoints_per_sec"))}
         print(f"| {c['workload'].split(',')[0]} | {c['points_per_scan']:,} | {c['batch_per_gpu']} | {d['value']:,.0f} | {c['mpoints_per_sec']:,.0f} | {d['ms_per_step']:.3f} | {d['e2e']['value']:,.0f} | {d.get('with_order', {}).get('value', 0):,.0f} | `{r['kernel']}` {r['frac']:.3f} |")
 elif mode == "scale":
     print("| GPUs | scans/s (HBM-resident) | efficiency | e2e scans/s | efficiency | lean e2e | with order |")

@@ -108,6 +108,32 @@ def test_gpu_param_sweep(det, port, kw):
     check(det, port, make_scan("C1", 3), make_params(**kw, **FULL_ROI))
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_gpu_random_parameter_draws(det, port, seed):
+    """Seeded random draws over the LidarFilters.cfg parameter ranges (cfg/LidarFilters.cfg:10-84), alternating sensor
+    layouts, ROI presets and cloud kinds: every stage against the oracle."""
+    rng = np.random.default_rng(500 + seed)
+    kind = seed % 4
+    if kind == 0:
+        pts, ch, iv = make_scan("C1", 30 + seed, order="column"), 64, None
+    elif kind == 1:
+        pts, ch, iv = make_scan("C2", 30 + seed, order="ring"), 64, None
+    elif kind == 2:
+        pts, ch, iv = random_cloud(8000, seed, rings=14), 64, None
+    else:
+        pts, ch, iv = make_scan("C4", 30 + seed, order="column"), 128, 0.07
+    prm = make_params(
+        x_zero_method=int(rng.integers(0, 2)), z_zero_method=int(rng.integers(0, 2)), star_shaped_method=int(rng.integers(0, 2)),
+        blind_spots=int(rng.integers(0, 2)), xDirection=int(rng.integers(0, 3)),
+        interval=float(iv if iv is not None else rng.uniform(0.05, 0.5)),
+        curb_height=float(rng.uniform(0.01, 0.2)), curb_points=int(rng.choice([5, 5, 3, 9, 17])), beamZone=float(rng.uniform(10, 100)),
+        cylinder_deg_x=float(rng.uniform(90, 180)), cylinder_deg_z=float(rng.uniform(90, 180)),
+        curb_slope_deg=float(rng.uniform(10, 90)), kdev_param=float(rng.uniform(0.5, 5)), kdist_param=float(rng.uniform(0.4, 10)),
+        starbeam_filter=int(rng.integers(0, 2)), dmin_param=int(rng.integers(3, 30)), channels=ch,
+        **(FULL_ROI if seed % 2 else dict(min_x=-20.0, max_x=40.0, min_y=-15.0, max_y=15.0, min_z=-3.0, max_z=1.0)))
+    check(det, port, pts, prm)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_gpu_random_clouds_and_exact_registration(det, port, seed):
     pts = random_cloud(5000, seed)
