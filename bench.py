@@ -367,6 +367,10 @@ def main():
                 det.set_option(9, f[5])                 # marker search: cluster (0) or one CTA per scan (1)
             if len(f) > 6:
                 det.set_option(10, f[6])                # near-first pivot rank among 32 samples
+            if len(f) > 7:
+                det.set_option(11, f[7])                # ring detector on a side stream next to the star-shaped search
+            if len(f) > 8:
+                det.set_option(12, f[8])                # widest single-warp star sort network: 32 or 16 elements per lane
             for _ in range(3):
                 step_device()
             torch.cuda.synchronize()
@@ -422,6 +426,16 @@ def main():
         with_order = {"dev_ms": w0.elapsed_time(w1)}
         assert lib.urf_finish_batch_device(ctx, outs) == 0
         assert sum(o.n_road for o in outs) == n_road
+        det.set_option(1, 3)                 # three more steps on one stream with per-kernel events: what the order costs
+        for _ in range(3):
+            step_order()
+        assert lib.urf_finish_batch_device(ctx, outs) == 0
+        okt: dict[str, float] = {}
+        for slot in range(3):
+            for name, ms in det.kernel_times(slot):
+                okt[name] = okt.get(name, 0.0) + ms / 3
+        det.set_option(1, 0)
+        with_order["kernel_ms"] = {k: okt[k] for k in ("k_sort_rings", "k_scatter") if k in okt}
         del order
     # ---- timed region 1b: the same steps once more on ONE stream with a CUDA event in front of every kernel (per-kernel
     # ---- durations are only meaningful without inter-stream overlap); feeds the roofline block, not `value`
@@ -593,6 +607,7 @@ def main():
                             "d2h_bytes_per_step": B * n + B * C.sizeof(UrfResult), "entry": "urf_process_batch_xyz (opt-in; e2e above is the float4 / int32 drop-in call)"}
         if with_order is not None:           # labels + vertices + emission order (k_sort_rings inside the timed region)
             line["with_order"] = {"value": scans / (with_order["dev_ms"] / 1e3), "unit": "scans/s", "ms_per_step": with_order["dev_ms"] / K,
+                                  "kernel_ms_per_step": with_order.get("kernel_ms"),
                                   "e2e": {"value": scans / (with_order["e2e_ms"] / 1e3), "unit": "scans/s", "h2d_bytes_per_step": B * n * 16,
                                           "d2h_bytes_per_step": 2 * B * n * 4 + B * C.sizeof(UrfResult)}}
         if cpu_baseline is not None:

@@ -522,6 +522,9 @@ def test_gpu_packed_clouds_match_oracle(det, port, shape, step, offs):
         assert r.label is None and (r.n_road, r.n_curb) == (len(exp["road"]), len(exp["curb"]))
 
 
+SORT_WIDTH_DEFAULT = 16
+
+
 @pytest.mark.parametrize("variant", ["scan", "flat", "half_flat"])
 @pytest.mark.parametrize("shape", ["C2", "C4"])
 def test_gpu_near_first_star_sort(det, port, shape, variant):
@@ -541,11 +544,14 @@ def test_gpu_near_first_star_sort(det, port, shape, variant):
     if variant == "flat":
         assert int((np.asarray(o.star_mark) == 2).sum()) == 0
     res = {}
-    for mode in (1, 0):
+    for mode, width in ((1, 16), (0, 16), (1, 32), (0, 32)):   # option 12: widest single-warp network (wider sorts: k_star_sort_big)
         det.set_option(4, mode)
+        det.set_option(12, width)
         r = det.filtered(pts)
-        assert stage_diffs(o, GpuDebug(det, r, n), n) == [], f"star_prefix={mode}"
-        res[mode] = r
+        assert stage_diffs(o, GpuDebug(det, r, n), n) == [], f"star_prefix={mode} width={width}"
+        res[mode, width] = r
     det.set_option(4, 1)
-    np.testing.assert_array_equal(res[0].label, res[1].label)
-    np.testing.assert_array_equal(res[0].vert, res[1].vert)
+    det.set_option(12, SORT_WIDTH_DEFAULT)
+    for k in res:
+        np.testing.assert_array_equal(res[k].label, res[1, 32].label)
+        np.testing.assert_array_equal(res[k].vert, res[1, 32].vert)

@@ -1,4 +1,4 @@
-"""The near-first star sort (k_star_sort_warp / k_star_scan / k_star_scan_resume) is exact: on random sectors, splitting at
+"""The near-first star sort (k_star_sort_warp / k_star_scan / k_star_refine) is exact: on random sectors, splitting at
 the sampled pivot, walking the sorted near part and — without an edge there — resuming on the full order from the saved
 running mean / deviation marks the same point as sorting everything and walking from the start (the reference's way,
 star_shaped_search.cpp:109-150). Host check with the kernels' own arithmetic functions (tests/kat/star_prefix_check.cpp);

@@ -24,6 +24,13 @@ struct urf_ctx {
   static constexpr int kGroups = 16;               // sub-batches of a device-resident call run on separate streams: scans are
   cudaStream_t s_grp[kGroups] = {};               // independent, so their (short, partly latency-bound) kernels overlap
   cudaEvent_t ev_fork = nullptr, ev_join[kGroups] = {};
+  // inside one pipeline the star-shaped search (four kernels) and the ring detector (one kernel) are independent between
+  // k_scatter and k_tab1: with `inner_fork` the ring detector runs on a side stream of the pipeline's stream (tuning option 11)
+  cudaStream_t s_side[kGroups + 1] = {};
+  cudaEvent_t ev_sfork[kGroups + 1] = {}, ev_sjoin[kGroups + 1] = {};
+  bool inner_fork = true;              // measured at C2 x 128: 1.240 -> 1.233 ms on two streams, 1.282 -> 1.263 on one
+  int sort_variant = 16;               // widest single-warp network of k_star_sort_warp in elements per lane: 16 (64 registers, 32 warps/SM)
+                                       // or 32 (128 registers, 16 warps/SM; measured 2 % slower per step at C2 x 128) (tuning option 12)
   int groups = 2;                                 // measured at C2 x 128: 1 stream 1.37 ms, 2 streams 1.31, 4 streams 1.34, 8 streams 1.40
   // device-resident batches as many small sub-batches: `sub` scans per sub-batch (0 = one sub-batch per stream), dealt
   // round-robin to the `groups` streams, the whole fork/join captured once as a CUDA graph (bgraph) and replayed; with
@@ -154,24 +161,43 @@ int launch_pipeline(urf_ctx* ctx, const DevBuffers& buf, int B, int S, bool want
   K("k_register", k_register<<<B, 256, 0, st>>>(buf, dp, S));
   K("k_assign", k_assign<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
   K("k_scan_offsets", k_scan_offsets<<<B, 1024, 0, st>>>(buf, dp, S, T));   // + exact re-registration of refuted scans
-  K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));
+  K("k_scatter", k_scatter<<<gchunk, kWarpsPerBlock * 32, 0, st>>>(buf, dp, S, T));   // 64 registers, 4 CTAs/SM (48 / 40 registers spill: measured slower)
+  // the ring detector next to the star-shaped search: both only read what k_scatter left and add curb hits (idempotent
+  // marks, atomic min / max aggregates); k_tab1 is the first reader of the aggregates
+  const bool fork = ctx->inner_fork && dp.star && !ctx->profile;
+  cudaStream_t st_ring = st;
+  int side = urf_ctx::kGroups;
+  if (fork) {
+    for (int g = 0; g < urf_ctx::kGroups; g++) if (st == ctx->s_grp[g]) side = g;
+    st_ring = ctx->s_side[side];
+    CK(cudaEventRecord(ctx->ev_sfork[side], st));
+    CK(cudaStreamWaitEvent(st_ring, ctx->ev_sfork[side], 0));
+  }
+  const dim3 gtile((S + kTile4 - 1) / kTile4, B);
+  {
+    cudaStream_t st_main = st;
+    st = st_ring;
+    if (ctx->rd_variant == 4 && dp.curbPoints == 5)        // four positions per thread (default curb_points only)
+      K("k_ring_detect4", k_ring_detect4<4><<<gtile, 256, 0, st>>>(buf, dp, S));
+    else if (ctx->rd_variant == 45 && dp.curbPoints == 5) K("k_ring_detect4", k_ring_detect4<5><<<gtile, 256, 0, st>>>(buf, dp, S));
+    else if (ctx->rd_variant == 46 && dp.curbPoints == 5) K("k_ring_detect4", k_ring_detect4<6><<<gtile, 256, 0, st>>>(buf, dp, S));
+    else if (ctx->rd_variant == 6) K("k_ring_detect", k_ring_detect<6><<<gpts, 256, 0, st>>>(buf, dp, S));
+    else if (ctx->rd_variant == 5) K("k_ring_detect", k_ring_detect<5><<<gpts, 256, 0, st>>>(buf, dp, S));
+    else K("k_ring_detect", k_ring_detect<8><<<gpts, 256, 0, st>>>(buf, dp, S));   // 8 CTAs/SM (32 registers)
+    st = st_main;
+  }
+  if (fork) CK(cudaEventRecord(ctx->ev_sjoin[side], st_ring));
   if (dp.star) {
     const int gbig = std::max(4, std::min(kSectKeys, 2048 / B));
     const dim3 gscan((kSectKeys + kScanWarps * 32 - 1) / (kScanWarps * 32), B);
-    K("k_star_sort_warp", k_star_sort_warp<<<dim3(kSectKeys, B), 32, 0, st>>>(buf, dp, S));
+    if (ctx->sort_variant == 16) K("k_star_sort_warp", k_star_sort_warp<16><<<dim3(kSectKeys, B), 32, 0, st>>>(buf, dp, S));
+    else K("k_star_sort_warp", k_star_sort_warp<32><<<dim3(kSectKeys, B), 32, 0, st>>>(buf, dp, S));
     K("k_star_sort_big", k_star_sort_big<<<dim3(gbig, B), 256, kStarCtaSmem, st>>>(buf, dp, S));
     K("k_star_scan", k_star_scan<<<gscan, kScanWarps * 32, 0, st>>>(buf, dp, S));
     if (dp.star_prefix)            // sectors whose edge search ran off the near-first prefix: full sort, search resumed
       K("k_star_refine", k_star_refine<<<dim3(std::max(8, std::min(kSectKeys / 8, 8192 / B)), B), 256, kStarCtaSmem, st>>>(buf, dp, S));
   }
-  const dim3 gtile((S + kTile4 - 1) / kTile4, B);
-  if (ctx->rd_variant == 4 && dp.curbPoints == 5)        // four positions per thread (default curb_points only)
-    K("k_ring_detect4", k_ring_detect4<4><<<gtile, 256, 0, st>>>(buf, dp, S));
-  else if (ctx->rd_variant == 45 && dp.curbPoints == 5) K("k_ring_detect4", k_ring_detect4<5><<<gtile, 256, 0, st>>>(buf, dp, S));
-  else if (ctx->rd_variant == 46 && dp.curbPoints == 5) K("k_ring_detect4", k_ring_detect4<6><<<gtile, 256, 0, st>>>(buf, dp, S));
-  else if (ctx->rd_variant == 6) K("k_ring_detect", k_ring_detect<6><<<gpts, 256, 0, st>>>(buf, dp, S));
-  else if (ctx->rd_variant == 5) K("k_ring_detect", k_ring_detect<5><<<gpts, 256, 0, st>>>(buf, dp, S));
-  else K("k_ring_detect", k_ring_detect<8><<<gpts, 256, 0, st>>>(buf, dp, S));   // 8 CTAs/SM (32 registers)
+  if (fork) CK(cudaStreamWaitEvent(st, ctx->ev_sjoin[side], 0));
   K("k_tab1", k_tab1<<<dim3((dp.channels + 7) / 8, B), 256, 0, st>>>(buf, dp));
   K("k_reach", k_reach<<<dim3((2 * kDegBins + 7) / 8, B), 256, 0, st>>>(buf, dp));
   K("k_tab2", k_tab2<<<dim3((dp.channels + kTab2Rings - 1) / kTab2Rings, B), kTab2Rings * 64, 0, st>>>(buf, dp));
@@ -303,6 +329,11 @@ int urf_create(urf_ctx** out, int device, int max_points, int max_batch) {
     CKF(cudaEventCreateWithFlags(&ctx->ev_join[g], cudaEventDisableTiming));
   }
   CKF(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  for (int g = 0; g <= urf_ctx::kGroups; g++) {
+    CKF(cudaStreamCreateWithFlags(&ctx->s_side[g], cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&ctx->ev_sfork[g], cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&ctx->ev_sjoin[g], cudaEventDisableTiming));
+  }
   CKF(cudaEventCreate(&ctx->ev0));
   CKF(cudaEventCreate(&ctx->ev1));
   const size_t P = ctx->P;
@@ -386,6 +417,11 @@ void urf_destroy(urf_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_comp) cudaEventDestroy(e);
   for (int g = 0; g < urf_ctx::kGroups; g++) { if (ctx->s_grp[g]) cudaStreamDestroy(ctx->s_grp[g]); if (ctx->ev_join[g]) cudaEventDestroy(ctx->ev_join[g]); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int g = 0; g <= urf_ctx::kGroups; g++) {
+    if (ctx->s_side[g]) cudaStreamDestroy(ctx->s_side[g]);
+    if (ctx->ev_sfork[g]) cudaEventDestroy(ctx->ev_sfork[g]);
+    if (ctx->ev_sjoin[g]) cudaEventDestroy(ctx->ev_sjoin[g]);
+  }
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -421,7 +457,9 @@ int urf_get_params(const urf_ctx* ctx, urf_params* p) {
 // 2 = number of compute streams a device-resident batch is spread over (1..4); 3 = CUDA graph for small batches (0/1);
 // 4 = near-first star sort (0/1, default 1); 5 = scans per sub-batch of a device-resident batch (0 = batch / streams);
 // 6 = replay the fork/join of a device-resident batch as one CUDA graph (0/1); 7 = sub-batches of a stream share one
-// workspace slot (0/1)
+// workspace slot (0/1); 8 = ring detector variant; 9 = marker search variant; 10 = near-first pivot rank (3..28 of 32 samples);
+// 11 = ring detector on a side stream next to the star-shaped search (0/1, default 1); 12 = widest single-warp star sort
+// network in elements per lane (16 default, or 32)
 int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (!ctx) return URF_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
@@ -435,6 +473,8 @@ int urf_set_option(urf_ctx* ctx, int option, int value) {
   if (option == 7) { ctx->slot_reuse = value != 0; return URF_OK; }
   if (option == 8) { ctx->rd_variant = value; return URF_OK; }
   if (option == 9) { ctx->markers_variant = value; return URF_OK; }
+  if (option == 12) { ctx->sort_variant = value == 16 ? 16 : 32; return URF_OK; }
+  if (option == 11) { ctx->inner_fork = value != 0; return URF_OK; }
   if (option == 10) { ctx->dp.star_pivot = value < 3 ? 3 : (value > 28 ? 28 : value); return URF_OK; }
   if (option == 1) {                   // value = number of event slots (0 = off)
     CK(cudaStreamSynchronize(ctx->stream));               // events of the previous setting may still be pending

@@ -96,7 +96,7 @@ struct DevBuffers {
   float4* ssorted;       // [P]   sector buckets sorted by r
   float* az;             // [P]   azimuth per input point (ROI points only)
   float* d2;             // [P]   planar range per input point (ROI points only)
-  float* baz;            // [P]   azimuth per bucket position (written by k_scatter only when the emission order is wanted)
+  uint2* baz;            // [P]   (azimuth bits, input index) per bucket position (written by k_scatter only when the emission order is wanted)
   uint4* roadlist;       // [P]   road points, 32 slots per warp of input points: (bin | ring << 16, azimuth bits, range bits, input index)
   unsigned char* roadcnt; // [B][ceil(S / 32)] road points of each input warp (entries used in its 32 list slots)
   float* Tf;             // [B][channels][kTStride] forward threshold table (urf_logic.cuh build_T_row)

@@ -203,7 +203,7 @@ __device__ void publish_rings_cta(ScanTab& tab, ScanOut& out, unsigned short* lu
 
 // k_register: one CTA (256 threads) per scan. Fast path: the greedy registration is run over "candidates" only — the
 // first point of every non-empty fine elevation bin, in input order. That is a speculation (a registrant need not be
-// the first of its bin); k_assign verifies it against every point and k_register_exact repairs a failed speculation.
+// the first of its bin); k_assign verifies it against every point and k_scan_offsets repairs a failed speculation (exact greedy, in-kernel).
 __global__ void __launch_bounds__(256) k_register(DevBuffers buf, DevParams prm, int S) {
   const int b = blockIdx.x;
   const int n = buf.n[b];
@@ -547,7 +547,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
         if (t < total) {
           const unsigned dst = gb + dl[j] + (unsigned)t;
           buf.bpt[dst] = make_float4(p[j].x, p[j].y, p[j].z, __int_as_float(chunk * kChunk + li[j]));
-          if (prm.want_order) buf.baz[dst] = buf.az[g0 + li[j]];       // azimuth in bucket order: what k_sort_rings sorts by
+          // (azimuth, input index) in bucket order: all k_sort_rings reads
+          if (prm.want_order) buf.baz[dst] = make_uint2(fbits(buf.az[g0 + li[j]]), (unsigned)(chunk * kChunk + li[j]));
         }
       }
     }
@@ -584,9 +585,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_scatter(DevBuffers buf,
 // in the unsorted sector as payload). Strides below EPL are register-only compare-exchanges, strides below 32*EPL go
 // through warp shuffles, larger strides (multi-warp CTAs only) exchange through shared memory. One warp sorts up to 1024
 // points (k_star_sort_warp, one 32-thread CTA per sector so that all control flow around the shuffles is provably
-// uniform), eight warps up to 8192 (k_star_sort_cta, work list). Returns true when two points share a radius: their
-// order must follow the input index, which the network does not see — such a sector, like any sector beyond 8192
-// points, is redone by the 64-bit bitonic fallback k_star_sort.
+// uniform), eight warps up to 8192 (k_star_sort_big / k_star_refine, work lists). Returns true when two points share a
+// radius: their order is what the reference's std::sort leaves (urf_stdsort.cuh), which the network does not see — such a
+// sector, like any sector beyond 8192 points, is redone by slow_sort_sector.
 constexpr int kWarpCap = 1024, kCtaCap = 8192;
 
 // LIST (single-warp only): the n elements to sort are given as (radius bits, slot in src) pairs in s_xk / s_xe instead of
@@ -692,7 +693,7 @@ __device__ __forceinline__ bool sort_sector_warp(const float4* __restrict__ src,
 // smallest of 32 evenly spaced samples, and the (radius bits, slot) pairs below the pivot are appended to the shared
 // lists in any order. Returns their number.
 template <int EPL>
-__device__ __forceinline__ int select_near(const float4* __restrict__ src, int n, int lane, unsigned* s_pk, unsigned* s_pe, int pivot_rank) {
+__device__ __forceinline__ int select_near(const float4* __restrict__ src, int n, int lane, unsigned* s_pk, unsigned* s_pe, int pivot_rank, int cap = kWarpCap) {
   const unsigned mine = fbits(src[(int)(((unsigned)lane * (unsigned)n) >> 5)].x);
   unsigned key[EPL];
 #pragma unroll
@@ -710,7 +711,8 @@ __device__ __forceinline__ int select_near(const float4* __restrict__ src, int n
   for (int r = 0; r < EPL; r++) {
     const bool sel = key[r] < pivot;                   // padding keys are 0xffffffff: never selected
     const unsigned bs = __ballot_sync(0xffffffffu, sel);
-    if (sel) { const int pos = m + __popc(bs & lt); s_pk[pos] = key[r]; s_pe[pos] = (unsigned)(r * 32 + lane); }
+    const int pos = m + __popc(bs & lt);
+    if (sel && pos < cap) { s_pk[pos] = key[r]; s_pe[pos] = (unsigned)(r * 32 + lane); }   // beyond cap: counted only
     m += __popc(bs);
   }
   __syncwarp();
@@ -725,11 +727,16 @@ __device__ __forceinline__ int select_near(const float4* __restrict__ src, int n
 // 18th smallest of 32 evenly spaced samples): points below the pivot are compacted into shared memory and sorted (about
 // half the sector -> a network of half the width, ~40 % of the compare-exchanges); the rest is not written at all.
 // tab.sorted_len tells k_star_scan how far it may walk; a sector whose walk reaches the end of the sorted prefix
-// without an edge is put on tab.refine and redone in full (k_star_sort_refine + a second k_star_scan pass). Exact either
+// without an edge is put on tab.refine and redone in full (k_star_refine: full sort + star_resume_walk). Exact either
 // way: every point of the prefix is closer than every point behind it.
 constexpr int kPrefixMin = 128;
-__global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, DevParams prm, int S) {
-  __shared__ unsigned s_pk[kWarpCap], s_pe[kWarpCap];
+// MAXEPL = 32: every sector of up to kWarpCap points is sorted here (128 registers, 16 warps per SM). MAXEPL = 16: sorts
+// of more than 512 elements go to k_star_sort_big's list instead, which leaves this kernel with the networks of up to 16
+// elements per lane (fewer registers, more resident warps to hide the shuffle latency).
+template <int MAXEPL>
+__global__ void __launch_bounds__(32, MAXEPL >= 32 ? 16 : 32) k_star_sort_warp(DevBuffers buf, DevParams prm, int S) {
+  constexpr int kList = 32 * MAXEPL;                                    // longest list this kernel sorts itself
+  __shared__ unsigned s_pk[kList], s_pe[kList];
   const int b = blockIdx.y, s = blockIdx.x, lane = threadIdx.x;
   ScanTab& tab = buf.tab[b];
   const int base = tab.sect_start[s], n = tab.sect_start[s + 1] - base;
@@ -748,18 +755,26 @@ __global__ void __launch_bounds__(32) k_star_sort_warp(DevBuffers buf, DevParams
   bool tie;
   int m = 0;
   if (prm.star_prefix && n > kPrefixMin) {
-    if (n <= 256) m = select_near<8>(src, n, lane, s_pk, s_pe, prm.star_pivot);
-    else if (n <= 512) m = select_near<16>(src, n, lane, s_pk, s_pe, prm.star_pivot);
-    else m = select_near<32>(src, n, lane, s_pk, s_pe, prm.star_pivot);
+    if (n <= 256) m = select_near<8>(src, n, lane, s_pk, s_pe, prm.star_pivot, kList);
+    else if (n <= 512) m = select_near<16>(src, n, lane, s_pk, s_pe, prm.star_pivot, kList);
+    else m = select_near<32>(src, n, lane, s_pk, s_pe, prm.star_pivot, kList);
   }
-  if (m >= 32 && 4 * m <= 3 * n) {                                      // worth it: sort the near part only
+  const bool near = m >= 32 && 4 * m <= 3 * n;                          // worth it: sort the near part only
+  if (MAXEPL < 32 && (near ? m : n) > 32 * MAXEPL) {                    // a wide network: eight warps do it (k_star_sort_big)
+    if (lane == 0) tab.biglist[atomicAdd(&tab.nbig, 1)] = (unsigned short)s;
+    return;
+  }
+  if (near) {
     if (m <= 128) tie = bitonic_sector<4, 1, true>(src, dst, m, lane, s_pk, s_pe);
     else if (m <= 256) tie = bitonic_sector<8, 1, true>(src, dst, m, lane, s_pk, s_pe);
-    else if (m <= 512) tie = bitonic_sector<16, 1, true>(src, dst, m, lane, s_pk, s_pe);
-    else tie = bitonic_sector<32, 1, true>(src, dst, m, lane, s_pk, s_pe);
+    else if (MAXEPL >= 32 && m > 512) tie = bitonic_sector<32, 1, true>(src, dst, m, lane, s_pk, s_pe);
+    else tie = bitonic_sector<16, 1, true>(src, dst, m, lane, s_pk, s_pe);
     if (lane == 0) tab.sorted_len[s] = m;
   } else {
-    tie = sort_sector_warp(src, dst, n, lane);
+    if (n <= 128) tie = bitonic_sector<4, 1>(src, dst, n, lane, nullptr, nullptr);
+    else if (n <= 256) tie = bitonic_sector<8, 1>(src, dst, n, lane, nullptr, nullptr);
+    else if (MAXEPL >= 32 && n > 512) tie = bitonic_sector<32, 1>(src, dst, n, lane, nullptr, nullptr);
+    else tie = bitonic_sector<16, 1>(src, dst, n, lane, nullptr, nullptr);
   }
   if (__any_sync(0xffffffffu, tie) && lane == 0) tab.slowlist[atomicAdd(&tab.nslow, 1)] = (unsigned short)s;   // sets F_TIE_SECTOR there
 }
@@ -1063,7 +1078,7 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
     if (__all_sync(0xffffffffu, done)) break;
   }
   if (hit >= 0) curb_hit(buf, prm, b, scan_base(b, S), __float_as_int(all[base + hit].z), -1);   // star_shaped_search.cpp:146
-  else if (n < whole) {                               // ran off the sorted prefix: sort in full, k_star_scan_resume continues from here
+  else if (n < whole) {                               // ran off the sorted prefix: sort in full, k_star_refine continues from here
     const int w = atomicAdd(&tab.nrefine, 1);
     tab.refine[w] = (unsigned short)s;
     tab.resume[w][0] = st.avg; tab.resume[w][1] = st.dev; tab.resume[w][2] = st.nan; tab.resume[w][3] = __int_as_float(n);
@@ -1758,7 +1773,7 @@ __global__ void __launch_bounds__(384) k_verts(DevBuffers buf, int S) {
 // are close to uniform in azimuth) are ordered by one thread with an insertion sort on (azimuth bits, position). A ring
 // with a crowded bin (more than kBinCap points) or more than kRingFast points falls back to the CTA-wide bitonic sort on
 // 64-bit (azimuth bits, position) keys. Both paths produce the same total order.
-constexpr int kRingSmemKeys = 8192;                     // 64 KB of dynamic shared memory
+constexpr int kRingSmemKeys = 6144;                     // 48 KB of dynamic shared memory: four CTAs per SM
 constexpr int kRingFast = 4096, kRingBins = 4096, kBinCap = 48;
 constexpr int kSortThreads = 512;
 __global__ void __launch_bounds__(kSortThreads) k_sort_rings(DevBuffers buf, int S) {
@@ -1772,8 +1787,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_rings(DevBuffers buf, int
   const int tid = threadIdx.x;
   if (n <= kRingFast) {
     unsigned* s_az = reinterpret_cast<unsigned*>(s_rkeys);            // [kRingFast] azimuth bits by ring position
-    unsigned* s_idx = s_az + kRingFast;                               // [kRingFast] input index by ring position
-    unsigned* s_cnt = s_idx + kRingFast;                              // [kRingBins] bin counts, then exclusive starts
+    unsigned* s_cnt = s_az + kRingFast;                               // [kRingBins] bin counts, then exclusive starts
     unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_cnt + kRingBins);   // [kRingFast] arrival rank inside the bin
     unsigned short* s_slot = s_rank + kRingFast;                      // [kRingFast] ring position by sorted position
     __shared__ unsigned s_lo, s_hi, s_over, s_wsum[kSortThreads / 32];
@@ -1781,19 +1795,18 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_rings(DevBuffers buf, int
     for (int t = tid; t < kRingBins; t += kSortThreads) s_cnt[t] = 0u;
     __syncthreads();
     unsigned lo = 0xffffffffu, hi = 0u;
-    for (int t0 = tid; t0 < n; t0 += 4 * kSortThreads) {             // four coalesced (azimuth, input index) pairs in flight per thread
-      unsigned av[4], iv[4];
+    for (int t0 = tid; t0 < n; t0 += 4 * kSortThreads) {             // four coalesced loads in flight per thread
+      unsigned av[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int t = t0 + u * kSortThreads;
-        av[u] = t < n ? fbits(buf.baz[g0 + t]) : 0u;                 // azimuth in bucket order, written by k_scatter
-        iv[u] = t < n ? (unsigned)__float_as_int(buf.bpt[g0 + t].w) : 0u;
+        av[u] = t < n ? buf.baz[g0 + t].x : 0u;                      // (azimuth, input index) in bucket order, written by k_scatter
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int t = t0 + u * kSortThreads;
         if (t < n) {
-          s_az[t] = av[u]; s_idx[t] = iv[u];
+          s_az[t] = av[u];
           if (av[u] <= 0x7f800000u) { lo = min(lo, av[u]); hi = max(hi, av[u]); }   // azimuths are >= +0: their bits order them; NaN stays out
         }
       }
@@ -1851,7 +1864,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_rings(DevBuffers buf, int
       bool tie = false;
       for (int p = tid; p < n; p += kSortThreads) {
         const unsigned short slot = s_slot[p];
-        buf.order[g0 + p] = (int)s_idx[slot];
+        buf.order[g0 + p] = (int)buf.baz[g0 + slot].y;               // the ring's pairs are in L2 from the first pass
         if (p > 0 && s_az[s_slot[p - 1]] == s_az[slot]) tie = true;
       }
       if (tie) atomicOr(&out.flags, F_TIE_AZIMUTH);
@@ -1862,13 +1875,13 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_rings(DevBuffers buf, int
   const int npad = next_pow2(n < 2 ? 2 : n);
   unsigned long long* keys = npad <= kRingSmemKeys ? s_rkeys : buf.sortbuf + 2 * g0;
   for (int t = tid; t < npad; t += blockDim.x)
-    keys[t] = t < n ? (((unsigned long long)fbits(buf.baz[g0 + t]) << 32) | (unsigned)t) : ~0ull;
+    keys[t] = t < n ? (((unsigned long long)buf.baz[g0 + t].x << 32) | (unsigned)t) : ~0ull;
   __syncthreads();
   cta_bitonic(keys, npad);
   bool tie = false;
   for (int t = tid; t < n; t += blockDim.x) {
     const unsigned long long key = keys[t];
-    buf.order[g0 + t] = __float_as_int(buf.bpt[g0 + (unsigned)key].w);
+    buf.order[g0 + t] = (int)buf.baz[g0 + (unsigned)key].y;
     if (t > 0 && (unsigned)(keys[t - 1] >> 32) == (unsigned)(key >> 32)) tie = true;
   }
   if (tie) atomicOr(&out.flags, F_TIE_AZIMUTH);
