@@ -719,6 +719,30 @@ __device__ __forceinline__ int select_near(const float4* __restrict__ src, int n
   return m;
 }
 
+// The other side of a near-first split, for k_star_refine: the (radius bits, slot) pairs of the points whose radius lies
+// ABOVE `kmax` (the largest radius of the sorted prefix; prefix radii are all below the pivot, the rest at or above it),
+// appended to the shared lists in any order. Returns their number.
+template <int EPL>
+__device__ __forceinline__ int select_far(const float4* __restrict__ src, int n, int lane, unsigned* s_pk, unsigned* s_pe, unsigned kmax) {
+  unsigned key[EPL];
+#pragma unroll
+  for (int r = 0; r < EPL; r++) {
+    const int e = r * 32 + lane;
+    key[r] = e < n ? fbits(src[e].x) : 0u;             // padding: radius bits 0 are never above kmax
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  int m = 0;
+#pragma unroll
+  for (int r = 0; r < EPL; r++) {
+    const bool sel = key[r] > kmax;
+    const unsigned bs = __ballot_sync(0xffffffffu, sel);
+    if (sel) { const int pos = m + __popc(bs & lt); s_pk[pos] = key[r]; s_pe[pos] = (unsigned)(r * 32 + lane); }
+    m += __popc(bs);
+  }
+  __syncwarp();
+  return m;
+}
+
 // One 32-thread CTA per sector: sector index and size derive from blockIdx, so the compiler knows the control flow
 // around the shuffles is warp-uniform (no convergence barriers around every SHFL).
 //
@@ -969,11 +993,39 @@ __device__ void star_resume_walk(const DevBuffers& buf, const DevParams& prm, Sc
   if (hit >= 0) curb_hit(buf, prm, b, scan_base(b, S), __float_as_int(dst[hit].z), -1);     // star_shaped_search.cpp:146
 }
 
+// the same by one WARP (all 32 lanes call it): per tile of 32 points every lane computes what does not depend on the
+// recurrence for one point (slope, radius step, 1 / i: the IEEE divisions), then all lanes run the dependent part of the
+// 32 points in lock step on their own copy of the state (values handed round by shuffles), so control flow stays uniform.
+__device__ __forceinline__ void star_resume_walk_warp(const DevBuffers& buf, const DevParams& prm, ScanTab& tab, int b, int S, int w, int s,
+                                                      const float4* dst, int n, int lane) {
+  if (lane == 0) tab.sorted_len[s] = n;
+  StarState st;
+  st.avg = tab.resume[w][0]; st.dev = tab.resume[w][1]; st.nan = tab.resume[w][2];
+  const int n0 = __float_as_int(tab.resume[w][3]);     // >= 32: a prefix is never shorter
+  st.bx = 0.f; st.by = 0.f;                            // unused: slopes come from the points themselves
+  int hit = -1;
+  for (int t0 = n0; t0 < n && hit < 0; t0 += 32) {
+    const int e = min(t0 + lane, n - 1);
+    const float4 p = dst[e], pp = dst[e - 1];
+    float dx;
+    const float slp = star_slope(pp.x, pp.y, p.x, p.y, &dx);
+    const float dxk = __fmul_rn(dx, prm.kdist);
+    const float inv = star_inv(e);
+    const int cnt = min(32, n - t0);
+    for (int j = 0; j < cnt; j++) {
+      const float sj = __shfl_sync(0xffffffffu, slp, j), dj = __shfl_sync(0xffffffffu, dxk, j), ij = __shfl_sync(0xffffffffu, inv, j);
+      if (star_update(prm, st, t0 + j, sj, dj, ij)) { hit = t0 + j; break; }
+    }
+  }
+  if (hit >= 0 && lane == 0) curb_hit(buf, prm, b, scan_base(b, S), __float_as_int(dst[hit].z), -1);   // star_shaped_search.cpp:146
+}
+
 // k_star_refine: second pass for the sectors whose edge search ran off their sorted prefix (tab.refine, filled by
-// k_star_scan): the sector is sorted completely, then one thread resumes the walk at point n0 with the saved running
-// mean / deviation — the first n0 points of the full order are the prefix already walked (all of them are closer than the
-// rest). Sectors of up to kWarpCap points: one WARP per sector (register network, exact fallback on equal radii in the
-// warp's shared memory), the eight warps of a CTA working on eight sectors; larger sectors: the whole CTA, one at a time.
+// k_star_scan): the rest of the sector is sorted behind the prefix (single-warp path; the CTA path sorts the whole sector
+// again), then one thread resumes the walk at point n0 with the saved running mean / deviation — the first n0 points of
+// the full order are the prefix already walked (all of them are closer than the rest). Sectors of up to kWarpCap points:
+// one WARP per sector (register network, exact fallback on equal radii in the warp's shared memory), the eight warps of a
+// CTA working on eight sectors; larger sectors: the whole CTA, one at a time.
 __global__ void __launch_bounds__(256) k_star_refine(DevBuffers buf, DevParams prm, int S) {
   extern __shared__ unsigned s_dyn[];
   const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -987,10 +1039,25 @@ __global__ void __launch_bounds__(256) k_star_refine(DevBuffers buf, DevParams p
     if (n > kWarpCap) continue;                                            // second loop
     const float4* src = buf.spt + (size_t)b * S + base;
     float4* dst = buf.ssorted + (size_t)b * S + base;
-    const bool tie = sort_sector_warp(src, dst, n, lane);
-    if (__any_sync(0xffffffffu, tie)) slow_sort_sector_warp(buf, b, S, base, n, wkeys, lane);
+    // dst[0, n0) already holds the n0 closest points in order (the walked prefix): only the rest is sorted, behind it
+    const int n0 = __float_as_int(tab.resume[w][3]);
+    unsigned* s_pk = reinterpret_cast<unsigned*>(wkeys);
+    unsigned* s_pe = s_pk + kWarpCap;
+    const unsigned kmax = fbits(dst[n0 - 1].x);
+    int m;
+    if (n <= 256) m = select_far<8>(src, n, lane, s_pk, s_pe, kmax);
+    else if (n <= 512) m = select_far<16>(src, n, lane, s_pk, s_pe, kmax);
+    else m = select_far<32>(src, n, lane, s_pk, s_pe, kmax);
+    bool tie;
+    if (m != n - n0) tie = true;                                           // cannot happen (prefix = everything below the pivot); exact path if it does
+    else if (m <= 128) tie = bitonic_sector<4, 1, true>(src, dst + n0, m, lane, s_pk, s_pe);
+    else if (m <= 256) tie = bitonic_sector<8, 1, true>(src, dst + n0, m, lane, s_pk, s_pe);
+    else if (m <= 512) tie = bitonic_sector<16, 1, true>(src, dst + n0, m, lane, s_pk, s_pe);
+    else tie = bitonic_sector<32, 1, true>(src, dst + n0, m, lane, s_pk, s_pe);
     __syncwarp();
-    if (lane == 0) star_resume_walk(buf, prm, tab, b, S, w, s, dst, n);
+    if (__any_sync(0xffffffffu, tie)) slow_sort_sector_warp(buf, b, S, base, n, wkeys, lane);   // equal radii: whole sector, std::sort's order
+    __syncwarp();
+    star_resume_walk_warp(buf, prm, tab, b, S, w, s, dst, n, lane);
     __syncwarp();
   }
   __syncthreads();
@@ -1041,7 +1108,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) k_star_scan(DevBuffers buf, D
   for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
   for (int t0 = 0; t0 < nmax; t0 += 32) {
     // stage tile [t0, t0 + 32) of all 32 sector rows: 8 rows at a time so that the 16 loads of a group are in flight
-    // together (one L2 round trip per group instead of one per row)
+    // together (one L2 round trip per group instead of one per row). (Measured and dropped: 16 rows at a time with 8-byte
+    // loads and the predecessor taken from the left neighbour by shuffle — 0.102 instead of 0.068 ms at C2 x 128.)
     for (int q0 = 0; q0 < 32; q0 += 8) {
       float4 p[8], pp[8];
       bool ok[8];
