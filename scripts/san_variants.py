@@ -25,5 +25,20 @@ rs = det.filtered_batch_records([np.ascontiguousarray(pts[:, :3]), np.ascontiguo
 assert np.array_equal(rs[0].label, base.label)
 flat = make_scan("C1", 4).copy(); flat[:, 2] = -1.8                              # no edges: every sector refined
 det.filtered(flat)
+det.set_option(12, 32); r32 = det.filtered(pts); det.set_option(12, 16)          # single-warp star sort at 32 elements per lane
+det.set_option(11, 0); r1s = det.filtered(pts); det.set_option(11, 1)            # ring detector on the pipeline's own stream
+assert np.array_equal(r32.label, base.label) and np.array_equal(r1s.label, base.label)
+det.close()
+# OS1-64 sectors (364 points) are sorted near-first; in a flat / half-flat world the walks run off the prefix:
+# k_star_refine (remainder sort behind the prefix + warp-wide resumed walk) on every / every other sector
+det = api.Detector(max_points=131072, max_batch=1, params=prm)
+big = make_scan("C2", 5)
+ref = det.filtered(big)
+for variant in ("flat", "half"):
+    w = big.copy()
+    w[(w[:, 0] < 0) if variant == "half" else slice(None), 2] = -1.8
+    a = det.filtered(w)
+    det.set_option(4, 0); b = det.filtered(w); det.set_option(4, 1)             # whole-sector sorting: same result
+    assert np.array_equal(a.label, b.label) and np.array_equal(a.order, b.order), variant
 print("ok")
 det.close()

@@ -101,6 +101,9 @@ template <class T> int dalloc(urf_ctx* ctx, T** p, size_t count) {
   void* q = nullptr;
   CK(cudaMalloc(&q, count * sizeof(T) + 256));
   ctx->allocs.push_back(q);
+  // zero once: a few kernels issue loads ahead of the bound they are checked against (the values are dropped), and slots of
+  // a buffer that a call does not fill must read as something defined
+  CK(cudaMemset(q, 0, count * sizeof(T) + 256));
   *p = static_cast<T*>(q);
   return URF_OK;
 }
