@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-for tool in initcheck memcheck racecheck; do
-echo "== $tool variants"; timeout 1500 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 9 python scripts/san_variants.py > gpurun_out/san_${tool}_variants.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/san_${tool}_variants.log
-done
-echo "== initcheck smoke"; timeout 600 compute-sanitizer --tool initcheck --print-limit 20 --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/san_initcheck_smoke.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/san_initcheck_smoke.log
+nvidia-smi -L > gpurun_out/gpus.txt; nproc >> gpurun_out/gpus.txt
+echo "== mq, 8 devices"; timeout 240 python scripts/bench_mq.py --gpus 8 --scans 8000 --producers 1,8 --slots 96 --max-batch 64 > gpurun_out/mq_r02_v11q_8gpu.jsonl 2> gpurun_out/mq_r02_v11q8.err; echo "mq rc=$?"; cat gpurun_out/mq_r02_v11q_8gpu.jsonl; tail -3 gpurun_out/mq_r02_v11q8.err

@@ -1,8 +1,10 @@
 // tests/kat/star_prefix_check.cpp — host check of the near-first star sort's exactness argument (k_star_sort_warp /
-// k_star_scan / k_star_scan_resume in urf_kernels.cuh), with the same arithmetic functions the kernels call
+// k_star_scan / k_star_refine in urf_kernels.cuh), with the same arithmetic functions the kernels call
 // (urf_logic.cuh): for random sectors, "sort everything, walk until the first edge" (star_shaped_search.cpp:109-150) must
-// mark the same point as "split at the sampled pivot, sort and walk the near part, and if no edge was found sort
-// everything and resume the walk from the saved running mean / deviation".
+// mark the same point as "split at the sampled pivot, sort and walk the near part, and if no edge was found sort the
+// points ABOVE the prefix's largest radius behind the prefix (that must be exactly the rest, and give the full order) and
+// resume the walk there from the saved running mean / deviation, slopes and reciprocals computed per point up front"
+// (k_star_refine's select_far + star_resume_walk_warp).
 // usage: star_prefix_check <sectors> <seed>   -> prints "sectors=.. hits=.. prefix_hits=.. refined=.. mismatches=.."
 #include <algorithm>
 #include <cstdio>
@@ -71,10 +73,23 @@ int main(int argc, char** argv) {
       if (hit >= 0) { prefix_hits++; mark_nf = fbits(near[hit].z); }
       else {                                                  // resume on the full order from the saved state
         refined++;
+        const unsigned kmax = fbits(near[m - 1].x);           // select_far: everything above the prefix's largest radius
+        std::vector<float4> far;
+        for (const float4& p : pts) if (fbits(p.x) > kmax) far.push_back(p);
+        std::sort(far.begin(), far.end(), by_r);
+        std::vector<float4> all = near;
+        all.insert(all.end(), far.begin(), far.end());
+        bool same = (int)all.size() == n;
+        for (int i = 0; same && i < n; i++) same = fbits(all[i].x) == fbits(full[i].x) && fbits(all[i].z) == fbits(full[i].z);
+        if (!same) { if (bad < 5) fprintf(stderr, "sector %d: prefix + sorted rest is not the full order (n=%d m=%d rest=%zu)\n", t, n, m, far.size()); bad++; continue; }
         StarState rs;
-        rs.avg = st.avg; rs.dev = st.dev; rs.nan = st.nan; rs.bx = full[m - 1].x; rs.by = full[m - 1].y;
-        for (int i = m; i < n && hit < 0; i++) if (star_step(prm, rs, i, full[i].x, full[i].y)) hit = i;
-        if (hit >= 0) mark_nf = fbits(full[hit].z);
+        rs.avg = st.avg; rs.dev = st.dev; rs.nan = st.nan; rs.bx = 0.f; rs.by = 0.f;
+        for (int i = m; i < n && hit < 0; i++) {              // star_resume_walk_warp: per-point part first, then the recurrence
+          float dx;
+          const float slp = star_slope(all[i - 1].x, all[i - 1].y, all[i].x, all[i].y, &dx);
+          if (star_update(prm, rs, i, slp, URF_FMUL(dx, prm.kdist), star_inv(i))) hit = i;
+        }
+        if (hit >= 0) mark_nf = fbits(all[hit].z);
       }
     } else {
       if (hit_full >= 0) mark_nf = fbits(full[hit_full].z);   // the kernel sorts the whole sector in this case
