@@ -103,7 +103,10 @@ template <class T> int dalloc(urf_ctx* ctx, T** p, size_t count) {
   ctx->allocs.push_back(q);
   // zero once: a few kernels issue loads ahead of the bound they are checked against (the values are dropped), and slots of
   // a buffer that a call does not fill must read as something defined
-  CK(cudaMemset(q, 0, count * sizeof(T) + 256));
+  // (on the context's own stream and waited for: the legacy default stream is not ordered against the non-blocking streams
+  // that use the buffer next)
+  CK(cudaMemsetAsync(q, 0, count * sizeof(T) + 256, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   *p = static_cast<T*>(q);
   return URF_OK;
 }
