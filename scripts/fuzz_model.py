@@ -3,7 +3,8 @@
 urf_logic.cuh functions the kernels call, in the kernels' stage order) against the oracle port and, where it is built,
 against the unmodified reference (oracle/_ref), on seeded random parameter draws over the LidarFilters.cfg ranges and
 varied clouds (sensor layouts, flat worlds, quantised ranges = equal radii, random clouds). No GPU needed.
-usage: fuzz_model.py [first_seed] [count]   -> one line per mismatch, a summary line at the end"""
+usage: fuzz_model.py [first_seed] [count] [big]   -> one line per mismatch, a summary line at the end
+("big": whole OS1-64 / HDL-64E / OS2-128 scans instead of the small clouds, a few tenths of a second per case and side)"""
 import os
 import sys
 import time
@@ -20,6 +21,7 @@ from util import CpuModel, stage_diffs  # noqa: E402
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+big = len(sys.argv) > 3 and sys.argv[3] == "big"
 port, model = PortOracle(), CpuModel()
 ref = RefOracle() if RefOracle.available() else None
 bad = nref = nties = ncrash = 0
@@ -29,7 +31,14 @@ for seed in range(first, first + count):
     rng = np.random.default_rng(9000 + seed)
     kind = seed % 6
     ch, iv = 64, None
-    if kind == 0:
+    if big:
+        shape = ("C2", "C2", "C3", "C4")[seed % 4]
+        pts = make_scan(shape, 100 + seed, order="ring" if seed % 4 == 1 else "column")
+        if shape == "C4":
+            ch, iv = 128, 0.07
+        if seed % 5 == 0:
+            pts[:, 2] = np.where(pts[:, 0] < rng.uniform(-30, 30), -1.8, pts[:, 2])        # partly flat world
+    elif kind == 0:
         pts = make_scan("C1", 100 + seed, order="column")
     elif kind == 1:
         pts = make_scan("C1", 100 + seed, order="ring")
@@ -64,7 +73,7 @@ for seed in range(first, first + count):
         print(f"seed {seed} kind {kind}: model vs port: {d[:3]}", flush=True)
     nties += bool(m.flags & 2)
     road += int((np.asarray(m.label) == 1).sum()); curb += int((np.asarray(m.label) == 2).sum())
-    if ref is not None and n <= 40000:
+    if ref is not None and (n <= 40000 or big):
         # the reference runs in a forked child: it has undefined behaviour of its own on some inputs and
         # a crash there must not end the sweep
         tmp = f"/tmp/fuzz_ref_{os.getpid()}.npy"
